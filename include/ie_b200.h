@@ -1,0 +1,162 @@
+/* ie_b200.h — C ABI of the B200-native batched `{key}` interpolation engine.
+ *
+ * Drop-in boundary for the resolver of tillfalko/interpolation-engine.  The reference has no
+ * FFI of its own; the boundary is the Rust module API of rust-project/src/interp.rs plus the
+ * two wildcard helpers of rust-project/src/runtime.rs.  Every entry point below names the
+ * reference item (file:line) it replaces.  All functions return an ie_status_t (0 = IE_OK) and
+ * never throw or abort across the boundary; ie_last_error() returns the message for the calling
+ * thread.  There is no CPU fallback: every resolve/escape/glob call runs CUDA kernels on the
+ * engine's device and fails with IE_E_CUDA when no device is usable.
+ *
+ * Data layout conventions
+ *   string arenas   : `bytes` + `offs[n+1]` (uint64, offs[0]=0, offs[n]=total bytes), no separators
+ *   packed inserts  : key arena + value arena + tags[n]; a value is the value_to_string()
+ *                     rendering (interp.rs:314-322) of the serde_json::Value, the tag its type
+ *   results         : out arena + out_offs[n] + out_lens[n] + status[n] + aux[n]
+ */
+#ifndef IE_B200_H
+#define IE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- call status --------------------------------------------------------------------------- */
+typedef enum {
+    IE_OK = 0,
+    IE_E_INVALID = 1,  /* bad argument */
+    IE_E_CUDA = 2,     /* CUDA runtime error (no device, launch failure, ...) */
+    IE_E_NOMEM = 3,    /* host or device allocation failed */
+    IE_E_OVERFLOW = 4, /* caller-provided output arena too small; see ie_batch_info.out_bytes */
+} ie_status_t;
+
+/* ---- per-template result status (low 8 bits of status[i]; bits 8..15 = value tag) ----------- */
+enum {
+    IE_RES_STRING = 0,      /* Ok(Value::String(out bytes))                          interp.rs:88 */
+    IE_RES_TYPED = 1,       /* simple path: Ok(inserts[key].clone()); out bytes = value_to_string,
+                               aux = entry index of the insert (n, n+1 = "HH:MM", "HH:MM:SS")  :45-52 */
+    IE_RES_UNEVEN = 2,      /* Err("Interpolation error: uneven number of '{' and '}' in: " + out) :58 */
+    IE_RES_UNSUPPORTED = 3, /* Err("Trying to interpolate '" + out + "' of unsupported type")     :76 */
+    IE_RES_EMPTY_KEY = 4,   /* Err("Tried to interpolate empty string ''")                        :105 */
+    IE_RES_ARG_MISSING = 5, /* Err("Argument interpolation key '" + out + "' is used but not provided") :113 */
+    IE_RES_NOT_FOUND = 6,   /* Err("Could not find variable '" + out + "'")                       :136 */
+    IE_RES_PANIC = 7,       /* the reference panics: unwrap() on "no '}' after the last '{'"      :63-66 */
+    IE_RES_LIMIT = 8,       /* expansion bound hit (the reference would loop forever)              */
+};
+#define IE_RES_CODE(s) ((int)((s) & 0xFF))
+#define IE_RES_TAG(s) ((int)(((s) >> 8) & 0xFF))
+#define IE_AUX_NONE 0xFFFFFFFFu
+
+/* value type tags (serde_json::Value variants) */
+enum { IE_TAG_NULL = 0, IE_TAG_BOOL = 1, IE_TAG_NUMBER = 2, IE_TAG_STRING = 3, IE_TAG_ARRAY = 4, IE_TAG_OBJECT = 5 };
+
+typedef struct ie_engine ie_engine; /* one per (process, device): stream, staging, scratch      */
+typedef struct ie_table ie_table;   /* device-resident packed `inserts` map (immutable snapshot) */
+
+/* Expansion bounds.  The reference has none (a self-referential insert loops forever,
+ * interp.rs:54); exceeding one yields IE_RES_LIMIT for that template only. */
+typedef struct {
+    uint32_t max_expansions;   /* lookups per template on the general path (default 4096)       */
+    uint32_t max_result_bytes; /* bytes of intermediate/final text per template on the general
+                                  path (default 64 KiB)                                         */
+} ie_limits;
+
+typedef struct {
+    uint64_t n;           /* templates processed */
+    uint64_t out_bytes;   /* bytes used in the out arena (needed size when IE_E_OVERFLOW)        */
+    uint64_t n_general;   /* templates that took the general (slow) path                         */
+    float kernel_ms;      /* device time of the resolve kernels (CUDA events), host API only     */
+} ie_batch_info;
+
+const char* ie_last_error(void);
+int ie_device_count(void);
+
+/* ---- engine ------------------------------------------------------------------------------- */
+ie_status_t ie_engine_create(int device, ie_engine** out);
+void ie_engine_destroy(ie_engine* e);
+void* ie_engine_stream(ie_engine* e); /* cudaStream_t the engine launches on */
+ie_status_t ie_engine_sync(ie_engine* e);
+
+/* ---- inserts snapshot -> device table ------------------------------------------------------
+ * Replaces the `&Map<String, Value>` argument of interp.rs:31/:91/:179 (callers pass a snapshot
+ * clone, runtime.rs:700).  Later duplicates of a key win (Map::insert semantics, interp.rs:139).
+ * `hhmm` / `hhmmss` (may be NULL) are the renderings of the special keys "HH:MM" / "HH:MM:SS"
+ * (interp.rs:96-104); when given they shadow inserts of the same name, as in the reference. */
+ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const uint64_t* key_offs,
+                          const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags,
+                          const char* hhmm, const char* hhmmss, ie_table** out);
+void ie_table_free(ie_table* t);
+uint64_t ie_table_device_bytes(const ie_table* t);
+
+/* ---- interpolate_inserts, batched (interp.rs:31-89) -----------------------------------------
+ * Host-buffer form: copies the template arena to the device, resolves all n templates against
+ * `t`, copies results back.  Result pointers stay owned by the engine and are valid until the
+ * next call on the same engine. */
+typedef struct {
+    const uint8_t* out;       /* result bytes */
+    const uint64_t* out_offs; /* [n] start of result i in `out` */
+    const uint32_t* out_lens; /* [n] length of result i */
+    const int32_t* status;    /* [n] IE_RES_* | tag << 8 */
+    const uint32_t* aux;      /* [n] insert entry index for IE_RES_TYPED */
+    ie_batch_info info;
+} ie_result;
+ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs,
+                             uint64_t n, const ie_limits* limits, ie_result* res);
+
+/* Device-buffer form (inputs and outputs already resident in HBM; asynchronous on `stream`,
+ * which may be NULL for the engine's own stream).  `d_info` is a device ie_batch_info. */
+ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs,
+                                    uint64_t n, const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity,
+                                    uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                    ie_batch_info* d_info, void* stream);
+
+/* ---- get_interpdata for a batch of literal keys (interp.rs:91-137; map probe only: the caller
+ * handles "" and the ARG<digits> error text).  tag_out[i] = IE_TAG_* or -1 on a miss;
+ * entry_out[i] = insert index (n, n+1 = the clock keys) or IE_AUX_NONE. */
+ie_status_t ie_lookup_batch(ie_engine* e, const ie_table* t, const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
+                            int32_t* tag_out, uint32_t* entry_out);
+
+/* ---- recursive_unescape / recursive_escape on strings, batched (interp.rs:147-177; also the
+ * inline replaces of `print` / `write`, runtime.rs:1053-1055, 1272) --------------------------
+ * mode 0: unescape ("\{" -> "{", then "\}" -> "}");  mode 1: escape ("{" -> "\{", "}" -> "\}"). */
+ie_status_t ie_escape_batch(ie_engine* e, int mode, const uint8_t* in, const uint64_t* in_offs, uint64_t n,
+                            const uint8_t** out, const uint64_t** out_offs);
+ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n,
+                                   uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs, void* stream);
+
+/* ---- wildcard_match over a key set: `delete` / `delete_except` (runtime.rs:1198-1239, 1633-1647)
+ * mask bit k (uint32 words, LSB first) = key k is deleted, i.e. (any pattern matches) != invert.
+ * Survivors keep their (sorted) input order.  n_pat <= IE_MAX_PATTERNS. */
+#define IE_MAX_PATTERNS 64
+ie_status_t ie_glob_sweep(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
+                          const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, int invert,
+                          uint32_t* mask, uint64_t* n_deleted);
+ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n,
+                                 const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, int invert,
+                                 uint32_t* d_mask, uint64_t* d_n_deleted, void* stream);
+
+/* ---- device memory helpers for hosts without a CUDA binding (tests, bench, FFI callers) ----- */
+ie_status_t ie_device_alloc(ie_engine* e, uint64_t bytes, void** d_ptr);
+void ie_device_free(ie_engine* e, void* d_ptr);
+ie_status_t ie_copy_to_device(ie_engine* e, void* d_dst, const void* h_src, uint64_t bytes);
+ie_status_t ie_copy_to_host(ie_engine* e, void* h_dst, const void* d_src, uint64_t bytes);
+ie_status_t ie_host_alloc(uint64_t bytes, void** h_ptr); /* page-locked host memory for the host-buffer calls */
+void ie_host_free(void* h_ptr);
+
+/* ---- JSON-level mirror of the interp.rs public functions (host logic above the batch ABI) ----
+ * args: {"fn": name, "inserts": {...}, "content"|"key"|"value"|"pattern"|"text"|"wildcards": ...}
+ * with fn one of interpolate_inserts (:31), get_simple_insertkey (:11), get_interpdata (:91),
+ * recursive_interpolate (:179), recursive_escape (:163), recursive_unescape (:147),
+ * extract_insert_keys (:248), value_to_string (:314), wildcard_match (runtime.rs:1633),
+ * delete / delete_except (runtime.rs:1198 / 1219).  Returns malloc'ed UTF-8 JSON
+ * {"ok": value} | {"err": {"code", "message", "payload"}}; free with ie_free. */
+ie_status_t ie_call_json(ie_engine* e, const char* args_json, size_t len, char** out_json, size_t* out_len);
+void ie_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IE_B200_H */

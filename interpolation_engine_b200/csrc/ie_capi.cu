@@ -1,0 +1,441 @@
+// C ABI of the engine (include/ie_b200.h): engine / table lifetime, host- and device-buffer
+// batch entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ie_host.hpp"
+#include "ie_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+ie_status_t fail(ie_status_t st, const std::string& msg) { g_err = msg; return st; }
+ie_status_t cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorMemoryAllocation ? IE_E_NOMEM : IE_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, cudaStream_t stream) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaStreamSynchronize(stream); cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr uint32_t kDefaultExpansions = 4096;
+constexpr uint32_t kDefaultResultBytes = 64u << 10;
+
+}  // namespace
+
+struct ie_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // workspace
+    DevBuf ws_zero, ws_list, ws_scratch;
+    uint32_t tcap = 0;
+    // host-API staging
+    DevBuf d_in, d_in_offs, d_out, d_out_offs, d_out_lens, d_status, d_aux, d_info, d_mask, d_misc;
+    PinBuf h_out, h_out_offs, h_out_lens, h_status, h_aux, h_info;
+};
+
+struct ie_table {
+    ie_engine* e = nullptr;
+    void* d_base = nullptr;
+    size_t bytes = 0;
+    IeTableView view{};
+};
+
+namespace {
+
+// Lays the per-batch workspace out for n items; returns the kernel-side view.
+ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws) {
+    const uint64_t tiles = (n + IE_TILE - 1) / IE_TILE;
+    const size_t zero_bytes = 64 + (size_t)(tiles + 1) * sizeof(uint64_t);
+    CU(e->ws_zero.ensure(zero_bytes, e->stream));
+    ws->zero_base = (uint8_t*)e->ws_zero.p;
+    ws->zero_bytes = zero_bytes;
+    ws->tile_counter = (uint32_t*)e->ws_zero.p;
+    ws->general_count = ws->tile_counter + 1;
+    ws->overflow = ws->tile_counter + 2;
+    ws->tile_state = (uint64_t*)((uint8_t*)e->ws_zero.p + 64);
+    ws->general_list = nullptr;
+    ws->scratch = nullptr;
+    ws->general_workers = IE_GENERAL_WORKERS;
+    if (need_general) {
+        CU(e->ws_list.ensure((size_t)std::max<uint64_t>(n, 1) * sizeof(uint32_t), e->stream));
+        ws->general_list = (uint32_t*)e->ws_list.p;
+        if (tcap > e->tcap || !e->ws_scratch.p) {
+            CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH), e->stream));
+            e->tcap = tcap;
+        }
+        ws->scratch = (uint8_t*)e->ws_scratch.p;
+    }
+    return IE_OK;
+}
+
+void resolve_limits(const ie_limits* in, uint32_t* max_exp, uint32_t* tcap) {
+    *max_exp = (in && in->max_expansions) ? in->max_expansions : kDefaultExpansions;
+    uint32_t rb = (in && in->max_result_bytes) ? in->max_result_bytes : kDefaultResultBytes;
+    *tcap = (rb + 15u) & ~15u;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ie_last_error(void) { return g_err.c_str(); }
+
+int ie_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+ie_status_t ie_engine_create(int device, ie_engine** out) {
+    if (!out) return fail(IE_E_INVALID, "ie_engine_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(IE_E_CUDA, "ie_engine_create: no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(IE_E_INVALID, "ie_engine_create: device index out of range");
+    CU(cudaSetDevice(device));
+    ie_engine* e = new (std::nothrow) ie_engine();
+    if (!e) return fail(IE_E_NOMEM, "ie_engine_create: out of host memory");
+    e->device = device;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
+    if (err != cudaSuccess) { ie_engine_destroy(e); return cuda_fail(err, "ie_engine_create"); }
+    *out = e;
+    return IE_OK;
+}
+
+void ie_engine_destroy(ie_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (DevBuf* b : {&e->ws_zero, &e->ws_list, &e->ws_scratch, &e->d_in, &e->d_in_offs, &e->d_out, &e->d_out_offs, &e->d_out_lens,
+                      &e->d_status, &e->d_aux, &e->d_info, &e->d_mask, &e->d_misc})
+        b->release();
+    for (PinBuf* b : {&e->h_out, &e->h_out_offs, &e->h_out_lens, &e->h_status, &e->h_aux, &e->h_info}) b->release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+void* ie_engine_stream(ie_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+ie_status_t ie_engine_sync(ie_engine* e) {
+    if (!e) return fail(IE_E_INVALID, "ie_engine_sync: engine is NULL");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return IE_OK;
+}
+
+ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals,
+                          const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out) {
+    if (!e || !out || (n && (!keys || !key_offs || !vals || !val_offs || !tags)))
+        return fail(IE_E_INVALID, "ie_table_pack: NULL argument");
+    *out = nullptr;
+    std::vector<uint8_t> image;
+    uint32_t capacity = 0;
+    std::string why;
+    if (!ie_host::build_table_image(n, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, &image, &capacity, &why))
+        return fail(IE_E_INVALID, "ie_table_pack: " + why);
+    CU(cudaSetDevice(e->device));
+    ie_table* t = new (std::nothrow) ie_table();
+    if (!t) return fail(IE_E_NOMEM, "ie_table_pack: out of host memory");
+    t->e = e;
+    t->bytes = image.size();
+    cudaError_t err = cudaMalloc(&t->d_base, image.size());
+    if (err == cudaSuccess) err = cudaMemcpyAsync(t->d_base, image.data(), image.size(), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) { if (t->d_base) cudaFree(t->d_base); delete t; return cuda_fail(err, "ie_table_pack"); }
+    t->view.base = (const uint8_t*)t->d_base;
+    t->view.mask = capacity - 1;
+    t->view.n_entries = (uint32_t)n;
+    *out = t;
+    return IE_OK;
+}
+
+void ie_table_free(ie_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->e->device);
+    cudaStreamSynchronize(t->e->stream);
+    if (t->d_base) cudaFree(t->d_base);
+    delete t;
+}
+
+uint64_t ie_table_device_bytes(const ie_table* t) { return t ? t->bytes : 0; }
+
+ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
+                                    const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
+                                    uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, void* stream) {
+    if (!e || !t || !d_info || (n && (!d_tmpl_offs || !d_out_offs || !d_out_lens || !d_status || !d_aux)))
+        return fail(IE_E_INVALID, "ie_resolve_batch_device: NULL argument");
+    if (n >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "ie_resolve_batch_device: at most 2^32-2 templates per batch");
+    CU(cudaSetDevice(e->device));
+    uint32_t max_exp, tcap;
+    resolve_limits(limits, &max_exp, &tcap);
+    IeWorkspace ws;
+    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws);
+    if (st != IE_OK) return st;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+                         max_exp, tcap, s));
+    return IE_OK;
+}
+
+ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs, uint64_t n,
+                             const ie_limits* limits, ie_result* res) {
+    if (!e || !t || !res || (n && (!tmpl_offs))) return fail(IE_E_INVALID, "ie_resolve_batch: NULL argument");
+    std::memset(res, 0, sizeof *res);
+    CU(cudaSetDevice(e->device));
+    const uint64_t in_bytes = n ? tmpl_offs[n] : 0;
+    if (in_bytes && !tmpl) return fail(IE_E_INVALID, "ie_resolve_batch: NULL template arena");
+    cudaStream_t s = e->stream;
+    CU(e->d_in.ensure(in_bytes + 16, s));
+    CU(e->d_in_offs.ensure((n + 1) * 8, s));
+    CU(e->d_out_offs.ensure(n * 8 + 8, s));
+    CU(e->d_out_lens.ensure(n * 4 + 4, s));
+    CU(e->d_status.ensure(n * 4 + 4, s));
+    CU(e->d_aux.ensure(n * 4 + 4, s));
+    CU(e->d_info.ensure(sizeof(ie_batch_info), s));
+    CU(e->h_info.ensure(sizeof(ie_batch_info)));
+    CU(e->d_out.ensure(std::max<uint64_t>(in_bytes * 2 + (1u << 16), 1u << 20), s));
+    if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, tmpl, in_bytes, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, tmpl_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
+    float kernel_ms = 0.f;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CU(cudaEventRecord(e->ev0, s));
+        ie_status_t st = ie_resolve_batch_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
+                                                 (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p,
+                                                 (uint32_t*)e->d_out_lens.p, (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p,
+                                                 (ie_batch_info*)e->d_info.p, s);
+        if (st != IE_OK) return st;
+        CU(cudaEventRecord(e->ev1, s));
+        CU(cudaMemcpyAsync(hinfo, e->d_info.p, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        CU(cudaEventElapsedTime(&kernel_ms, e->ev0, e->ev1));
+        if (hinfo->out_bytes <= e->d_out.cap) break;
+        if (attempt == 2) return fail(IE_E_OVERFLOW, "ie_resolve_batch: output arena overflow after regrow");
+        CU(e->d_out.ensure(hinfo->out_bytes, s));  // out arena was too small: regrow to the exact need and rerun
+    }
+    const uint64_t ob = hinfo->out_bytes;
+    CU(e->h_out.ensure(ob + 1));
+    CU(e->h_out_offs.ensure(n * 8 + 8));
+    CU(e->h_out_lens.ensure(n * 4 + 4));
+    CU(e->h_status.ensure(n * 4 + 4));
+    CU(e->h_aux.ensure(n * 4 + 4));
+    if (ob) CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, ob, cudaMemcpyDeviceToHost, s));
+    if (n) {
+        CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, n * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_out_lens.p, e->d_out_lens.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_aux.p, e->d_aux.p, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    res->out = (const uint8_t*)e->h_out.p;
+    res->out_offs = (const uint64_t*)e->h_out_offs.p;
+    res->out_lens = (const uint32_t*)e->h_out_lens.p;
+    res->status = (const int32_t*)e->h_status.p;
+    res->aux = (const uint32_t*)e->h_aux.p;
+    res->info = *hinfo;
+    res->info.n = n;
+    res->info.kernel_ms = kernel_ms;
+    return IE_OK;
+}
+
+ie_status_t ie_lookup_batch(ie_engine* e, const ie_table* t, const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
+                            int32_t* tag_out, uint32_t* entry_out) {
+    if (!e || !t || (n && (!key_offs || !tag_out || !entry_out))) return fail(IE_E_INVALID, "ie_lookup_batch: NULL argument");
+    if (!n) return IE_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint64_t bytes = key_offs[n];
+    CU(e->d_in.ensure(bytes + 16, s));
+    CU(e->d_in_offs.ensure((n + 1) * 8, s));
+    CU(e->d_status.ensure(n * 4, s));
+    CU(e->d_aux.ensure(n * 4, s));
+    if (bytes) CU(cudaMemcpyAsync(e->d_in.p, keys, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->d_in_offs.p, key_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CU(ie_launch_lookup(t->view, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (int32_t*)e->d_status.p,
+                        (uint32_t*)e->d_aux.p, s));
+    CU(cudaMemcpyAsync(tag_out, e->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(entry_out, e->d_aux.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return IE_OK;
+}
+
+ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint8_t* d_out,
+                                   uint64_t out_capacity, uint64_t* d_out_offs, void* stream) {
+    if (!e || !d_out_offs || (n && !d_in_offs) || (mode != 0 && mode != 1)) return fail(IE_E_INVALID, "ie_escape_batch_device: bad argument");
+    CU(cudaSetDevice(e->device));
+    IeWorkspace ws;
+    ie_status_t st = prepare_workspace(e, n, 0, false, &ws);
+    if (st != IE_OK) return st;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CU(ie_launch_escape(mode, d_in, d_in_offs, n, d_out, out_capacity, d_out_offs, ws, s));
+    return IE_OK;
+}
+
+ie_status_t ie_escape_batch(ie_engine* e, int mode, const uint8_t* in, const uint64_t* in_offs, uint64_t n, const uint8_t** out,
+                            const uint64_t** out_offs) {
+    if (!e || !out || !out_offs || (n && !in_offs)) return fail(IE_E_INVALID, "ie_escape_batch: NULL argument");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint64_t in_bytes = n ? in_offs[n] : 0;
+    const uint64_t cap = mode == 1 ? in_bytes * 2 : in_bytes;  // escape at most doubles, unescape never grows
+    CU(e->d_in.ensure(in_bytes + 16, s));
+    CU(e->d_in_offs.ensure((n + 1) * 8, s));
+    CU(e->d_out.ensure(cap + 16, s));
+    CU(e->d_out_offs.ensure((n + 1) * 8, s));
+    CU(e->h_out.ensure(cap + 1));
+    CU(e->h_out_offs.ensure((n + 1) * 8));
+    if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, in_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    ie_status_t st = ie_escape_batch_device(e, mode, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (uint8_t*)e->d_out.p,
+                                            cap, (uint64_t*)e->d_out_offs.p, s);
+    if (st != IE_OK) return st;
+    CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint64_t ob = ((const uint64_t*)e->h_out_offs.p)[n];
+    if (ob) CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, ob, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *out = (const uint8_t*)e->h_out.p;
+    *out_offs = (const uint64_t*)e->h_out_offs.p;
+    return IE_OK;
+}
+
+static ie_status_t pack_patterns(const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, int invert, IeGlobPatterns* gp) {
+    if (n_pat > IE_MAX_PATTERNS) return fail(IE_E_INVALID, "ie_glob_sweep: more than IE_MAX_PATTERNS patterns");
+    if (n_pat && (!pat_offs || pat_offs[n_pat] > sizeof gp->bytes)) return fail(IE_E_INVALID, "ie_glob_sweep: patterns exceed 3584 bytes");
+    std::memset(gp, 0, sizeof *gp);
+    gp->n_pat = n_pat;
+    gp->invert = invert ? 1u : 0u;
+    for (uint32_t i = 0; i <= n_pat && n_pat; ++i) gp->off[i] = (uint16_t)pat_offs[i];
+    if (n_pat && pat_offs[n_pat]) std::memcpy(gp->bytes, pats, pat_offs[n_pat]);
+    return IE_OK;
+}
+
+ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const uint8_t* pats,
+                                 const uint64_t* pat_offs, uint32_t n_pat, int invert, uint32_t* d_mask, uint64_t* d_n_deleted,
+                                 void* stream) {
+    if (!e || !d_n_deleted || (n && (!d_key_offs || !d_mask))) return fail(IE_E_INVALID, "ie_glob_sweep_device: NULL argument");
+    IeGlobPatterns gp;
+    ie_status_t st = pack_patterns(pats, pat_offs, n_pat, invert, &gp);
+    if (st != IE_OK) return st;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CU(ie_launch_glob(d_keys, d_key_offs, n, gp, d_mask, d_n_deleted, s));
+    return IE_OK;
+}
+
+ie_status_t ie_glob_sweep(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n, const uint8_t* pats,
+                          const uint64_t* pat_offs, uint32_t n_pat, int invert, uint32_t* mask, uint64_t* n_deleted) {
+    if (!e || (n && (!key_offs || !mask))) return fail(IE_E_INVALID, "ie_glob_sweep: NULL argument");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint64_t bytes = n ? key_offs[n] : 0;
+    const uint64_t words = (n + 31) / 32;
+    CU(e->d_in.ensure(bytes + 16, s));
+    CU(e->d_in_offs.ensure((n + 1) * 8, s));
+    CU(e->d_mask.ensure(words * 4 + 4, s));
+    CU(e->d_misc.ensure(64, s));
+    if (bytes) CU(cudaMemcpyAsync(e->d_in.p, keys, bytes, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, key_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    ie_status_t st = ie_glob_sweep_device(e, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, pats, pat_offs, n_pat, invert,
+                                          (uint32_t*)e->d_mask.p, (uint64_t*)e->d_misc.p, s);
+    if (st != IE_OK) return st;
+    uint64_t nd = 0;
+    if (words) CU(cudaMemcpyAsync(mask, e->d_mask.p, words * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&nd, e->d_misc.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (n_deleted) *n_deleted = nd;
+    return IE_OK;
+}
+
+ie_status_t ie_device_alloc(ie_engine* e, uint64_t bytes, void** d_ptr) {
+    if (!e || !d_ptr) return fail(IE_E_INVALID, "ie_device_alloc: NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return IE_OK;
+}
+void ie_device_free(ie_engine* e, void* d_ptr) {
+    if (!e || !d_ptr) return;
+    cudaSetDevice(e->device);
+    cudaFree(d_ptr);
+}
+ie_status_t ie_copy_to_device(ie_engine* e, void* d_dst, const void* h_src, uint64_t bytes) {
+    if (!e) return fail(IE_E_INVALID, "ie_copy_to_device: engine is NULL");
+    CU(cudaSetDevice(e->device));
+    if (bytes) CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return IE_OK;
+}
+ie_status_t ie_copy_to_host(ie_engine* e, void* h_dst, const void* d_src, uint64_t bytes) {
+    if (!e) return fail(IE_E_INVALID, "ie_copy_to_host: engine is NULL");
+    CU(cudaSetDevice(e->device));
+    if (bytes) CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return IE_OK;
+}
+ie_status_t ie_host_alloc(uint64_t bytes, void** h_ptr) {
+    if (!h_ptr) return fail(IE_E_INVALID, "ie_host_alloc: NULL argument");
+    CU(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return IE_OK;
+}
+void ie_host_free(void* h_ptr) { if (h_ptr) cudaFreeHost(h_ptr); }
+
+void ie_free(void* p) { std::free(p); }
+
+ie_status_t ie_call_json(ie_engine* e, const char* args_json, size_t len, char** out_json, size_t* out_len) {
+    if (!e || !args_json || !out_json) return fail(IE_E_INVALID, "ie_call_json: NULL argument");
+    std::string out;
+    std::string why;
+    ie_status_t st = ie_host::call_json(e, std::string(args_json, len), &out, &why);
+    if (st != IE_OK) return fail(st, why);
+    char* p = (char*)std::malloc(out.size() + 1);
+    if (!p) return fail(IE_E_NOMEM, "ie_call_json: out of host memory");
+    std::memcpy(p, out.data(), out.size());
+    p[out.size()] = 0;
+    *out_json = p;
+    if (out_len) *out_len = out.size();
+    return IE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,673 @@
+// Host mirror of the reference's resolver API over the CUDA batch ABI.
+//
+// Function names, argument meaning and error texts follow rust-project/src/interp.rs; the tree
+// walkers gather every string they would resolve into ONE batch per call (the shape of
+// runtime.rs:700-701, which resolves a whole task object against a snapshot of the inserts), run it
+// through ie_resolve_batch / ie_escape_batch / ie_glob_sweep on the GPU and rebuild the tree.
+// Nothing here interprets "{...}" text on the CPU; the host only does what the reference's leaves
+// do outside the resolver proper: JSON (de)serialisation, value_to_string, the wall clock
+// (interp.rs:96-104), the --inserts-dir file reads (interp.rs:122-134) and message formatting.
+#include "ie_host.hpp"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+
+namespace ie_host {
+
+namespace {
+
+// ---- JSON value ------------------------------------------------------------------------------
+struct JVal;
+using JArr = std::vector<JVal>;
+using JObj = std::map<std::string, JVal>;  // serde_json::Map without preserve_order = BTreeMap
+
+struct JVal {
+    enum T { Null, Bool, Num, Str, Arr, Obj } t = Null;
+    bool b = false;
+    std::string s;  // Str: text; Num: canonical rendering (serde_json::Number::to_string)
+    std::shared_ptr<JArr> a;
+    std::shared_ptr<JObj> o;
+    static JVal str(std::string x) { JVal v; v.t = Str; v.s = std::move(x); return v; }
+    static JVal num(std::string x) { JVal v; v.t = Num; v.s = std::move(x); return v; }
+    static JVal boolean(bool x) { JVal v; v.t = Bool; v.b = x; return v; }
+    static JVal arr(JArr x = {}) { JVal v; v.t = Arr; v.a = std::make_shared<JArr>(std::move(x)); return v; }
+    static JVal obj(JObj x = {}) { JVal v; v.t = Obj; v.o = std::make_shared<JObj>(std::move(x)); return v; }
+};
+
+// serde_json renders f64 through ryu's "pretty" layout (not vendored: PARITY UNPINNED)
+std::string render_f64(double x) {
+    if (!std::isfinite(x)) return "null";
+    if (x == 0.0) return std::signbit(x) ? "-0.0" : "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(x), std::chars_format::scientific);
+    std::string sci(buf, r.ptr);
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t i = 0; i < epos; ++i) if (sci[i] != '.') digits.push_back(sci[i]);
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int e10 = std::atoi(sci.c_str() + epos + 1);
+    const int len = (int)digits.size();
+    const int kk = e10 + 1;  // decimal point position relative to the digit string
+    const int k = kk - len;
+    std::string out = x < 0 ? "-" : "";
+    if (0 <= k && kk <= 16) out += digits + std::string((size_t)k, '0') + ".0";
+    else if (0 < kk && kk <= 16) out += digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+    else if (-5 < kk && kk <= 0) out += "0." + std::string((size_t)(-kk), '0') + digits;
+    else if (len == 1) out += digits + "e" + std::to_string(kk - 1);
+    else out += digits.substr(0, 1) + "." + digits.substr(1) + "e" + std::to_string(kk - 1);
+    return out;
+}
+
+struct Reader {
+    const char* p; const char* e;
+    [[noreturn]] void bad(const char* m) { throw std::runtime_error(std::string("JSON parse error: ") + m); }
+    void skip() {
+        for (;;) {
+            while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+            if (e - p >= 2 && p[0] == '/' && p[1] == '/') { while (p < e && *p != '\n') ++p; }
+            else if (e - p >= 2 && p[0] == '/' && p[1] == '*') { p += 2; while (e - p >= 2 && !(p[0] == '*' && p[1] == '/')) ++p; p = (e - p >= 2) ? p + 2 : e; }
+            else return;
+        }
+    }
+    static void utf8(uint32_t c, std::string& o) {
+        if (c < 0x80) o += (char)c;
+        else if (c < 0x800) { o += (char)(0xC0 | (c >> 6)); o += (char)(0x80 | (c & 63)); }
+        else if (c < 0x10000) { o += (char)(0xE0 | (c >> 12)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+        else { o += (char)(0xF0 | (c >> 18)); o += (char)(0x80 | ((c >> 12) & 63)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+    }
+    uint32_t hex4() {
+        if (e - p < 4) bad("\\u escape");
+        uint32_t v = 0;
+        for (int i = 0; i < 4; ++i, ++p) {
+            const char c = *p;
+            v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : (bad("hex digit"), 0));
+        }
+        return v;
+    }
+    std::string string_lit() {
+        const char q = *p++;
+        std::string o;
+        for (;;) {
+            if (p >= e) bad("unterminated string");
+            const char c = *p++;
+            if (c == q) return o;
+            if (c != '\\') { o += c; continue; }
+            if (p >= e) bad("escape");
+            const char n = *p++;
+            switch (n) {
+                case 'n': o += '\n'; break; case 't': o += '\t'; break; case 'r': o += '\r'; break;
+                case 'b': o += '\b'; break; case 'f': o += '\f'; break; case '0': o += '\0'; break;
+                case '\n': break;
+                case 'u': {
+                    uint32_t c1 = hex4();
+                    if (c1 >= 0xD800 && c1 < 0xDC00 && e - p >= 6 && p[0] == '\\' && p[1] == 'u') { p += 2; c1 = 0x10000 + ((c1 - 0xD800) << 10) + (hex4() - 0xDC00); }
+                    utf8(c1, o);
+                    break;
+                }
+                default: o += n;
+            }
+        }
+    }
+    JVal number_lit() {
+        const char* b = p;
+        if (p < e && (*p == '-' || *p == '+')) ++p;
+        bool flt = false;
+        while (p < e && (std::isdigit((unsigned char)*p) || *p == '.' || *p == 'e' || *p == 'E' || *p == '-' || *p == '+')) {
+            flt |= (*p == '.' || *p == 'e' || *p == 'E');
+            ++p;
+        }
+        std::string tok(b, p);
+        if (!tok.empty() && tok[0] == '+') tok.erase(0, 1);
+        if (tok.empty() || tok == "-") bad("number");
+        if (!flt) {
+            // canonical integer text: strip leading zeros; fall back to f64 beyond u64/i64 like serde_json
+            const bool neg = tok[0] == '-';
+            size_t i = neg ? 1 : 0;
+            while (i + 1 < tok.size() && tok[i] == '0') ++i;
+            const std::string mag = tok.substr(i);
+            const std::string lim = neg ? "9223372036854775808" : "18446744073709551615";
+            if (mag.size() < lim.size() || (mag.size() == lim.size() && mag <= lim)) return JVal::num((neg && mag != "0" ? "-" : "") + mag);
+        }
+        return JVal::num(render_f64(std::strtod(tok.c_str(), nullptr)));
+    }
+    JVal value() {
+        skip();
+        if (p >= e) bad("unexpected end");
+        const char c = *p;
+        if (c == '{') {
+            ++p;
+            JObj o;
+            for (;;) {
+                skip();
+                if (p < e && *p == '}') { ++p; break; }
+                std::string k;
+                if (p < e && (*p == '"' || *p == '\'')) k = string_lit();
+                else { const char* b = p; while (p < e && (std::isalnum((unsigned char)*p) || *p == '_' || *p == '$')) ++p; if (p == b) bad("object key"); k.assign(b, p); }
+                skip();
+                if (p >= e || *p != ':') bad("':' expected");
+                ++p;
+                o[k] = value();
+                skip();
+                if (p < e && *p == ',') { ++p; continue; }
+                if (p < e && *p == '}') { ++p; break; }
+                bad("',' or '}' expected");
+            }
+            return JVal::obj(std::move(o));
+        }
+        if (c == '[') {
+            ++p;
+            JArr a;
+            for (;;) {
+                skip();
+                if (p < e && *p == ']') { ++p; break; }
+                a.push_back(value());
+                skip();
+                if (p < e && *p == ',') { ++p; continue; }
+                if (p < e && *p == ']') { ++p; break; }
+                bad("',' or ']' expected");
+            }
+            return JVal::arr(std::move(a));
+        }
+        if (c == '"' || c == '\'') return JVal::str(string_lit());
+        if (e - p >= 4 && !std::memcmp(p, "true", 4)) { p += 4; return JVal::boolean(true); }
+        if (e - p >= 5 && !std::memcmp(p, "false", 5)) { p += 5; return JVal::boolean(false); }
+        if (e - p >= 4 && !std::memcmp(p, "null", 4)) { p += 4; return JVal(); }
+        return number_lit();
+    }
+};
+
+JVal parse(const std::string& text) {
+    Reader r{text.data(), text.data() + text.size()};
+    JVal v = r.value();
+    r.skip();
+    if (r.p != r.e) r.bad("trailing characters");
+    return v;
+}
+
+void quote(const std::string& s, std::string& o) {
+    static const char* hexd = "0123456789abcdef";
+    o += '"';
+    for (unsigned char c : s) {
+        if (c == '"') o += "\\\"";
+        else if (c == '\\') o += "\\\\";
+        else if (c == '\n') o += "\\n";
+        else if (c == '\r') o += "\\r";
+        else if (c == '\t') o += "\\t";
+        else if (c == '\b') o += "\\b";
+        else if (c == '\f') o += "\\f";
+        else if (c < 0x20) { o += "\\u00"; o += hexd[c >> 4]; o += hexd[c & 15]; }
+        else o += (char)c;
+    }
+    o += '"';
+}
+void dump(const JVal& v, std::string& o) {  // serde_json::to_string (compact)
+    switch (v.t) {
+        case JVal::Null: o += "null"; break;
+        case JVal::Bool: o += v.b ? "true" : "false"; break;
+        case JVal::Num: o += v.s; break;
+        case JVal::Str: quote(v.s, o); break;
+        case JVal::Arr: { o += '['; bool f = true; for (auto& x : *v.a) { if (!f) o += ','; f = false; dump(x, o); } o += ']'; break; }
+        case JVal::Obj: { o += '{'; bool f = true; for (auto& kv : *v.o) { if (!f) o += ','; f = false; quote(kv.first, o); o += ':'; dump(kv.second, o); } o += '}'; break; }
+    }
+}
+
+// interp.rs:314-322
+void render(const JVal& v, std::string& o) {
+    switch (v.t) {
+        case JVal::Str: case JVal::Num: o += v.s; break;
+        case JVal::Bool: o += v.b ? "true" : "false"; break;
+        case JVal::Arr: for (auto& x : *v.a) render(x, o); break;
+        default: dump(v, o);
+    }
+}
+std::string value_to_string(const JVal& v) { std::string o; render(v, o); return o; }
+uint8_t tag_of(const JVal& v) {
+    switch (v.t) {
+        case JVal::Null: return IE_TAG_NULL; case JVal::Bool: return IE_TAG_BOOL; case JVal::Num: return IE_TAG_NUMBER;
+        case JVal::Str: return IE_TAG_STRING; case JVal::Arr: return IE_TAG_ARRAY; default: return IE_TAG_OBJECT;
+    }
+}
+
+struct Arena {
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> offs{0};
+    void push(const std::string& s) { bytes.insert(bytes.end(), s.begin(), s.end()); offs.push_back(bytes.size()); }
+    uint64_t n() const { return offs.size() - 1; }
+    const uint8_t* data() const { static const uint8_t z = 0; return bytes.empty() ? &z : bytes.data(); }
+};
+
+struct ApiError {
+    int code;
+    std::string message, payload;
+};
+struct CallFailure {  // engine-level failure (CUDA etc.): aborts the call
+    ie_status_t st;
+    std::string why;
+};
+void check(ie_status_t st) { if (st != IE_OK) throw CallFailure{st, ie_last_error()}; }
+
+std::string message_for(int code, const std::string& payload) {
+    switch (code) {
+        case IE_RES_UNEVEN: return "Interpolation error: uneven number of '{' and '}' in: " + payload;  // interp.rs:58-60
+        case IE_RES_UNSUPPORTED: return "Trying to interpolate '" + payload + "' of unsupported type";    // :76-78
+        case IE_RES_EMPTY_KEY: return "Tried to interpolate empty string ''";                             // :105
+        case IE_RES_ARG_MISSING: return "Argument interpolation key '" + payload + "' is used but not provided";  // :113-115
+        case IE_RES_NOT_FOUND: return "Could not find variable '" + payload + "'";                        // :136
+        case IE_RES_PANIC: return "panic: called `Option::unwrap()` on a `None` value";                   // :66
+        case IE_RES_LIMIT: return "expansion limit exceeded";
+        default: return "error";
+    }
+}
+
+// interp.rs:11-29 (pure text predicate used by the analyzer and the tree walker; not a resolve step)
+bool simple_insertkey(const std::string& c, std::string* inner) {
+    const size_t n = c.size();
+    if (n < 2 || c.front() != '{' || c.back() != '}') return false;
+    long depth = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (c[i] == '}') --depth;
+        if ((depth == 0) != (i == 0 || i == n - 1)) return false;
+        if (c[i] == '{') ++depth;
+    }
+    if (inner) *inner = c.substr(1, n - 2);
+    return true;
+}
+
+bool is_arg_key(const std::string& k) {
+    if (k.rfind("ARG", 0) != 0) return false;
+    for (size_t i = 3; i < k.size(); ++i) if (k[i] < '0' || k[i] > '9') return false;
+    return true;
+}
+
+// ---- a resolver session: one inserts snapshot packed on the device ------------------------------
+struct Outcome {
+    int code = 0;          // IE_RES_*
+    std::string bytes;     // result text / error payload
+    JVal typed;            // IE_RES_TYPED: the insert's value
+    std::string io_error;  // non-empty: inserts-dir read/parse failure for this template's key
+};
+
+struct Session {
+    ie_engine* e;
+    JObj inserts;  // snapshot (plus inserts-dir hits, which the reference reads on a map miss)
+    std::string hhmm, hhmmss, inserts_dir;
+    bool has_dir = false;
+    ie_table* table = nullptr;
+    std::vector<const JVal*> entry_vals;
+    std::map<std::string, std::string> dir_errors;
+    std::map<std::string, bool> dir_probed;
+
+    Session(ie_engine* eng, const JVal& args) : e(eng) {
+        if (args.t == JVal::Obj) {
+            auto it = args.o->find("inserts");
+            if (it != args.o->end() && it->second.t == JVal::Obj) inserts = *it->second.o;
+            auto d = args.o->find("inserts_dir");
+            if (d != args.o->end() && d->second.t == JVal::Str) { inserts_dir = d->second.s; has_dir = true; }
+            auto c = args.o->find("clock");
+            if (c != args.o->end() && c->second.t == JVal::Obj) {
+                auto a = c->second.o->find("hhmm"); if (a != c->second.o->end()) hhmm = a->second.s;
+                auto b = c->second.o->find("hhmmss"); if (b != c->second.o->end()) hhmmss = b->second.s;
+            }
+        }
+        if (hhmm.empty() || hhmmss.empty()) {  // chrono::Local::now() (interp.rs:98,102), snapshotted once per call
+            std::time_t now = std::time(nullptr);
+            std::tm tmv{};
+            localtime_r(&now, &tmv);
+            char buf[16];
+            if (hhmm.empty()) { std::strftime(buf, sizeof buf, "%H:%M", &tmv); hhmm = buf; }
+            if (hhmmss.empty()) { std::strftime(buf, sizeof buf, "%H:%M:%S", &tmv); hhmmss = buf; }
+        }
+    }
+    ~Session() { if (table) ie_table_free(table); }
+
+    void pack() {
+        if (table) { ie_table_free(table); table = nullptr; }
+        Arena keys, vals;
+        std::vector<uint8_t> tags;
+        entry_vals.clear();
+        for (auto& kv : inserts) {
+            keys.push(kv.first);
+            vals.push(value_to_string(kv.second));
+            tags.push_back(tag_of(kv.second));
+            entry_vals.push_back(&kv.second);
+        }
+        static const uint8_t z = 0;
+        check(ie_table_pack(e, keys.n(), keys.data(), keys.offs.data(), vals.data(), vals.offs.data(), tags.empty() ? &z : tags.data(),
+                            hhmm.c_str(), hhmmss.c_str(), &table));
+    }
+
+    JVal entry_value(uint32_t entry) const {
+        if (entry < entry_vals.size()) return *entry_vals[entry];
+        return JVal::str(entry == entry_vals.size() ? hhmm : hhmmss);
+    }
+
+    // interp.rs:122-134: `<dir>/<key>.json5` (parsed, recursive_escape'd) then `<dir>/<key>` (trimmed, escaped)
+    bool probe_dir(const std::string& key);
+
+    std::vector<Outcome> resolve(const std::vector<std::string>& templates) {
+        std::vector<Outcome> out(templates.size());
+        if (templates.empty()) return out;
+        if (!table) pack();
+        Arena t;
+        for (auto& s : templates) t.push(s);
+        for (int round = 0; round < 64; ++round) {
+            ie_result r;
+            check(ie_resolve_batch(e, table, t.data(), t.offs.data(), t.n(), nullptr, &r));
+            bool grew = false;
+            for (size_t i = 0; i < templates.size(); ++i) {
+                Outcome& oc = out[i];
+                oc.code = IE_RES_CODE(r.status[i]);
+                oc.bytes.assign((const char*)r.out + r.out_offs[i], r.out_lens[i]);
+                if (oc.code == IE_RES_TYPED) oc.typed = entry_value(r.aux[i]);
+                if (oc.code == IE_RES_NOT_FOUND && has_dir) {
+                    if (probe_dir(oc.bytes)) grew = true;
+                    auto de = dir_errors.find(oc.bytes);
+                    if (de != dir_errors.end()) oc.io_error = de->second;
+                }
+            }
+            if (!grew) break;
+            pack();
+        }
+        return out;
+    }
+};
+
+JVal escape_tree(ie_engine* e, int mode, const JVal& v);
+
+bool Session::probe_dir(const std::string& key) {
+    if (dir_probed.count(key) || is_arg_key(key)) return false;  // ARG keys never fall back (interp.rs:109-116)
+    dir_probed[key] = true;
+    if (key.find('\0') != std::string::npos) return false;
+    struct stat st;
+    const std::string j5 = inserts_dir + "/" + key + ".json5", plain = inserts_dir + "/" + key;
+    auto slurp = [](const std::string& path, std::string* o) { std::ifstream f(path, std::ios::binary); if (!f) return false; std::stringstream ss; ss << f.rdbuf(); *o = ss.str(); return true; };
+    std::string raw;
+    if (::stat(j5.c_str(), &st) == 0) {
+        if (!slurp(j5, &raw)) { dir_errors[key] = "cannot read " + j5; return false; }
+        try { inserts[key] = escape_tree(e, 1, parse(raw)); } catch (const std::exception& ex) { dir_errors[key] = ex.what(); return false; }
+        return true;
+    }
+    if (::stat(plain.c_str(), &st) == 0) {
+        if (!slurp(plain, &raw)) { dir_errors[key] = "cannot read " + plain; return false; }
+        size_t a = 0, b = raw.size();
+        auto ws = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); };
+        while (a < b && ws((unsigned char)raw[a])) ++a;
+        while (b > a && ws((unsigned char)raw[b - 1])) --b;
+        inserts[key] = escape_tree(e, 1, JVal::str(raw.substr(a, b - a)));
+        return true;
+    }
+    return false;
+}
+
+JVal outcome_value(const Outcome& oc) {
+    if (oc.code == IE_RES_STRING) return JVal::str(oc.bytes);
+    if (oc.code == IE_RES_TYPED) return oc.typed;
+    if (!oc.io_error.empty()) throw ApiError{9, oc.io_error, oc.bytes};
+    throw ApiError{oc.code, message_for(oc.code, oc.bytes), oc.bytes};
+}
+
+// ---- recursive_interpolate (interp.rs:179-246) as gather -> one GPU batch -> rebuild -------------
+struct Gather {
+    std::vector<std::string> templates;
+    std::vector<std::string> lookups;  // simple keys of for/serial/parallel_* `tasks` (get_interpdata, :217, :224)
+};
+bool is_control_cmd(const std::string& c) { return c == "for" || c == "serial" || c == "parallel_wait" || c == "parallel_race"; }
+const std::string* cmd_of(const JVal& v) {
+    auto it = v.o->find("cmd");
+    return (it != v.o->end() && it->second.t == JVal::Str) ? &it->second.s : nullptr;
+}
+void gather(const JVal& v, Gather& g) {
+    if (v.t == JVal::Str) { g.templates.push_back(v.s); return; }
+    if (v.t == JVal::Arr) { for (auto& x : *v.a) gather(x, g); return; }
+    if (v.t != JVal::Obj) return;
+    if (const std::string* cmd = cmd_of(v)) {
+        if (*cmd == "goto_map" || *cmd == "replace_map") return;  // :210-212
+        if (is_control_cmd(*cmd)) {                              // :213-233
+            auto t = v.o->find("tasks");
+            if (t != v.o->end()) {
+                std::string k;
+                if (t->second.t == JVal::Str) { if (simple_insertkey(t->second.s, &k)) g.lookups.push_back(k); }
+                else if (t->second.t == JVal::Arr) for (auto& x : *t->second.a) if (x.t == JVal::Str && simple_insertkey(x.s, &k)) g.lookups.push_back(k);
+            }
+            return;
+        }
+    }
+    for (auto& kv : *v.o) { g.templates.push_back(kv.first); gather(kv.second, g); }
+}
+struct Rebuild {
+    const std::vector<Outcome>& res;
+    const std::vector<JVal>& looked;
+    size_t ti = 0, li = 0;
+    JVal string_result(const std::string& original) {
+        const Outcome& oc = res[ti++];
+        if (oc.code == IE_RES_STRING) return JVal::str(oc.bytes);
+        if (oc.code == IE_RES_TYPED) return oc.typed;
+        if (oc.code == IE_RES_PANIC || oc.code == IE_RES_LIMIT) throw ApiError{oc.code, message_for(oc.code, oc.bytes), oc.bytes};
+        return JVal::str(original);  // interp.rs:192, :201 — resolver errors are swallowed
+    }
+    JVal walk(const JVal& v) {
+        if (v.t == JVal::Str) return string_result(v.s);
+        if (v.t == JVal::Arr) { JArr a; for (auto& x : *v.a) a.push_back(walk(x)); return JVal::arr(std::move(a)); }
+        if (v.t != JVal::Obj) return v;
+        if (const std::string* cmd = cmd_of(v)) {
+            if (*cmd == "goto_map" || *cmd == "replace_map") return v;
+            if (is_control_cmd(*cmd)) {
+                JObj o = *v.o;
+                auto t = o.find("tasks");
+                if (t != o.end()) {
+                    if (t->second.t == JVal::Str) { if (simple_insertkey(t->second.s, nullptr)) t->second = looked[li++]; }
+                    else if (t->second.t == JVal::Arr) {
+                        JArr a = *t->second.a;
+                        for (auto& x : a) if (x.t == JVal::Str && simple_insertkey(x.s, nullptr)) x = looked[li++];
+                        t->second = JVal::arr(std::move(a));
+                    }
+                }
+                return JVal::obj(std::move(o));
+            }
+        }
+        JObj out;
+        for (auto& kv : *v.o) {
+            JVal nk = string_result(kv.first);
+            JVal nv = walk(kv.second);
+            out[value_to_string(nk)] = std::move(nv);  // later duplicates win (:241)
+        }
+        return JVal::obj(std::move(out));
+    }
+};
+
+// get_interpdata (interp.rs:91-137) for literal keys through the device table
+std::vector<JVal> lookup_keys(Session& s, const std::vector<std::string>& keys) {
+    std::vector<JVal> out(keys.size());
+    if (keys.empty()) return out;
+    if (!s.table) s.pack();
+    for (int round = 0; round < 64; ++round) {
+        Arena a;
+        for (auto& k : keys) a.push(k);
+        std::vector<int32_t> tag(keys.size());
+        std::vector<uint32_t> entry(keys.size());
+        check(ie_lookup_batch(s.e, s.table, a.data(), a.offs.data(), a.n(), tag.data(), entry.data()));
+        bool grew = false;
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const std::string& k = keys[i];
+            if (tag[i] >= 0) { out[i] = s.entry_value(entry[i]); continue; }
+            if (k.empty()) throw ApiError{IE_RES_EMPTY_KEY, message_for(IE_RES_EMPTY_KEY, ""), ""};
+            if (is_arg_key(k)) throw ApiError{IE_RES_ARG_MISSING, message_for(IE_RES_ARG_MISSING, k), k};
+            if (s.has_dir && s.probe_dir(k)) { grew = true; continue; }
+            auto de = s.dir_errors.find(k);
+            if (de != s.dir_errors.end()) throw ApiError{9, de->second, k};
+            throw ApiError{IE_RES_NOT_FOUND, message_for(IE_RES_NOT_FOUND, k), k};
+        }
+        if (!grew) break;
+        s.pack();
+    }
+    return out;
+}
+
+// recursive_escape / recursive_unescape (interp.rs:147-177): strings and object keys, one GPU batch
+void gather_strings(const JVal& v, std::vector<std::string>& g) {
+    if (v.t == JVal::Str) g.push_back(v.s);
+    else if (v.t == JVal::Arr) for (auto& x : *v.a) gather_strings(x, g);
+    else if (v.t == JVal::Obj) for (auto& kv : *v.o) { g.push_back(kv.first); gather_strings(kv.second, g); }
+}
+JVal rebuild_strings(const JVal& v, const std::vector<std::string>& r, size_t& i) {
+    if (v.t == JVal::Str) return JVal::str(r[i++]);
+    if (v.t == JVal::Arr) { JArr a; for (auto& x : *v.a) a.push_back(rebuild_strings(x, r, i)); return JVal::arr(std::move(a)); }
+    if (v.t == JVal::Obj) { JObj o; for (auto& kv : *v.o) { std::string k = r[i++]; o[k] = rebuild_strings(kv.second, r, i); } return JVal::obj(std::move(o)); }
+    return v;
+}
+JVal escape_tree(ie_engine* e, int mode, const JVal& v) {
+    std::vector<std::string> g;
+    gather_strings(v, g);
+    if (g.empty()) return v;
+    Arena a;
+    for (auto& s : g) a.push(s);
+    const uint8_t* ob; const uint64_t* oo;
+    check(ie_escape_batch(e, mode, a.data(), a.offs.data(), a.n(), &ob, &oo));
+    std::vector<std::string> r(g.size());
+    for (size_t i = 0; i < g.size(); ++i) r[i].assign((const char*)ob + oo[i], oo[i + 1] - oo[i]);
+    size_t i = 0;
+    return rebuild_strings(v, r, i);
+}
+
+// interp.rs:273-312 — analyzer helper (analyzer.rs:783); a scan, not a resolve: no table involved
+void extract_from_str(const std::string& s, JArr& keys) {
+    long depth = 0;
+    std::string cur;
+    bool in_key = false, escaped = false;
+    for (char ch : s) {
+        if (escaped) { escaped = false; if (in_key) cur += ch; continue; }
+        if (ch == '\\') { escaped = true; continue; }
+        if (ch == '{') { if (++depth == 1) { in_key = true; cur.clear(); continue; } }
+        if (ch == '}') {
+            if (depth == 1 && in_key) { keys.push_back(JVal::str(cur)); in_key = false; --depth; continue; }
+            if (depth > 0) --depth;
+        }
+        if (in_key) cur += ch;
+    }
+}
+void extract_keys(const JVal& v, JArr& keys) {
+    if (v.t == JVal::Str) extract_from_str(v.s, keys);
+    else if (v.t == JVal::Arr) for (auto& x : *v.a) extract_keys(x, keys);
+    else if (v.t == JVal::Obj) for (auto& kv : *v.o) { extract_from_str(kv.first, keys); extract_keys(kv.second, keys); }
+}
+
+const JVal& arg(const JVal& args, const char* name) {
+    static const JVal null_v;
+    if (args.t != JVal::Obj) return null_v;
+    auto it = args.o->find(name);
+    return it == args.o->end() ? null_v : it->second;
+}
+const std::string& sarg(const JVal& args, const char* name) {
+    const JVal& v = arg(args, name);
+    if (v.t != JVal::Str) throw std::runtime_error(std::string("missing string argument '") + name + "'");
+    return v.s;
+}
+
+JVal dispatch(ie_engine* e, const JVal& args) {
+    const std::string& fn = sarg(args, "fn");
+    if (fn == "interpolate_inserts") {  // interp.rs:31
+        Session s(e, args);
+        return outcome_value(s.resolve({sarg(args, "content")})[0]);
+    }
+    if (fn == "interpolate_many") {  // batch form: [{ok|err}] per template, one launch
+        Session s(e, args);
+        std::vector<std::string> ts;
+        for (auto& x : *arg(args, "contents").a) ts.push_back(x.s);
+        JArr out;
+        for (auto& oc : s.resolve(ts)) {
+            JObj r;
+            try { r["ok"] = outcome_value(oc); }
+            catch (const ApiError& er) { r["err"] = JVal::obj({{"code", JVal::num(std::to_string(er.code))}, {"message", JVal::str(er.message)}, {"payload", JVal::str(er.payload)}}); }
+            out.push_back(JVal::obj(std::move(r)));
+        }
+        return JVal::arr(std::move(out));
+    }
+    if (fn == "get_simple_insertkey") {  // interp.rs:11
+        std::string k;
+        return simple_insertkey(sarg(args, "content"), &k) ? JVal::str(k) : JVal();
+    }
+    if (fn == "get_interpdata") {  // interp.rs:91
+        Session s(e, args);
+        return lookup_keys(s, {sarg(args, "key")})[0];
+    }
+    if (fn == "recursive_interpolate") {  // interp.rs:179
+        Session s(e, args);
+        const JVal& v = arg(args, "value");
+        Gather g;
+        gather(v, g);
+        const std::vector<JVal> looked = lookup_keys(s, g.lookups);
+        const std::vector<Outcome> res = s.resolve(g.templates);
+        Rebuild rb{res, looked};
+        return rb.walk(v);
+    }
+    if (fn == "recursive_escape") return escape_tree(e, 1, arg(args, "value"));      // interp.rs:163
+    if (fn == "recursive_unescape") return escape_tree(e, 0, arg(args, "value"));    // interp.rs:147
+    if (fn == "value_to_string") return JVal::str(value_to_string(arg(args, "value")));  // interp.rs:314
+    if (fn == "extract_insert_keys") { JArr k; extract_keys(arg(args, "value"), k); return JVal::arr(std::move(k)); }  // interp.rs:248
+    if (fn == "wildcard_match" || fn == "delete" || fn == "delete_except") {
+        Arena keys, pats;
+        JObj ins;
+        if (fn == "wildcard_match") {  // runtime.rs:1633
+            keys.push(sarg(args, "text"));
+            pats.push(sarg(args, "pattern"));
+        } else {  // runtime.rs:1198-1239: keys in sorted order; wildcards through value_to_string
+            const JVal& iv = arg(args, "inserts");
+            if (iv.t == JVal::Obj) ins = *iv.o;
+            for (auto& kv : ins) keys.push(kv.first);
+            const JVal& w = arg(args, "wildcards");
+            if (w.t == JVal::Arr) for (auto& x : *w.a) pats.push(value_to_string(x));
+        }
+        JArr deleted;
+        // more than IE_MAX_PATTERNS wildcards: sweep in groups; a key is matched when any group matches it
+        const uint64_t n = keys.n(), words = (n + 31) / 32;
+        std::vector<uint32_t> any(words, 0), mask(words + 1, 0);
+        for (uint64_t p0 = 0; p0 < pats.n(); p0 += IE_MAX_PATTERNS) {
+            const uint32_t np = (uint32_t)std::min<uint64_t>(IE_MAX_PATTERNS, pats.n() - p0);
+            std::vector<uint64_t> po(np + 1);
+            for (uint32_t i = 0; i <= np; ++i) po[i] = pats.offs[p0 + i] - pats.offs[p0];
+            uint64_t nd = 0;
+            check(ie_glob_sweep(e, keys.data(), keys.offs.data(), n, pats.data() + pats.offs[p0], po.data(), np, 0, mask.data(), &nd));
+            for (uint64_t w = 0; w < words; ++w) any[w] |= mask[w];
+        }
+        if (fn == "wildcard_match") return JVal::boolean(n && (any[0] & 1u));
+        const bool except = fn == "delete_except";
+        uint64_t k = 0;
+        std::vector<std::string> doomed;
+        for (auto& kv : ins) { const bool m = (any[k >> 5] >> (k & 31)) & 1u; if (m != except) doomed.push_back(kv.first); ++k; }
+        for (auto& d : doomed) { ins.erase(d); deleted.push_back(JVal::str(d)); }
+        return JVal::obj({{"deleted", JVal::arr(std::move(deleted))}, {"inserts", JVal::obj(std::move(ins))}});
+    }
+    throw std::runtime_error("unknown fn '" + fn + "'");
+}
+
+}  // namespace
+
+ie_status_t call_json(ie_engine* e, const std::string& args_json, std::string* out_json, std::string* why) {
+    JObj res;
+    try {
+        const JVal args = parse(args_json);
+        res["ok"] = dispatch(e, args);
+    } catch (const ApiError& er) {
+        res["err"] = JVal::obj({{"code", JVal::num(std::to_string(er.code))}, {"message", JVal::str(er.message)}, {"payload", JVal::str(er.payload)}});
+    } catch (const CallFailure& cf) {
+        *why = cf.why;
+        return cf.st;
+    } catch (const std::exception& ex) {
+        res["err"] = JVal::obj({{"code", JVal::num("-1")}, {"message", JVal::str(ex.what())}, {"payload", JVal::str("")}});
+    }
+    out_json->clear();
+    dump(JVal::obj(std::move(res)), *out_json);
+    return IE_OK;
+}
+
+}  // namespace ie_host

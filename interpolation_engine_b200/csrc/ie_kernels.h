@@ -1,0 +1,44 @@
+// Internal launch interface between the C ABI (ie_capi.cpp) and the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ie_common.cuh"
+
+#define IE_TILE 256           // templates per CTA in the fast resolve kernel
+#define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
+#define IE_GENERAL_WORKERS 2048u
+
+// Per-engine device workspace.  [zero_base, zero_base + zero_bytes) is cleared before a batch.
+struct IeWorkspace {
+    uint8_t* zero_base;
+    size_t zero_bytes;
+    uint32_t* tile_counter;   // dynamic tile ids (look-back forward progress)
+    uint32_t* general_count;  // templates handed to the general kernel
+    uint32_t* overflow;       // set when the out arena was too small
+    uint64_t* tile_state;     // [tiles] flag << 62 | bytes
+    uint32_t* general_list;   // [n]
+    uint8_t* scratch;         // general_workers * (tcap + IE_KEY_SCRATCH)
+    uint32_t general_workers;
+};
+
+cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                              uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                              const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
+                              cudaStream_t stream);
+
+// tag_out[i] = value tag or -1 on a miss; entry_out[i] = insert index (>= n_entries: clock key)
+cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,
+                             uint32_t* d_entry, cudaStream_t stream);
+
+// mode 0 unescape, 1 escape (interp.rs:147-177).  d_tile_state: [(n + IE_TILE - 1) / IE_TILE + 1] zeroed words.
+cudaError_t ie_launch_escape(int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint8_t* d_out,
+                             uint64_t out_cap, uint64_t* d_out_offs, const IeWorkspace& ws, cudaStream_t stream);
+
+struct IeGlobPatterns {  // passed by value as a kernel parameter (<= 4 KiB)
+    uint32_t n_pat;
+    uint32_t invert;
+    uint16_t off[IE_MAX_PATTERNS + 1];
+    uint8_t bytes[3584];
+};
+cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
+                           uint32_t* d_mask, uint64_t* d_n_deleted, cudaStream_t stream);

@@ -1,0 +1,514 @@
+// Batched `{key}` resolver kernels for sm_100a.
+//
+// Replaces interpolate_inserts (rust-project/src/interp.rs:31-89) + get_interpdata (:91-137) for
+// many independent templates against one immutable inserts snapshot.
+//
+//   ie_resolve_fast_kernel     one thread per template, 256 templates per CTA tile, single pass
+//                              over HBM: prescan -> size traversal -> CTA scan + decoupled
+//                              look-back across tiles -> write traversal into the compacted arena.
+//   ie_resolve_general_kernel  exact right-to-left rewriting machine for the templates the fast
+//                              path declines (values that are rescanned, sentinel collisions,
+//                              uneven braces, very long keys, deep nesting).
+//
+// Why a static traversal is exact on the fast path: the reference repeatedly rewrites the
+// rightmost "{...}" group (interp.rs:62-83).  When every spliced value is free of unescaped
+// braces and of the sentinel corner cases (IE_VF_* flags, checked per lookup), rewriting cannot
+// create or destroy groups, so the rewrite order equals ordinary bracket matching processed by
+// descending '{' position, and the first failure met in that order is the reference's error.
+#include <cuda_runtime.h>
+
+#include "ie_common.cuh"
+#include "ie_kernels.h"
+#include "ie_scan.cuh"
+
+namespace {
+
+constexpr int kTile = IE_TILE;  // templates per CTA
+constexpr uint32_t KCAP = 128;  // bytes of nested-key text a fast-path thread can hold
+constexpr uint32_t MAXLVL = 8;  // nesting depth of the fast path
+constexpr uint32_t MAXF = 24;   // splice depth of the general path
+constexpr uint32_t KSCR = IE_KEY_SCRATCH;
+
+// ---- table lookup --------------------------------------------------------------------------
+__device__ __forceinline__ const IeSlot* ie_lookup(const IeTableView& tv, const uint8_t* key, uint32_t len) {
+    const uint32_t h = ie_hash_bytes(key, len);
+    const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
+    uint32_t idx = h & tv.mask;
+    for (;;) {
+        const IeSlot* s = slots + idx;
+        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(s));  // hash, key_len, val_len, entry
+        if (hd.y == IE_SLOT_EMPTY) return nullptr;
+        if (hd.x == h && hd.y == len) {
+            const uint8_t* stored = tv.base + (size_t)s->key_off16 * 16u;
+            uint32_t i = 0;
+            for (; i < len; ++i) if (__ldg(stored + i) != key[i]) break;
+            if (i == len) return s;
+        }
+        idx = (idx + 1) & tv.mask;
+    }
+}
+
+__device__ __forceinline__ bool is_arg_key(const uint8_t* k, uint32_t len) {  // interp.rs:109
+    if (len < 3 || k[0] != 'A' || k[1] != 'R' || k[2] != 'G') return false;
+    for (uint32_t i = 3; i < len; ++i) if (k[i] < '0' || k[i] > '9') return false;
+    return true;
+}
+__device__ __forceinline__ bool tag_splices(uint32_t tag) {  // interp.rs:71-80
+    return tag == IE_TAG_STRING || tag == IE_TAG_NUMBER || tag == IE_TAG_ARRAY;
+}
+
+// ---- fast path -------------------------------------------------------------------------------
+struct Prescan {
+    uint32_t n_open, n_close, m0;
+    bool punt;
+};
+
+// One left-to-right pass: unescaped brace counts, the sentinel corner cases that the fast path
+// does not reproduce, and m0 = min(leading '{' run, trailing unescaped '}' run).
+__device__ __forceinline__ Prescan prescan(const uint8_t* __restrict__ t, uint32_t n) {
+    Prescan ps{0, 0, 0, false};
+    uint8_t p1 = 0, p2 = 0;  // previous two bytes
+    uint32_t lead = 0;
+    bool in_lead = true;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t c = __ldg(t + i);
+        if (c == '{') {
+            if (p1 != '\\') { ++ps.n_open; if (in_lead) ++lead; }
+            else in_lead = false;
+        } else {
+            in_lead = false;
+            if (c == '}') {
+                if (p1 != '\\') ++ps.n_close;
+                else if (p2 == '.' || p2 == '}') ps.punt = true;  // ".\}" / "}\}": '.' + "〠." collides with ".〠"
+            } else if (c == 0xA0 && p1 == 0x80 && p2 == 0xE3) ps.punt = true;  // literal U+3020
+        }
+        p2 = p1; p1 = c;
+    }
+    uint32_t trail = 0;
+    for (uint32_t i = n; i > 0; --i) {
+        if (__ldg(t + i - 1) != '}') break;
+        if (i >= 2 && __ldg(t + i - 2) == '\\') break;
+        ++trail;
+    }
+    ps.m0 = min(lead, trail);
+    if (ps.n_open && ps.n_open != ps.n_close) ps.punt = true;  // uneven: the general path emits the exact text
+    return ps;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void fast_traverse(const IeTableView& tv, const uint8_t* __restrict__ t, uint32_t n, uint32_t m0,
+                                              uint8_t* wend, uint32_t known_status, uint32_t& out_len, uint32_t& status,
+                                              uint32_t& aux) {
+    uint8_t kbuf[KCAP];
+    uint32_t lvl_mark[MAXLVL], lvl_pos[MAXLVL];
+    uint32_t ktop = KCAP, lvl = 0, p = n, olen = 0;
+    uint8_t* w = wend;
+    const bool emit = WRITE && known_status == IE_RES_STRING;
+    status = IE_RES_STRING;
+    aux = 0;
+    while (p > 0) {
+        const uint8_t c = __ldg(t + p - 1);
+        const bool brace = (c == '{') || (c == '}');
+        if (brace && p >= 2 && __ldg(t + p - 2) == '\\') {  // escaped brace: opaque pair
+            if (lvl) {
+                if (ktop < 2) { status = IE_RES_PUNT; break; }
+                kbuf[--ktop] = c; kbuf[--ktop] = '\\';
+            } else {
+                olen += 2;
+                if (emit) { *--w = c; *--w = '\\'; }
+            }
+            p -= 2;
+            continue;
+        }
+        if (c == '}') {
+            if (lvl == MAXLVL) { status = IE_RES_PUNT; break; }
+            lvl_mark[lvl] = ktop; lvl_pos[lvl] = p - 1; ++lvl; --p;
+            continue;
+        }
+        if (c == '{') {
+            if (lvl == 0) { status = IE_RES_PANIC; olen = 0; break; }  // interp.rs:63-66
+            --lvl;
+            const uint32_t mark = lvl_mark[lvl], klen = mark - ktop, o = p - 1;
+            const bool simple_layer = (o < m0) && (lvl_pos[lvl] == n - 1 - o);  // interp.rs:45-52
+            const uint8_t* key = kbuf + ktop;
+            uint32_t err = 0;
+            const IeSlot* s = nullptr;
+            if (klen == 0) err = IE_RES_EMPTY_KEY;
+            else {
+                s = ie_lookup(tv, key, klen);
+                if (!s) err = is_arg_key(key, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
+                else if (!simple_layer) {
+                    const uint32_t tf = s->tagflags;
+                    if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;
+                    else if ((tf >> 8) & IE_VF_ANY) { status = IE_RES_PUNT; break; }
+                }
+            }
+            if (err) {
+                status = err; olen = klen;
+                if (WRITE) for (uint32_t i = 0; i < klen; ++i) wend[(int)i - (int)klen] = key[i];
+                break;
+            }
+            ktop = mark;
+            const uint32_t vlen = s->val_len;
+            const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
+            if (lvl) {
+                if (ktop < vlen) { status = IE_RES_PUNT; break; }
+                ktop -= vlen;
+                for (uint32_t i = 0; i < vlen; ++i) kbuf[ktop + i] = __ldg(v + i);
+            } else if (simple_layer) {
+                status = IE_RES_TYPED | ((s->tagflags & 0xFF) << 8);
+                aux = s->entry;
+                olen = vlen;
+                if (WRITE) for (uint32_t i = 0; i < vlen; ++i) wend[(int)i - (int)vlen] = __ldg(v + i);
+            } else {
+                olen += vlen;
+                if (emit) { w -= vlen; for (uint32_t i = 0; i < vlen; ++i) w[i] = __ldg(v + i); }
+            }
+            --p;
+            continue;
+        }
+        if (lvl) {
+            if (!ktop) { status = IE_RES_PUNT; break; }
+            kbuf[--ktop] = c;
+        } else {
+            ++olen;
+            if (emit) *--w = c;
+        }
+        --p;
+    }
+    out_len = (status == IE_RES_PUNT) ? 0u : olen;
+}
+
+__global__ void __launch_bounds__(kTile) ie_resolve_fast_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+                                                                const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
+                                                                uint64_t out_cap, uint64_t* __restrict__ out_offs,
+                                                                uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
+                                                                uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info) {
+    __shared__ ie_scan::TileSmem s_scan;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = ie_scan::acquire_tile(s_scan, ws.tile_counter);
+    const uint64_t i = (uint64_t)tile * kTile + tid;
+    const bool active = i < n;
+
+    const uint8_t* t = nullptr;
+    uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
+    bool verbatim = false;
+    if (active) {
+        const uint64_t a = __ldg(offs + i), b = __ldg(offs + i + 1);
+        t = tmpl + a;
+        if (b - a > 0x7FFFFFFFull) { status = IE_RES_LIMIT; }
+        else {
+            len = (uint32_t)(b - a);
+            const Prescan ps = prescan(t, len);
+            m0 = ps.m0;
+            if (ps.punt) status = IE_RES_PUNT;
+            else if (ps.n_open == 0) { verbatim = true; olen = len; }  // loop at interp.rs:54 never entered
+            else fast_traverse<false>(tv, t, len, m0, nullptr, 0, olen, status, aux);
+        }
+        if (status == IE_RES_PUNT) {
+            olen = 0;
+            const uint32_t k = atomicAdd(ws.general_count, 1u);
+            ws.general_list[k] = (uint32_t)i;  // batches are < 2^32 templates (checked on the host)
+        }
+    }
+
+    uint64_t tile_end;
+    const uint64_t off = ie_scan::exclusive_prefix(s_scan, ws.tile_state, tile, olen, &tile_end);
+    if (tid == 0 && (uint64_t)tile + 1 == (n + kTile - 1) / kTile) {  // last tile: size of the compacted region
+        info->n = n;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
+    }
+    if (!active) return;
+    out_offs[i] = off;
+    out_lens[i] = olen;
+    status_out[i] = (int32_t)status;
+    aux_out[i] = aux;
+    if (olen == 0) return;
+    if (off + olen > out_cap) { *ws.overflow = 1u; return; }
+    uint8_t* wend = out + off + olen;
+    if (verbatim) {
+        uint8_t* w = out + off;
+        for (uint32_t k = 0; k < len; ++k) w[k] = __ldg(t + k);
+    } else {
+        uint32_t l2, s2, a2;
+        fast_traverse<true>(tv, t, len, m0, wend, status & 0xFF, l2, s2, a2);
+    }
+}
+
+// ---- general path ----------------------------------------------------------------------------
+struct Frame {
+    const uint8_t* ptr;
+    uint32_t len, pos;
+};
+
+__device__ void count_braces(const uint8_t* v, uint32_t len, uint32_t& opens, uint32_t& closes) {
+    uint8_t prev = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint8_t c = v[i];
+        if (prev != '\\') { if (c == '{') ++opens; else if (c == '}') ++closes; }
+        prev = c;
+    }
+}
+
+// get_simple_insertkey (interp.rs:11-29) on the sentinelised form of t[lo, hi): escaped braces are
+// sentinel text there, i.e. ordinary middle characters.
+__device__ bool is_simple_range(const uint8_t* t, uint32_t lo, uint32_t hi) {
+    if (hi - lo < 2 || t[lo] != '{' || t[hi - 1] != '}') return false;
+    if (hi - lo >= 3 && t[hi - 2] == '\\') return false;  // last char is part of "〠."
+    int depth = 0;
+    uint8_t prev = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const uint8_t c = t[i];
+        const bool esc = (i > lo) && prev == '\\';
+        if (c == '}' && !esc) --depth;
+        if ((depth == 0) != (i == lo || i == hi - 1)) return false;
+        if (c == '{' && !esc) ++depth;
+        prev = c;
+    }
+    return true;
+}
+
+// unsentinelise (interp.rs:86-87: replace ".〠" -> "\{" everywhere, then "〠." -> "\}"), streamed.
+// An "〠." survives the first pass iff its '.' does not start a ".〠" (see DESIGN.md).
+template <bool WRITE>
+__device__ uint32_t unsentinelise(const uint8_t* b, uint32_t len, uint8_t* dst) {
+    uint32_t o = 0, i = 0;
+    while (i < len) {
+        if (i + 4 <= len) {
+            const uint8_t b0 = b[i], b1 = b[i + 1], b2 = b[i + 2], b3 = b[i + 3];
+            if (b0 == 0x2E && b1 == 0xE3 && b2 == 0x80 && b3 == 0xA0) {
+                if (WRITE) { dst[o] = '\\'; dst[o + 1] = '{'; }
+                o += 2; i += 4;
+                continue;
+            }
+            if (b0 == 0xE3 && b1 == 0x80 && b2 == 0xA0 && b3 == 0x2E &&
+                !(i + 7 <= len && b[i + 4] == 0xE3 && b[i + 5] == 0x80 && b[i + 6] == 0xA0)) {
+                if (WRITE) { dst[o] = '\\'; dst[o + 1] = '}'; }
+                o += 2; i += 4;
+                continue;
+            }
+        }
+        if (WRITE) dst[o] = b[i];
+        ++o; ++i;
+    }
+    return o;
+}
+
+// sentinelise (interp.rs:42-43) of raw bytes v[0, len), streamed; the first byte is never escaped
+// by what precedes it (see DESIGN.md "general path").
+template <bool WRITE>
+__device__ uint32_t sentinelise(const uint8_t* v, uint32_t len, uint8_t* dst) {
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint8_t c = v[i];
+        if (c == '\\' && i + 1 < len && (v[i + 1] == '{' || v[i + 1] == '}')) {
+            if (WRITE) {
+                if (v[i + 1] == '{') { dst[o] = 0x2E; dst[o + 1] = 0xE3; dst[o + 2] = 0x80; dst[o + 3] = 0xA0; }
+                else { dst[o] = 0xE3; dst[o + 1] = 0x80; dst[o + 2] = 0xA0; dst[o + 3] = 0x2E; }
+            }
+            o += 4; ++i;
+            continue;
+        }
+        if (WRITE) dst[o] = c;
+        ++o;
+    }
+    return o;
+}
+
+struct GenResult {
+    uint32_t status, aux;
+    const uint8_t* payload;  // already-final bytes (key / value), or nullptr when in T / frames
+    uint32_t payload_len;
+};
+
+__device__ uint8_t* reserve_out(uint8_t* out, uint64_t out_cap, ie_batch_info* info, uint32_t* overflow, uint32_t len,
+                                uint64_t& off) {
+    off = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)len);
+    if (off + len > out_cap) { *overflow = 1u; return nullptr; }
+    return out + off;
+}
+
+__global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+                                                                const uint64_t* __restrict__ offs, uint8_t* __restrict__ out,
+                                                                uint64_t out_cap, uint64_t* __restrict__ out_offs,
+                                                                uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
+                                                                uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info,
+                                                                uint32_t max_expansions, uint32_t tcap) {
+    const uint32_t worker = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_workers = gridDim.x * blockDim.x;
+    const uint32_t count = *ws.general_count;
+    if (worker == 0 && count) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_general), (unsigned long long)count);
+    uint8_t* T = ws.scratch + (size_t)worker * ((size_t)tcap + KSCR);
+    uint8_t* kscr = T + tcap;
+
+    for (uint32_t q = worker; q < count; q += n_workers) {
+        const uint32_t i = ws.general_list[q];
+        const uint8_t* t = tmpl + offs[i];
+        const uint32_t n = (uint32_t)(offs[i + 1] - offs[i]);
+
+        // peel simple layers (interp.rs:45-52, recursion on the inner key)
+        uint32_t lo = 0, hi = n, m = 0;
+        while (is_simple_range(t, lo, hi)) { ++lo; --hi; ++m; }
+
+        Frame frames[MAXF];
+        uint32_t nf = 0, ttop = tcap, in_open = 0, in_close = 0, t_close = 0, expansions = 0;
+        uint32_t status = IE_RES_STRING, aux = 0;
+        const uint8_t* payload = nullptr;  // final bytes when not in T
+        uint32_t payload_len = 0;
+        bool uneven = false;
+        if (hi > lo) {
+            frames[nf++] = Frame{t + lo, hi - lo, hi - lo};
+            count_braces(t + lo, hi - lo, in_open, in_close);
+        }
+        // right-to-left rewriting machine: T holds the (sentinelised) text to the right of the
+        // rightmost unresolved '{'; frames hold what is still to its left.
+        while (nf > 0 && status == IE_RES_STRING) {
+            Frame& f = frames[nf - 1];
+            if (f.pos == 0) { --nf; continue; }
+            const uint8_t c = f.ptr[f.pos - 1];
+            if (c == '{' || c == '}') {
+                if (f.pos >= 2 && f.ptr[f.pos - 2] == '\\') {  // escaped: sentinel text
+                    if (ttop < 4) { status = IE_RES_LIMIT; break; }
+                    ttop -= 4;
+                    if (c == '{') { T[ttop] = 0x2E; T[ttop + 1] = 0xE3; T[ttop + 2] = 0x80; T[ttop + 3] = 0xA0; }
+                    else { T[ttop] = 0xE3; T[ttop + 1] = 0x80; T[ttop + 2] = 0xA0; T[ttop + 3] = 0x2E; }
+                    f.pos -= 2;
+                    continue;
+                }
+                if (c == '}') {
+                    if (ttop < 1) { status = IE_RES_LIMIT; break; }
+                    T[--ttop] = '}'; --in_close; ++t_close; --f.pos;
+                    continue;
+                }
+                // rightmost unescaped '{' of the current string: one iteration of interp.rs:54-84
+                if (in_open != in_close + t_close) { status = IE_RES_UNEVEN; uneven = true; break; }
+                uint32_t idx = ttop;
+                while (idx < tcap && T[idx] != '}') ++idx;
+                if (idx == tcap) { status = IE_RES_PANIC; break; }
+                if (unsentinelise<false>(T + ttop, idx - ttop, nullptr) > KSCR) { status = IE_RES_LIMIT; break; }
+                const uint32_t klen = unsentinelise<true>(T + ttop, idx - ttop, kscr);
+                payload = kscr; payload_len = klen;
+                if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }
+                const IeSlot* s = ie_lookup(tv, kscr, klen);
+                if (!s) { status = is_arg_key(kscr, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
+                if (!tag_splices(s->tagflags & 0xFF)) { status = IE_RES_UNSUPPORTED; break; }
+                payload = nullptr; payload_len = 0;
+                ttop = idx + 1; --t_close; --in_open; --f.pos;
+                if (++expansions > max_expansions) { status = IE_RES_LIMIT; break; }
+                if (f.pos == 0) --nf;
+                const uint32_t vlen = s->val_len;
+                if (vlen) {
+                    if (nf == MAXF) { status = IE_RES_LIMIT; break; }
+                    const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
+                    frames[nf++] = Frame{v, vlen, vlen};
+                    count_braces(v, vlen, in_open, in_close);
+                }
+                continue;
+            }
+            if (c == '\\' && f.pos == f.len && ttop < tcap && T[ttop] == '}') {
+                // a spliced value ending in '\' escapes the '}' that now follows it (interp.rs:82-83)
+                if (ttop < 3) { status = IE_RES_LIMIT; break; }
+                ttop += 1; ttop -= 4;
+                T[ttop] = 0xE3; T[ttop + 1] = 0x80; T[ttop + 2] = 0xA0; T[ttop + 3] = 0x2E;
+                --t_close; --f.pos;
+                continue;
+            }
+            if (ttop < 1) { status = IE_RES_LIMIT; break; }
+            T[--ttop] = c; --f.pos;
+        }
+
+        uint64_t off = 0;
+        uint32_t olen = 0;
+        if (uneven) {
+            // payload = the current string: unread frame prefixes (sentinelised) + T   (interp.rs:57-61)
+            for (uint32_t k = 0; k < nf; ++k) olen += sentinelise<false>(frames[k].ptr, frames[k].pos, nullptr);
+            olen += tcap - ttop;
+            uint8_t* w = reserve_out(out, out_cap, info, ws.overflow, olen, off);
+            if (w) {
+                for (uint32_t k = 0; k < nf; ++k) w += sentinelise<true>(frames[k].ptr, frames[k].pos, w);
+                for (uint32_t k = ttop; k < tcap; ++k) *w++ = T[k];
+            }
+        } else if (status == IE_RES_STRING) {
+            if (m == 0) {
+                olen = unsentinelise<false>(T + ttop, tcap - ttop, nullptr);
+                uint8_t* w = reserve_out(out, out_cap, info, ws.overflow, olen, off);
+                if (w) unsentinelise<true>(T + ttop, tcap - ttop, w);
+            } else {
+                // simple path: the core's string is the first key; each layer looks up the
+                // rendering of the previous result, typed and without rescan (interp.rs:47-51)
+                uint32_t klen = unsentinelise<false>(T + ttop, tcap - ttop, nullptr);
+                const uint8_t* key = kscr;
+                if (klen > KSCR) status = IE_RES_LIMIT;
+                else {
+                    unsentinelise<true>(T + ttop, tcap - ttop, kscr);
+                    for (uint32_t layer = 0; layer < m; ++layer) {
+                        payload = key; payload_len = klen;
+                        if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }
+                        const IeSlot* s = ie_lookup(tv, key, klen);
+                        if (!s) { status = is_arg_key(key, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
+                        key = tv.base + (size_t)s->val_off16 * 16u;
+                        klen = s->val_len;
+                        payload = key; payload_len = klen;
+                        status = IE_RES_TYPED | ((s->tagflags & 0xFF) << 8);
+                        aux = s->entry;
+                    }
+                }
+                if (status == IE_RES_LIMIT) { payload = nullptr; payload_len = 0; }
+                olen = payload_len;
+                if (olen) {
+                    uint8_t* w = reserve_out(out, out_cap, info, ws.overflow, olen, off);
+                    if (w) for (uint32_t k = 0; k < olen; ++k) w[k] = payload[k];
+                }
+            }
+        } else {
+            olen = payload_len;  // error with key payload (or none)
+            if (status == IE_RES_PANIC || status == IE_RES_LIMIT) olen = 0;
+            if (olen) {
+                uint8_t* w = reserve_out(out, out_cap, info, ws.overflow, olen, off);
+                if (w) for (uint32_t k = 0; k < olen; ++k) w[k] = payload[k];
+            }
+        }
+        out_offs[i] = off;
+        out_lens[i] = olen;
+        status_out[i] = (int32_t)status;
+        aux_out[i] = aux;
+    }
+}
+
+// get_interpdata (interp.rs:91-137) for a batch of literal keys: one thread per key.
+__global__ void __launch_bounds__(256) ie_lookup_kernel(IeTableView tv, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ offs,
+                                                        uint64_t n, int32_t* __restrict__ tag_out, uint32_t* __restrict__ entry_out) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t a = offs[k];
+    const uint32_t len = (uint32_t)(offs[k + 1] - a);
+    const IeSlot* s = len ? ie_lookup(tv, keys + a, len) : nullptr;
+    tag_out[k] = s ? (int32_t)(s->tagflags & 0xFF) : -1;
+    entry_out[k] = s ? s->entry : IE_AUX_NONE;
+}
+
+}  // namespace
+
+cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,
+                             uint32_t* d_entry, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ie_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tv, d_keys, d_offs, n, d_tag, d_entry);
+    return cudaGetLastError();
+}
+
+cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                              uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                              const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
+                              cudaStream_t stream) {
+    cudaError_t err;
+    if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
+    if (n == 0) return cudaSuccess;
+    const uint64_t tiles = (n + kTile - 1) / kTile;
+    ie_resolve_fast_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens,
+                                                                 d_status, d_aux, ws, d_info);
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(tv, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+                                                                         d_status, d_aux, ws, d_info, max_expansions, tcap);
+    return cudaGetLastError();
+}

@@ -1,0 +1,87 @@
+// CTA-level exclusive scan of per-thread output lengths plus a decoupled look-back across CTA
+// tiles (single pass, Merrill & Garland style): every variable-length kernel in this engine
+// (resolve, escape) writes a compacted arena in input order without a second pass over HBM.
+#pragma once
+#include <cstdint>
+
+#include "ie_kernels.h"
+
+namespace ie_scan {
+
+constexpr uint64_t FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_state(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct TileSmem {
+    uint32_t tile;
+    uint64_t warp_tot[IE_TILE / 32];
+    uint64_t base;
+};
+
+// Tile ids are handed out in CTA start order, so every predecessor of a tile is already resident
+// or finished when it waits on it: forward progress does not depend on the block scheduler.
+__device__ __forceinline__ uint32_t acquire_tile(TileSmem& sm, uint32_t* tile_counter) {
+    if (threadIdx.x == 0) sm.tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    return sm.tile;
+}
+
+// Returns the global exclusive prefix of `len` for this thread; *grand_total is the inclusive
+// prefix at the end of this tile (valid on every thread).  Must be called by all IE_TILE threads.
+__device__ __forceinline__ uint64_t exclusive_prefix(TileSmem& sm, uint64_t* tile_state, uint32_t tile, uint64_t len,
+                                                     uint64_t* tile_end) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += y;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    uint64_t warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < IE_TILE / 32; ++w) {
+        const uint64_t x = sm.warp_tot[w];
+        if (w < (int)warp) warp_off += x;
+        tile_total += x;
+    }
+    if (warp == 0) {
+        uint64_t base = 0;
+        if (tile == 0) {
+            if (lane == 0) st_state(tile_state, FLAG_INC | tile_total);
+        } else {
+            if (lane == 0) st_state(tile_state + tile, FLAG_AGG | tile_total);
+            int64_t j = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t idx = j - (int64_t)lane;
+                uint64_t sv = FLAG_INC;  // before tile 0: inclusive prefix 0
+                if (idx >= 0) {
+                    do { sv = ld_state(tile_state + idx); } while ((sv >> 62) == 0);
+                }
+                const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (sv >> 62) == 2);
+                const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                uint64_t v = ((int)lane <= first) ? (sv & VAL_MASK) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                base += v;
+                if (inc_mask) break;
+                j -= 32;
+            }
+            if (lane == 0) st_state(tile_state + tile, FLAG_INC | (base + tile_total));
+        }
+        if (lane == 0) sm.base = base;
+    }
+    __syncthreads();
+    *tile_end = sm.base + tile_total;
+    return sm.base + warp_off + incl - len;
+}
+
+}  // namespace ie_scan
