@@ -193,7 +193,11 @@ def main():
             "out_lens": torch.empty(n, dtype=torch.int32, device=dev), "status": torch.empty(n, dtype=torch.int32, device=dev),
             "aux": torch.empty(n, dtype=torch.int32, device=dev), "info": torch.zeros(info_bytes, dtype=torch.uint8, device=dev),
         })
-    stream = torch.cuda.current_stream()
+    # an explicit non-default stream: the ABI maps a NULL stream to the engine's own stream, and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
 
     def step(k):
         s = sets[k % 2]

@@ -78,7 +78,7 @@ namespace {
 
 // Lays the per-batch workspace out for n items; returns the kernel-side view.
 ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws) {
-    const uint64_t tiles = (n + IE_TILE - 1) / IE_TILE;
+    const uint64_t tiles = (n + IE_RESOLVE_TILE - 1) / IE_RESOLVE_TILE;
     const size_t zero_bytes = 64 + (size_t)(tiles + 1) * sizeof(uint64_t);
     CU(e->ws_zero.ensure(zero_bytes, e->stream));
     ws->zero_base = (uint8_t*)e->ws_zero.p;

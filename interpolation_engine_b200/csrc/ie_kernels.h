@@ -4,7 +4,8 @@
 
 #include "ie_common.cuh"
 
-#define IE_TILE 256           // templates per CTA in the fast resolve kernel
+#define IE_TILE 256           // strings per CTA in the escape kernel
+#define IE_RESOLVE_TILE 128   // templates per CTA in the resolve tile kernel (sizes the tile-state array)
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
 #define IE_GENERAL_WORKERS 2048u
 
@@ -25,6 +26,10 @@ cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, cons
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
                               cudaStream_t stream);
+
+cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                                    uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                    const IeWorkspace& ws, ie_batch_info* d_info, cudaStream_t stream);
 
 // tag_out[i] = value tag or -1 on a miss; entry_out[i] = insert index (>= n_entries: clock key)
 cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,

@@ -3,237 +3,24 @@
 // Replaces interpolate_inserts (rust-project/src/interp.rs:31-89) + get_interpdata (:91-137) for
 // many independent templates against one immutable inserts snapshot.
 //
-//   ie_resolve_fast_kernel     one thread per template, 256 templates per CTA tile, single pass
-//                              over HBM: prescan -> size traversal -> CTA scan + decoupled
-//                              look-back across tiles -> write traversal into the compacted arena.
-//   ie_resolve_general_kernel  exact right-to-left rewriting machine for the templates the fast
-//                              path declines (values that are rescanned, sentinel collisions,
+//   ie_resolve_tile_kernel     (ie_resolve_tile.cu) the hot path: cooperative CTA tiles, single pass
+//                              over HBM, compacted output.
+//   ie_resolve_general_kernel  exact right-to-left rewriting machine for the templates the tile
+//                              kernel declines (values that are rescanned, sentinel collisions,
 //                              uneven braces, very long keys, deep nesting).
-//
-// Why a static traversal is exact on the fast path: the reference repeatedly rewrites the
-// rightmost "{...}" group (interp.rs:62-83).  When every spliced value is free of unescaped
-// braces and of the sentinel corner cases (IE_VF_* flags, checked per lookup), rewriting cannot
-// create or destroy groups, so the rewrite order equals ordinary bracket matching processed by
-// descending '{' position, and the first failure met in that order is the reference's error.
+//   ie_lookup_kernel           get_interpdata for literal keys.
 #include <cuda_runtime.h>
 
 #include "ie_common.cuh"
 #include "ie_kernels.h"
+#include "ie_device.cuh"
 #include "ie_scan.cuh"
 
 namespace {
 
-constexpr int kTile = IE_TILE;  // templates per CTA
-constexpr uint32_t KCAP = 128;  // bytes of nested-key text a fast-path thread can hold
-constexpr uint32_t MAXLVL = 8;  // nesting depth of the fast path
+using namespace ie_dev;
 constexpr uint32_t MAXF = 24;   // splice depth of the general path
 constexpr uint32_t KSCR = IE_KEY_SCRATCH;
-
-// ---- table lookup --------------------------------------------------------------------------
-__device__ __forceinline__ const IeSlot* ie_lookup(const IeTableView& tv, const uint8_t* key, uint32_t len) {
-    const uint32_t h = ie_hash_bytes(key, len);
-    const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
-    uint32_t idx = h & tv.mask;
-    for (;;) {
-        const IeSlot* s = slots + idx;
-        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(s));  // hash, key_len, val_len, entry
-        if (hd.y == IE_SLOT_EMPTY) return nullptr;
-        if (hd.x == h && hd.y == len) {
-            const uint8_t* stored = tv.base + (size_t)s->key_off16 * 16u;
-            uint32_t i = 0;
-            for (; i < len; ++i) if (__ldg(stored + i) != key[i]) break;
-            if (i == len) return s;
-        }
-        idx = (idx + 1) & tv.mask;
-    }
-}
-
-__device__ __forceinline__ bool is_arg_key(const uint8_t* k, uint32_t len) {  // interp.rs:109
-    if (len < 3 || k[0] != 'A' || k[1] != 'R' || k[2] != 'G') return false;
-    for (uint32_t i = 3; i < len; ++i) if (k[i] < '0' || k[i] > '9') return false;
-    return true;
-}
-__device__ __forceinline__ bool tag_splices(uint32_t tag) {  // interp.rs:71-80
-    return tag == IE_TAG_STRING || tag == IE_TAG_NUMBER || tag == IE_TAG_ARRAY;
-}
-
-// ---- fast path -------------------------------------------------------------------------------
-struct Prescan {
-    uint32_t n_open, n_close, m0;
-    bool punt;
-};
-
-// One left-to-right pass: unescaped brace counts, the sentinel corner cases that the fast path
-// does not reproduce, and m0 = min(leading '{' run, trailing unescaped '}' run).
-__device__ __forceinline__ Prescan prescan(const uint8_t* __restrict__ t, uint32_t n) {
-    Prescan ps{0, 0, 0, false};
-    uint8_t p1 = 0, p2 = 0;  // previous two bytes
-    uint32_t lead = 0;
-    bool in_lead = true;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint8_t c = __ldg(t + i);
-        if (c == '{') {
-            if (p1 != '\\') { ++ps.n_open; if (in_lead) ++lead; }
-            else in_lead = false;
-        } else {
-            in_lead = false;
-            if (c == '}') {
-                if (p1 != '\\') ++ps.n_close;
-                else if (p2 == '.' || p2 == '}') ps.punt = true;  // ".\}" / "}\}": '.' + "〠." collides with ".〠"
-            } else if (c == 0xA0 && p1 == 0x80 && p2 == 0xE3) ps.punt = true;  // literal U+3020
-        }
-        p2 = p1; p1 = c;
-    }
-    uint32_t trail = 0;
-    for (uint32_t i = n; i > 0; --i) {
-        if (__ldg(t + i - 1) != '}') break;
-        if (i >= 2 && __ldg(t + i - 2) == '\\') break;
-        ++trail;
-    }
-    ps.m0 = min(lead, trail);
-    if (ps.n_open && ps.n_open != ps.n_close) ps.punt = true;  // uneven: the general path emits the exact text
-    return ps;
-}
-
-template <bool WRITE>
-__device__ __forceinline__ void fast_traverse(const IeTableView& tv, const uint8_t* __restrict__ t, uint32_t n, uint32_t m0,
-                                              uint8_t* wend, uint32_t known_status, uint32_t& out_len, uint32_t& status,
-                                              uint32_t& aux) {
-    uint8_t kbuf[KCAP];
-    uint32_t lvl_mark[MAXLVL], lvl_pos[MAXLVL];
-    uint32_t ktop = KCAP, lvl = 0, p = n, olen = 0;
-    uint8_t* w = wend;
-    const bool emit = WRITE && known_status == IE_RES_STRING;
-    status = IE_RES_STRING;
-    aux = 0;
-    while (p > 0) {
-        const uint8_t c = __ldg(t + p - 1);
-        const bool brace = (c == '{') || (c == '}');
-        if (brace && p >= 2 && __ldg(t + p - 2) == '\\') {  // escaped brace: opaque pair
-            if (lvl) {
-                if (ktop < 2) { status = IE_RES_PUNT; break; }
-                kbuf[--ktop] = c; kbuf[--ktop] = '\\';
-            } else {
-                olen += 2;
-                if (emit) { *--w = c; *--w = '\\'; }
-            }
-            p -= 2;
-            continue;
-        }
-        if (c == '}') {
-            if (lvl == MAXLVL) { status = IE_RES_PUNT; break; }
-            lvl_mark[lvl] = ktop; lvl_pos[lvl] = p - 1; ++lvl; --p;
-            continue;
-        }
-        if (c == '{') {
-            if (lvl == 0) { status = IE_RES_PANIC; olen = 0; break; }  // interp.rs:63-66
-            --lvl;
-            const uint32_t mark = lvl_mark[lvl], klen = mark - ktop, o = p - 1;
-            const bool simple_layer = (o < m0) && (lvl_pos[lvl] == n - 1 - o);  // interp.rs:45-52
-            const uint8_t* key = kbuf + ktop;
-            uint32_t err = 0;
-            const IeSlot* s = nullptr;
-            if (klen == 0) err = IE_RES_EMPTY_KEY;
-            else {
-                s = ie_lookup(tv, key, klen);
-                if (!s) err = is_arg_key(key, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
-                else if (!simple_layer) {
-                    const uint32_t tf = s->tagflags;
-                    if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;
-                    else if ((tf >> 8) & IE_VF_ANY) { status = IE_RES_PUNT; break; }
-                }
-            }
-            if (err) {
-                status = err; olen = klen;
-                if (WRITE) for (uint32_t i = 0; i < klen; ++i) wend[(int)i - (int)klen] = key[i];
-                break;
-            }
-            ktop = mark;
-            const uint32_t vlen = s->val_len;
-            const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
-            if (lvl) {
-                if (ktop < vlen) { status = IE_RES_PUNT; break; }
-                ktop -= vlen;
-                for (uint32_t i = 0; i < vlen; ++i) kbuf[ktop + i] = __ldg(v + i);
-            } else if (simple_layer) {
-                status = IE_RES_TYPED | ((s->tagflags & 0xFF) << 8);
-                aux = s->entry;
-                olen = vlen;
-                if (WRITE) for (uint32_t i = 0; i < vlen; ++i) wend[(int)i - (int)vlen] = __ldg(v + i);
-            } else {
-                olen += vlen;
-                if (emit) { w -= vlen; for (uint32_t i = 0; i < vlen; ++i) w[i] = __ldg(v + i); }
-            }
-            --p;
-            continue;
-        }
-        if (lvl) {
-            if (!ktop) { status = IE_RES_PUNT; break; }
-            kbuf[--ktop] = c;
-        } else {
-            ++olen;
-            if (emit) *--w = c;
-        }
-        --p;
-    }
-    out_len = (status == IE_RES_PUNT) ? 0u : olen;
-}
-
-__global__ void __launch_bounds__(kTile) ie_resolve_fast_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
-                                                                const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
-                                                                uint64_t out_cap, uint64_t* __restrict__ out_offs,
-                                                                uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
-                                                                uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info) {
-    __shared__ ie_scan::TileSmem s_scan;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t tile = ie_scan::acquire_tile(s_scan, ws.tile_counter);
-    const uint64_t i = (uint64_t)tile * kTile + tid;
-    const bool active = i < n;
-
-    const uint8_t* t = nullptr;
-    uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
-    bool verbatim = false;
-    if (active) {
-        const uint64_t a = __ldg(offs + i), b = __ldg(offs + i + 1);
-        t = tmpl + a;
-        if (b - a > 0x7FFFFFFFull) { status = IE_RES_LIMIT; }
-        else {
-            len = (uint32_t)(b - a);
-            const Prescan ps = prescan(t, len);
-            m0 = ps.m0;
-            if (ps.punt) status = IE_RES_PUNT;
-            else if (ps.n_open == 0) { verbatim = true; olen = len; }  // loop at interp.rs:54 never entered
-            else fast_traverse<false>(tv, t, len, m0, nullptr, 0, olen, status, aux);
-        }
-        if (status == IE_RES_PUNT) {
-            olen = 0;
-            const uint32_t k = atomicAdd(ws.general_count, 1u);
-            ws.general_list[k] = (uint32_t)i;  // batches are < 2^32 templates (checked on the host)
-        }
-    }
-
-    uint64_t tile_end;
-    const uint64_t off = ie_scan::exclusive_prefix(s_scan, ws.tile_state, tile, olen, &tile_end);
-    if (tid == 0 && (uint64_t)tile + 1 == (n + kTile - 1) / kTile) {  // last tile: size of the compacted region
-        info->n = n;
-        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
-    }
-    if (!active) return;
-    out_offs[i] = off;
-    out_lens[i] = olen;
-    status_out[i] = (int32_t)status;
-    aux_out[i] = aux;
-    if (olen == 0) return;
-    if (off + olen > out_cap) { *ws.overflow = 1u; return; }
-    uint8_t* wend = out + off + olen;
-    if (verbatim) {
-        uint8_t* w = out + off;
-        for (uint32_t k = 0; k < len; ++k) w[k] = __ldg(t + k);
-    } else {
-        uint32_t l2, s2, a2;
-        fast_traverse<true>(tv, t, len, m0, wend, status & 0xFF, l2, s2, a2);
-    }
-}
 
 // ---- general path ----------------------------------------------------------------------------
 struct Frame {
@@ -504,10 +291,9 @@ cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, cons
     if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
-    const uint64_t tiles = (n + kTile - 1) / kTile;
-    ie_resolve_fast_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens,
-                                                                 d_status, d_aux, ws, d_info);
-    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    if ((err = ie_launch_resolve_tiles(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+                                       stream)) != cudaSuccess)
+        return err;
     ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(tv, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap);
     return cudaGetLastError();

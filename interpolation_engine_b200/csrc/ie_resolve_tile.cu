@@ -1,0 +1,628 @@
+// Cooperative tile kernel of the batched `{key}` resolver (sm_100a) — the hot path.
+//
+// Replaces interpolate_inserts + get_interpdata (rust-project/src/interp.rs:31-137) for one tile of
+// IE_RESOLVE_TILE consecutive templates per CTA.  The work is split into phases that keep a warp in
+// ONE kind of work at a time (the thread-per-template v1 kernel ran at 5 of 32 active lanes):
+//
+//   P1  flat scan      all lanes stream the tile's bytes as 16-byte coalesced chunks and emit an
+//                      ordered list of brace events (SIMD-in-register byte compares, warp scan)
+//   P2  structure      one thread per template: bracket matching over its (few) events, simple-path
+//                      layers (interp.rs:45-52), leaf groups pushed on a ready queue
+//   P3  lookups        one thread per READY GROUP, level by level: hash the key (literal pieces +
+//                      already resolved child values), probe the device table, type gate, flags
+//   P4  sizes          one thread per template -> CTA scan + decoupled look-back -> compacted offsets,
+//                      plus a tile-wide table of copy segments (literal runs and values)
+//   P5  flat copy      all lanes sweep the tile's output range in 16-byte aligned chunks, gathering
+//                      each chunk from its segment(s): coalesced 16-byte stores
+//
+// Exactness: identical argument to ie_device.cuh's per-thread traversal — with every spliced value
+// free of unescaped braces and sentinel corner cases the reference's rightmost-first rewriting equals
+// bracket matching, and the reference's error is the failing group with the largest '{' position.
+// Anything else (flagged values, uneven or improper braces, sentinel collisions, capacity overflow of
+// the per-tile tables) is handed to the general kernel or to the per-thread fallback, both exact.
+#include <cuda_runtime.h>
+
+#include "ie_common.cuh"
+#include "ie_device.cuh"
+#include "ie_kernels.h"
+#include "ie_scan.cuh"
+
+namespace {
+
+using namespace ie_dev;
+
+constexpr int TT = IE_RESOLVE_TILE;  // templates per tile == threads per CTA
+constexpr int NW = TT / 32;
+constexpr int E_CAP = 1536;          // brace events per tile
+constexpr int E_WARP = E_CAP / NW;   // staging capacity per warp in P1
+constexpr int S_CAP = 1024;          // copy segments per tile
+constexpr uint32_t POS_MASK = 0x00FFFFFFu;
+constexpr uint32_t EV_SIMPLE = 0x80000000u;
+enum : uint32_t { EV_OPEN = 0, EV_CLOSE = 1, EV_ESC_OPEN = 2, EV_ESC_CLOSE = 3, EV_PUNT = 4 };
+constexpr uint32_t NONE16 = 0xFFFFu;
+enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2 };
+
+struct Smem {
+    ie_scan::TileSmemT<TT> scan;
+    uint32_t ev_pos[E_CAP];    // position in tile | type << 24 (| EV_SIMPLE on opens)
+    uint32_t ev_a[E_CAP];      // open: val_off16 of the resolved value; close: its length
+    uint16_t ev_match[E_CAP];  // partner event
+    uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level); close: unresolved children
+    union {
+        uint32_t stage[NW][E_WARP];  // P1: per-warp event staging
+        uint32_t q[2][E_CAP / 2];    // P3: ready queues (template << 16 | open event)
+        struct {
+            uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
+            uint64_t src[S_CAP];      //     its source address
+        } seg;
+    } u;
+    uint32_t t_start[TT + 1];  // template start, tile-relative
+    uint32_t t_err[TT];        // max over failing groups of (open event << 8 | IE_RES_*)
+    uint32_t t_aux[TT];        // entry index of a typed (simple path) result
+    uint32_t t_flags[TT];
+    uint16_t t_eb[TT + 1];     // first event of the template
+    uint16_t t_ne[TT];         // its events after filtering
+    uint8_t t_tag[TT];
+    uint32_t warp_cnt[NW];
+    uint32_t warp_scan[NW];
+    uint32_t q_n[2];
+    uint32_t overflow;
+};
+
+__device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 in every byte of w equal to pat's
+    const uint32_t x = w ^ pat;
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x) & 0x80808080u;
+}
+
+// Iterates the bytes of group g's key: literal template bytes and the values of its (resolved) children.
+template <class F>
+__device__ __forceinline__ void walk_key(const Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t g, F& f) {
+    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[g];
+    uint32_t e = g + 1;
+    for (;;) {
+        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        for (; pos < stop; ++pos) if (!f(__ldg(tp + pos))) return;
+        if (e == c) return;
+        const uint32_t ce = sm.ev_match[e];
+        const uint8_t* v = tv.base + (size_t)sm.ev_a[e] * 16u;
+        const uint32_t vl = sm.ev_a[ce];
+        for (uint32_t k = 0; k < vl; ++k) if (!f(__ldg(v + k))) return;
+        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        e = ce + 1;
+    }
+}
+struct Hasher {
+    uint32_t h = 0x9747b28cu, w = 0, n = 0;
+    __device__ __forceinline__ bool operator()(uint8_t b) {
+        w |= (uint32_t)b << (8 * (n & 3));
+        if ((++n & 3) == 0) { h = ie_mur_step(h, w); w = 0; }
+        return true;
+    }
+    __device__ __forceinline__ uint32_t finish() const { return ie_fmix32(((n & 3) ? ie_mur_tail(h, w) : h) ^ n); }
+};
+struct Comparer {
+    const uint8_t* s;
+    uint32_t i = 0;
+    bool ok = true;
+    __device__ __forceinline__ bool operator()(uint8_t b) {
+        if (__ldg(s + i) != b) { ok = false; return false; }
+        ++i;
+        return true;
+    }
+};
+struct ArgCheck {  // interp.rs:109: "ARG" followed by ASCII digits only
+    uint32_t i = 0;
+    bool ok = true;
+    __device__ __forceinline__ bool operator()(uint8_t b) {
+        const bool good = i == 0 ? b == 'A' : i == 1 ? b == 'R' : i == 2 ? b == 'G' : (b >= '0' && b <= '9');
+        ++i;
+        if (!good) ok = false;
+        return good;
+    }
+};
+
+// Calls f(src, len, is_value) for each non-empty piece of group g's key (error payloads).
+template <class F>
+__device__ __forceinline__ void walk_key_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t g, F& f) {
+    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[g];
+    uint32_t e = g + 1;
+    for (;;) {
+        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        if (stop > pos) f(tp + pos, stop - pos);
+        if (e == c) return;
+        const uint32_t ce = sm.ev_match[e];
+        if (sm.ev_a[ce]) f(tv.base + (size_t)sm.ev_a[e] * 16u, sm.ev_a[ce]);
+        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        e = ce + 1;
+    }
+}
+
+// Calls f(src, len) for each non-empty output piece of a successfully resolved template.
+template <class F>
+__device__ __forceinline__ void walk_output_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t t, F& f) {
+    uint32_t pos = sm.t_start[t];
+    const uint32_t end = sm.t_start[t + 1];
+    uint32_t e = sm.t_eb[t];
+    const uint32_t ee = e + sm.t_ne[t];
+    while (e < ee) {
+        const uint32_t o = sm.ev_pos[e] & POS_MASK;
+        if (o > pos) f(tp + pos, o - pos);
+        const uint32_t ce = sm.ev_match[e];
+        if (sm.ev_a[ce]) f(tv.base + (size_t)sm.ev_a[e] * 16u, sm.ev_a[ce]);
+        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        e = ce + 1;
+    }
+    if (end > pos) f(tp + pos, end - pos);
+}
+
+struct PieceCount {
+    uint32_t bytes = 0, n = 0;
+    __device__ __forceinline__ void operator()(const uint8_t*, uint32_t len) { bytes += len; ++n; }
+};
+struct PieceEmit {
+    Smem& sm;
+    uint32_t idx, off;
+    __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
+        sm.u.seg.out[idx] = off;
+        sm.u.seg.src[idx] = (uint64_t)(uintptr_t)src;
+        ++idx;
+        off += len;
+    }
+};
+struct PieceCopy {  // per-thread byte copy (segment-table overflow fallback)
+    uint8_t* dst;
+    __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
+        for (uint32_t k = 0; k < len; ++k) dst[k] = __ldg(src + k);
+        dst += len;
+    }
+};
+
+__device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g, int nxt) {
+    const uint32_t c = sm.ev_match[g];
+    const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
+    Hasher hs;
+    walk_key(sm, tv, tp, g, hs);
+    const uint32_t klen = hs.n;
+    uint32_t err = 0;
+    const IeSlot* s = nullptr;
+    if (klen == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
+    else {
+        const uint32_t h = hs.finish();
+        const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
+        uint32_t idx = h & tv.mask;
+        for (;;) {
+            const IeSlot* cand = slots + idx;
+            const uint4 hd = __ldg(reinterpret_cast<const uint4*>(cand));
+            if (hd.y == IE_SLOT_EMPTY) break;
+            if (hd.x == h && hd.y == klen) {
+                Comparer cmp{tv.base + (size_t)__ldg(&cand->key_off16) * 16u};
+                walk_key(sm, tv, tp, g, cmp);
+                if (cmp.ok) { s = cand; break; }
+            }
+            idx = (idx + 1) & tv.mask;
+        }
+        if (!s) {
+            ArgCheck ac;
+            walk_key(sm, tv, tp, g, ac);
+            err = (ac.ok && klen >= 3) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;  // interp.rs:109-116, :136
+        }
+    }
+    uint32_t tf = 0;
+    if (s) {
+        tf = __ldg(&s->tagflags);
+        if (!simple) {
+            if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
+            else if ((tf >> 8) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
+        }
+    }
+    if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
+    sm.ev_a[g] = __ldg(&s->val_off16);
+    sm.ev_a[c] = __ldg(&s->val_len);
+    const uint32_t parent = sm.ev_c[g];
+    if (parent == NONE16) {
+        if (simple) { sm.t_aux[t] = __ldg(&s->entry); sm.t_tag[t] = (uint8_t)(tf & 0xFF); }
+        return;
+    }
+    // one child of `parent` resolved: pending counters are u16, decremented through the enclosing word
+    const uint32_t pc = sm.ev_match[parent];
+    uint32_t* word = reinterpret_cast<uint32_t*>(sm.ev_c) + (pc >> 1);
+    const uint32_t shift = (pc & 1) * 16;
+    const uint32_t old = atomicSub(word, 1u << shift);
+    if (((old >> shift) & 0xFFFFu) == 1u) {
+        const uint32_t k = atomicAdd(&sm.q_n[nxt], 1u);
+        sm.u.q[nxt][k] = (t << 16) | parent;
+    }
+}
+
+__global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+                                                             const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
+                                                             uint64_t out_cap, uint64_t* __restrict__ out_offs,
+                                                             uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
+                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info) {
+    __shared__ Smem sm;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = ie_scan::acquire_tile(sm.scan, ws.tile_counter);
+    const uint64_t i0 = (uint64_t)tile * TT;
+    const uint32_t nt = (uint32_t)min((uint64_t)TT, n - i0);
+    const uint64_t i = i0 + tid;
+    const bool active = tid < nt;
+    const bool last_tile = (uint64_t)tile + 1 == (n + TT - 1) / TT;
+
+    // ---- P0: tile extent ----------------------------------------------------------------------
+    const uint64_t off0 = __ldg(offs + i0);
+    const uint64_t off_end = __ldg(offs + i0 + nt);
+    const uint64_t my_off = active ? __ldg(offs + i) : off_end;
+    const uint8_t* __restrict__ tp = tmpl + off0;
+    const uint64_t tile_bytes64 = off_end - off0;
+    sm.t_start[tid] = (uint32_t)(my_off - off0);
+    if (tid == 0) {
+        sm.t_start[TT] = (uint32_t)tile_bytes64;
+        sm.q_n[0] = 0; sm.q_n[1] = 0; sm.overflow = 0;
+    }
+    sm.t_err[tid] = 0;
+    sm.t_flags[tid] = 0;
+    __syncthreads();
+    bool fallback = tile_bytes64 > POS_MASK;  // positions are 24-bit: huge tiles use the per-thread path
+    const uint32_t tile_bytes = (uint32_t)tile_bytes64;
+
+    // ---- P1: flat brace scan --------------------------------------------------------------------
+    if (!fallback) {
+        const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
+        const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
+        const uint32_t n_chunks = (lead + tile_bytes + 15) >> 4;
+        const uint32_t cw = (n_chunks + NW - 1) / NW;
+        const uint32_t cbeg = warp * cw, cend = min(n_chunks, cbeg + cw);
+        uint32_t wbase = 0;
+        for (uint32_t c0 = cbeg; c0 < cend; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool have = c < cend;
+            uint32_t w[4] = {0, 0, 0, 0};
+            const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;  // tile position of the chunk's first byte
+            if (have) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t keep = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int32_t p = p0 + 4 * k + j;
+                            if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
+                        }
+                        w[k] &= keep;
+                    }
+                }
+            }
+            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w[3], 1);
+            if (lane == 0) prev = (have && c > 0) ? __ldg(reinterpret_cast<const uint32_t*>(a0 + (size_t)c * 16 - 4)) : 0u;
+            uint32_t mo[4], mc[4], esc[4], mp[4];
+            uint32_t cnt = 0;
+            uint32_t carry = ((prev >> 24) == '\\') ? 0x80u : 0u;  // "previous byte is a backslash", byte 0 of word 0
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mo[k] = eqmask(w[k], 0x7B7B7B7Bu);
+                mc[k] = eqmask(w[k], 0x7D7D7D7Du);
+                const uint32_t mb = eqmask(w[k], 0x5C5C5C5Cu);
+                const uint32_t pb = (mb << 8) | carry;
+                carry = mb >> 24;
+                esc[k] = (mo[k] | mc[k]) & pb;
+                mp[k] = 0;
+                uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
+                while (me) {  // rare: confirm E3 80 A0 (literal U+3020 collides with the reference's sentinels)
+                    const int bit = __ffs(me) - 1;
+                    me &= me - 1;
+                    const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
+                    if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0) mp[k] |= 1u << bit;
+                }
+                cnt += __popc(mo[k] | mc[k] | mp[k]);
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            const uint32_t round_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (cnt) {
+                uint32_t idx = wbase + incl - cnt;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t m = mo[k] | mc[k] | mp[k];
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
+                        uint32_t type;
+                        if ((mp[k] >> bit) & 1u) type = EV_PUNT;
+                        else {
+                            const bool open = (mo[k] >> bit) & 1u, escd = (esc[k] >> bit) & 1u;
+                            type = escd ? (open ? EV_ESC_OPEN : EV_ESC_CLOSE) : (open ? EV_OPEN : EV_CLOSE);
+                            if (type == EV_ESC_CLOSE && p >= 2) {  // ".\}" / "}\}": '.' + "〠." reads as ".〠" + '.'
+                                const uint8_t b2 = __ldg(tp + p - 2);
+                                if (b2 == '.' || b2 == '}') type = EV_PUNT;
+                            }
+                        }
+                        if (idx < (uint32_t)E_WARP) sm.u.stage[warp][idx] = p | (type << 24);
+                        ++idx;
+                    }
+                }
+            }
+            wbase += round_total;
+        }
+        if (lane == 0) {
+            sm.warp_cnt[warp] = min(wbase, (uint32_t)E_WARP);
+            if (wbase > (uint32_t)E_WARP) sm.overflow = 1;
+        }
+    }
+    __syncthreads();
+    fallback = fallback || sm.overflow != 0;
+
+    if (fallback) {
+        // ---- per-thread exact path for tiles that do not fit the tile tables -----------------------
+        uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
+        bool verbatim = false;
+        const uint8_t* t = tmpl + my_off;
+        if (active) {
+            const uint64_t b = __ldg(offs + i + 1);
+            if (b - my_off > 0x7FFFFFFFull) status = IE_RES_LIMIT;
+            else {
+                len = (uint32_t)(b - my_off);
+                const Prescan ps = prescan(t, len);
+                m0 = ps.m0;
+                if (ps.punt) status = IE_RES_PUNT;
+                else if (ps.n_open == 0) { verbatim = true; olen = len; }
+                else fast_traverse<false>(tv, t, len, m0, nullptr, 0, olen, status, aux);
+            }
+            if (status == IE_RES_PUNT) { olen = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i; }
+        }
+        uint64_t tile_end;
+        const uint64_t off = ie_scan::exclusive_prefix(sm.scan, ws.tile_state, tile, olen, &tile_end);
+        if (tid == 0 && last_tile) {
+            info->n = n;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
+        }
+        if (!active) return;
+        out_offs[i] = off; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+        if (olen == 0) return;
+        if (off + olen > out_cap) { *ws.overflow = 1u; return; }
+        if (verbatim) { uint8_t* wr = out + off; for (uint32_t k = 0; k < len; ++k) wr[k] = __ldg(t + k); }
+        else { uint32_t l2, s2, a2; fast_traverse<true>(tv, t, len, m0, out + off + olen, status & 0xFF, l2, s2, a2); }
+        return;
+    }
+
+    // ---- P1b: compact the per-warp stages into one ordered event list ---------------------------------
+    uint32_t total_ev = 0;
+    {
+        uint32_t base = 0;
+#pragma unroll
+        for (int wv = 0; wv < NW; ++wv) {
+            const uint32_t cntw = sm.warp_cnt[wv];
+            for (uint32_t k = tid; k < cntw; k += TT) sm.ev_pos[base + k] = sm.u.stage[wv][k];
+            base += cntw;
+        }
+        total_ev = base;
+    }
+    __syncthreads();
+
+    // ---- P2: per-template structure -----------------------------------------------------------------
+    {
+        uint32_t lo = 0, hi = total_ev;  // first event at or after this template's start
+        const uint32_t start = sm.t_start[tid];
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((sm.ev_pos[mid] & POS_MASK) < start) lo = mid + 1; else hi = mid;
+        }
+        sm.t_eb[tid] = (uint16_t)lo;
+        if (tid == 0) sm.t_eb[TT] = (uint16_t)total_ev;
+    }
+    __syncthreads();
+    if (active) {
+        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
+        const uint32_t eb = sm.t_eb[tid], ee = sm.t_eb[tid + 1];
+        uint32_t wi = eb, depth = 0, n_open = 0;
+        uint16_t st_idx[MAXLVL], st_pend[MAXLVL];
+        bool punt = false, stray = false;
+        for (uint32_t e = eb; e < ee; ++e) {
+            const uint32_t x = sm.ev_pos[e];
+            const uint32_t pos = x & POS_MASK;
+            uint32_t type = (x >> 24) & 7u;
+            if (type == EV_PUNT) { punt = true; continue; }
+            if (type >= EV_ESC_OPEN) {  // an escape cannot reach across a template boundary
+                if (pos != start) continue;
+                type -= 2;
+            }
+            if (type == EV_OPEN) {
+                ++n_open;
+                if (depth == MAXLVL) { punt = true; break; }
+                if (depth) ++st_pend[depth - 1];
+                sm.ev_pos[wi] = pos;
+                sm.ev_c[wi] = depth ? st_idx[depth - 1] : (uint16_t)NONE16;
+                st_idx[depth] = (uint16_t)wi; st_pend[depth] = 0;
+                ++depth; ++wi;
+            } else {
+                if (depth == 0) { stray = true; continue; }
+                --depth;
+                const uint32_t o = st_idx[depth];
+                sm.ev_pos[wi] = pos | (EV_CLOSE << 24);
+                sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
+                sm.ev_c[wi] = st_pend[depth];
+                ++wi;
+            }
+        }
+        const uint32_t ne = wi - eb;
+        sm.t_ne[tid] = (uint16_t)ne;
+        uint32_t flags = 0;
+        if (end - start > 0x00FFFFFFu) punt = true;
+        if (punt) flags = TF_PUNT;
+        else if (n_open == 0) flags = TF_VERBATIM;  // the loop at interp.rs:54 is never entered (stray '}' stay)
+        else if (stray || depth != 0) flags = TF_PUNT;  // uneven or improper nesting: general path (exact error text / panic)
+        sm.t_flags[tid] = flags;
+        if (flags == 0) {
+            // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
+            uint32_t lead = 0, trail = 0;
+            while (lead < ne && sm.ev_pos[eb + lead] == start + lead) ++lead;  // type bits 0 = open
+            while (trail < ne && sm.ev_pos[eb + ne - 1 - trail] == ((end - 1 - trail) | (EV_CLOSE << 24))) ++trail;
+            const uint32_t m0 = min(lead, trail);
+            for (uint32_t j = 0; j < m0; ++j) {
+                if (sm.ev_match[eb + j] != eb + ne - 1 - j) break;
+                sm.ev_pos[eb + j] |= EV_SIMPLE;
+            }
+            for (uint32_t e = eb; e < eb + ne; ++e)
+                if ((sm.ev_pos[e] >> 24) == EV_CLOSE && sm.ev_c[e] == 0) {
+                    const uint32_t k = atomicAdd(&sm.q_n[0], 1u);
+                    sm.u.q[0][k] = (tid << 16) | sm.ev_match[e];
+                }
+        }
+    }
+
+    // ---- P3: lookups, one thread per ready group, level by level --------------------------------------
+    int cur = 0;
+    for (;;) {
+        __syncthreads();
+        const uint32_t nq = sm.q_n[cur];
+        if (nq == 0) break;
+        for (uint32_t k = tid; k < nq; k += TT) {
+            const uint32_t item = sm.u.q[cur][k];
+            resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu, cur ^ 1);
+        }
+        __syncthreads();
+        if (tid == 0) sm.q_n[cur] = 0;
+        cur ^= 1;
+    }
+
+    // ---- P4: sizes, offsets, copy segments ---------------------------------------------------------------
+    uint32_t olen = 0, nseg = 0, status = IE_RES_STRING, aux = 0, err_g = 0;
+    uint32_t mode = 0;  // 0 none, 1 verbatim, 2 error key, 3 resolved
+    if (active) {
+        const uint32_t flags = sm.t_flags[tid];
+        const uint32_t err = sm.t_err[tid];
+        if (flags & TF_PUNT) {
+            status = IE_RES_PUNT;
+            ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i;
+        } else if (flags & TF_VERBATIM) {
+            olen = sm.t_start[tid + 1] - sm.t_start[tid];
+            nseg = olen ? 1 : 0;
+            mode = 1;
+        } else if (err) {
+            status = err & 0xFF;
+            err_g = err >> 8;
+            PieceCount pc;
+            walk_key_pieces(sm, tv, tp, err_g, pc);
+            olen = pc.bytes; nseg = pc.n;
+            mode = 2;
+        } else {
+            PieceCount pc;
+            walk_output_pieces(sm, tv, tp, tid, pc);
+            olen = pc.bytes; nseg = pc.n;
+            mode = 3;
+            if (sm.ev_pos[sm.t_eb[tid]] & EV_SIMPLE) {  // the whole template is one group: typed result
+                status = IE_RES_TYPED | ((uint32_t)sm.t_tag[tid] << 8);
+                aux = sm.t_aux[tid];
+            }
+        }
+    }
+    uint64_t tile_end, tile_begin;
+    const uint64_t off = ie_scan::exclusive_prefix(sm.scan, ws.tile_state, tile, olen, &tile_end, &tile_begin);
+    if (tid == 0 && last_tile) {
+        info->n = n;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
+    }
+    // tile-local exclusive scan of segment counts
+    uint32_t sincl = nseg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, sincl, d);
+        if ((int)lane >= d) sincl += y;
+    }
+    if (lane == 31) sm.warp_scan[warp] = sincl;
+    __syncthreads();
+    uint32_t sbase = 0, total_seg = 0;
+#pragma unroll
+    for (int wv = 0; wv < NW; ++wv) {
+        if (wv < (int)warp) sbase += sm.warp_scan[wv];
+        total_seg += sm.warp_scan[wv];
+    }
+    sbase += sincl - nseg;
+    const uint32_t tile_out = (uint32_t)(tile_end - tile_begin);
+    const bool fits = tile_end <= out_cap;
+    if (active) {
+        out_offs[i] = off; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+    }
+    if (!fits) { if (tid == 0) *ws.overflow = 1u; return; }
+    if (total_seg > (uint32_t)S_CAP || tile_end - tile_begin > 0xFFFFFFFFull) {
+        // segment table overflow: every thread copies its own pieces
+        if (active && olen) {
+            PieceCopy cp{out + off};
+            if (mode == 1) cp(tp + sm.t_start[tid], olen);
+            else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, cp);
+            else if (mode == 3) walk_output_pieces(sm, tv, tp, tid, cp);
+        }
+        return;
+    }
+    if (active && nseg) {
+        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin)};
+        if (mode == 1) em(tp + sm.t_start[tid], olen);
+        else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
+        else walk_output_pieces(sm, tv, tp, tid, em);
+    }
+    if (tid == 0) sm.u.seg.out[total_seg] = tile_out;
+    __syncthreads();
+
+    // ---- P5: flat 16-byte output sweep -----------------------------------------------------------------
+    if (tile_out == 0) return;
+    uint8_t* gout = out + tile_begin;
+    const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
+    const uint32_t olead = (uint32_t)((uintptr_t)gout - o0);
+    const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
+    for (uint32_t c = tid; c < o_chunks; c += TT) {
+        const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
+        const uint32_t xb = x0s < 0 ? 0u : (uint32_t)x0s;
+        const uint32_t xe = min(tile_out, (uint32_t)(x0s + 16));
+        uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
+        }
+        uint32_t sidx = lo;
+        const uint32_t s_out = sm.u.seg.out[sidx], s_end = sm.u.seg.out[sidx + 1];
+        if (xe - xb == 16 && s_end >= xe) {
+            // the whole chunk comes from one segment: 5 aligned words + funnel shifts -> one 16-byte store
+            const uintptr_t src = (uintptr_t)sm.u.seg.src[sidx] + (xb - s_out);
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(src & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(src & 3) * 8;
+            const uint32_t a = __ldg(aw), b = __ldg(aw + 1), cc = __ldg(aw + 2), d = __ldg(aw + 3);
+            uint4 r;
+            if (sh == 0) r = make_uint4(a, b, cc, d);
+            else {
+                const uint32_t e5 = __ldg(aw + 4);
+                r = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, cc, sh), __funnelshift_r(cc, d, sh), __funnelshift_r(d, e5, sh));
+            }
+            *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = r;
+        } else {
+            uint32_t x = xb;
+            uint32_t so = s_out, se = s_end;
+            while (x < xe) {
+                while (se <= x) { ++sidx; so = se; se = sm.u.seg.out[sidx + 1]; }
+                const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (x - so);
+                const uint32_t m = min(xe, se) - x;
+                for (uint32_t k = 0; k < m; ++k) gout[x + k] = __ldg(src + k);
+                x += m;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                                    uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                    const IeWorkspace& ws, ie_batch_info* d_info, cudaStream_t stream) {
+    const uint64_t tiles = (n + TT - 1) / TT;
+    ie_resolve_tile_kernel<<<(unsigned)tiles, TT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
+                                                              d_aux, ws, d_info);
+    return cudaGetLastError();
+}

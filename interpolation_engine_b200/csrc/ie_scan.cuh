@@ -19,24 +19,29 @@ __device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-struct TileSmem {
+template <int NT = IE_TILE>
+struct TileSmemT {
     uint32_t tile;
-    uint64_t warp_tot[IE_TILE / 32];
+    uint64_t warp_tot[NT / 32];
     uint64_t base;
 };
+using TileSmem = TileSmemT<IE_TILE>;
 
 // Tile ids are handed out in CTA start order, so every predecessor of a tile is already resident
 // or finished when it waits on it: forward progress does not depend on the block scheduler.
-__device__ __forceinline__ uint32_t acquire_tile(TileSmem& sm, uint32_t* tile_counter) {
+template <int NT>
+__device__ __forceinline__ uint32_t acquire_tile(TileSmemT<NT>& sm, uint32_t* tile_counter) {
     if (threadIdx.x == 0) sm.tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     return sm.tile;
 }
 
-// Returns the global exclusive prefix of `len` for this thread; *grand_total is the inclusive
-// prefix at the end of this tile (valid on every thread).  Must be called by all IE_TILE threads.
-__device__ __forceinline__ uint64_t exclusive_prefix(TileSmem& sm, uint64_t* tile_state, uint32_t tile, uint64_t len,
-                                                     uint64_t* tile_end) {
+// Returns the global exclusive prefix of `len` for this thread; *tile_end is the inclusive prefix
+// at the end of this tile and *tile_begin the exclusive prefix at its start (valid on every
+// thread).  Must be called by all NT threads of the CTA.
+template <int NT>
+__device__ __forceinline__ uint64_t exclusive_prefix(TileSmemT<NT>& sm, uint64_t* tile_state, uint32_t tile, uint64_t len,
+                                                     uint64_t* tile_end, uint64_t* tile_begin = nullptr) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t incl = len;
 #pragma unroll
@@ -48,7 +53,7 @@ __device__ __forceinline__ uint64_t exclusive_prefix(TileSmem& sm, uint64_t* til
     __syncthreads();
     uint64_t warp_off = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < IE_TILE / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
         const uint64_t x = sm.warp_tot[w];
         if (w < (int)warp) warp_off += x;
         tile_total += x;
@@ -81,6 +86,7 @@ __device__ __forceinline__ uint64_t exclusive_prefix(TileSmem& sm, uint64_t* til
     }
     __syncthreads();
     *tile_end = sm.base + tile_total;
+    if (tile_begin) *tile_begin = sm.base;
     return sm.base + warp_off + incl - len;
 }
 
