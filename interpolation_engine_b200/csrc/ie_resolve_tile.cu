@@ -75,6 +75,38 @@ __device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 
     return ~(t | x) & 0x80808080u;
 }
 
+
+// Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero.
+// Only aligned words that contain at least one requested byte are touched.
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* __restrict__ p, uint32_t m) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t r = (uint32_t)(a & 3);
+    const uint32_t nw = (r + m + 3) >> 2;  // aligned words covering [p, p + m), <= 5
+    const uint32_t w0 = nw > 0 ? __ldg(aw) : 0u, w1 = nw > 1 ? __ldg(aw + 1) : 0u, w2 = nw > 2 ? __ldg(aw + 2) : 0u,
+                   w3 = nw > 3 ? __ldg(aw + 3) : 0u, w4 = nw > 4 ? __ldg(aw + 4) : 0u;
+    const uint32_t sh = r * 8;
+    uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    // zero the bytes at index >= m
+    const uint32_t full = m >> 2, rem = (m & 3) * 8;
+    const uint32_t part = rem ? ((1u << rem) - 1u) : 0u;
+    v.x &= full > 0 ? 0xFFFFFFFFu : (full == 0 ? part : 0u);
+    v.y &= full > 1 ? 0xFFFFFFFFu : (full == 1 ? part : 0u);
+    v.z &= full > 2 ? 0xFFFFFFFFu : (full == 2 ? part : 0u);
+    v.w &= full > 3 ? 0xFFFFFFFFu : (full == 3 ? part : 0u);
+    return v;
+}
+// acc |= v << (8 * s bytes), s in [0, 15], as one 128-bit little-endian quantity
+__device__ __forceinline__ void or_shifted(uint4& acc, const uint4& v, uint32_t s) {
+    const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    uint64_t rlo, rhi;
+    if (s == 0) { rlo = lo; rhi = hi; }
+    else if (s < 8) { rlo = lo << (8 * s); rhi = (hi << (8 * s)) | (lo >> (64 - 8 * s)); }
+    else if (s == 8) { rlo = 0; rhi = lo; }
+    else { rlo = 0; rhi = lo << (8 * (s - 8)); }
+    acc.x |= (uint32_t)rlo; acc.y |= (uint32_t)(rlo >> 32); acc.z |= (uint32_t)rhi; acc.w |= (uint32_t)(rhi >> 32);
+}
+
 // Iterates the bytes of group g's key: literal template bytes and the values of its (resolved) children.
 template <class F>
 __device__ __forceinline__ void walk_key(const Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t g, F& f) {
@@ -180,50 +212,109 @@ struct PieceCopy {  // per-thread byte copy (segment-table overflow fallback)
     }
 };
 
+// Assembles group g's key into 16 bytes of registers (literal pieces + inline child values).
+// Returns false when the key is longer than 16 bytes (the byte-walking path handles those).
+__device__ __forceinline__ bool short_key(const Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t g, uint4& key,
+                                          uint32_t& klen) {
+    key = make_uint4(0, 0, 0, 0);
+    klen = 0;
+    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[g];
+    uint32_t e = g + 1;
+    for (;;) {
+        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        const uint32_t m = stop - pos;
+        if (klen + m > 16) return false;
+        if (m) { or_shifted(key, load_unaligned16(tp + pos, m), klen); klen += m; }
+        if (e == c) return true;
+        const uint32_t ce = sm.ev_match[e];
+        const uint32_t vl = sm.ev_a[ce];
+        if (klen + vl > 16) return false;
+        if (vl) {  // values of <= 16 bytes live zero-padded in their slot's 16-byte aligned inline area
+            or_shifted(key, __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[e] * 16u)), klen);
+            klen += vl;
+        }
+        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        e = ce + 1;
+    }
+}
+__device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) {  // == ie_hash_bytes on the same bytes
+    uint32_t h = 0x9747b28cu;
+    const uint32_t nb = klen >> 2;
+    if (nb > 0) h = ie_mur_step(h, k.x);
+    if (nb > 1) h = ie_mur_step(h, k.y);
+    if (nb > 2) h = ie_mur_step(h, k.z);
+    if (nb > 3) h = ie_mur_step(h, k.w);
+    if (klen & 3) h = ie_mur_tail(h, nb == 0 ? k.x : nb == 1 ? k.y : nb == 2 ? k.z : k.w);
+    return ie_fmix32(h ^ klen);
+}
+
 __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g, int nxt) {
     const uint32_t c = sm.ev_match[g];
     const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
-    Hasher hs;
-    walk_key(sm, tv, tp, g, hs);
-    const uint32_t klen = hs.n;
-    uint32_t err = 0;
-    const IeSlot* s = nullptr;
-    if (klen == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
-    else {
+    uint32_t err = 0, klen, val_off16 = 0, val_len = 0, tf = 0, entry = 0;
+    bool found = false;
+    uint4 key;
+    const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
+    if (short_key(sm, tv, tp, g, key, klen)) {
+        if (klen == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
+        else {
+            const uint32_t h = hash_short(key, klen);
+            uint32_t idx = h & tv.mask;
+            for (;;) {
+                // the three 16-byte pieces of the slot are independent loads: one L2 round trip per probe
+                const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
+                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2);
+                if (q0.y == IE_SLOT_EMPTY) break;
+                if (q0.x == h && q0.y == klen && q2.x == key.x && q2.y == key.y && q2.z == key.z && q2.w == key.w) {
+                    found = true; val_len = q0.z; entry = q0.w; val_off16 = q1.y; tf = q1.z;
+                    break;
+                }
+                idx = (idx + 1) & tv.mask;
+            }
+            if (!found) {  // interp.rs:109-116, :136
+                bool arg = klen >= 3 && (key.x & 0x00FFFFFFu) == 0x00475241u;  // "ARG"
+                const uint32_t kw[4] = {key.x, key.y, key.z, key.w};
+                for (uint32_t j = 3; arg && j < klen; ++j) {
+                    const uint32_t b = (kw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    arg = b >= '0' && b <= '9';
+                }
+                err = arg ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
+            }
+        }
+    } else {
+        Hasher hs;
+        walk_key(sm, tv, tp, g, hs);
+        klen = hs.n;
         const uint32_t h = hs.finish();
-        const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
         uint32_t idx = h & tv.mask;
         for (;;) {
-            const IeSlot* cand = slots + idx;
-            const uint4 hd = __ldg(reinterpret_cast<const uint4*>(cand));
-            if (hd.y == IE_SLOT_EMPTY) break;
-            if (hd.x == h && hd.y == klen) {
-                Comparer cmp{tv.base + (size_t)__ldg(&cand->key_off16) * 16u};
+            const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
+            const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+            if (q0.y == IE_SLOT_EMPTY) break;
+            if (q0.x == h && q0.y == klen) {
+                Comparer cmp{tv.base + (size_t)q1.x * 16u};
                 walk_key(sm, tv, tp, g, cmp);
-                if (cmp.ok) { s = cand; break; }
+                if (cmp.ok) { found = true; val_len = q0.z; entry = q0.w; val_off16 = q1.y; tf = q1.z; break; }
             }
             idx = (idx + 1) & tv.mask;
         }
-        if (!s) {
+        if (!found) {
             ArgCheck ac;
             walk_key(sm, tv, tp, g, ac);
-            err = (ac.ok && klen >= 3) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;  // interp.rs:109-116, :136
+            err = ac.ok ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
         }
     }
-    uint32_t tf = 0;
-    if (s) {
-        tf = __ldg(&s->tagflags);
-        if (!simple) {
-            if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
-            else if ((tf >> 8) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
-        }
+    if (found && !simple) {
+        if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
+        else if ((tf >> 8) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
     }
     if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
-    sm.ev_a[g] = __ldg(&s->val_off16);
-    sm.ev_a[c] = __ldg(&s->val_len);
+    sm.ev_a[g] = val_off16;
+    sm.ev_a[c] = val_len;
     const uint32_t parent = sm.ev_c[g];
     if (parent == NONE16) {
-        if (simple) { sm.t_aux[t] = __ldg(&s->entry); sm.t_tag[t] = (uint8_t)(tf & 0xFF); }
+        if (simple) { sm.t_aux[t] = entry; sm.t_tag[t] = (uint8_t)(tf & 0xFF); }
         return;
     }
     // one child of `parent` resolved: pending counters are u16, decremented through the enclosing word
@@ -588,29 +679,24 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
             if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
         }
         uint32_t sidx = lo;
-        const uint32_t s_out = sm.u.seg.out[sidx], s_end = sm.u.seg.out[sidx + 1];
-        if (xe - xb == 16 && s_end >= xe) {
-            // the whole chunk comes from one segment: 5 aligned words + funnel shifts -> one 16-byte store
-            const uintptr_t src = (uintptr_t)sm.u.seg.src[sidx] + (xb - s_out);
-            const uint32_t* aw = reinterpret_cast<const uint32_t*>(src & ~(uintptr_t)3);
-            const uint32_t sh = (uint32_t)(src & 3) * 8;
-            const uint32_t a = __ldg(aw), b = __ldg(aw + 1), cc = __ldg(aw + 2), d = __ldg(aw + 3);
-            uint4 r;
-            if (sh == 0) r = make_uint4(a, b, cc, d);
-            else {
-                const uint32_t e5 = __ldg(aw + 4);
-                r = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, cc, sh), __funnelshift_r(cc, d, sh), __funnelshift_r(d, e5, sh));
-            }
-            *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = r;
-        } else {
-            uint32_t x = xb;
-            uint32_t so = s_out, se = s_end;
-            while (x < xe) {
-                while (se <= x) { ++sidx; so = se; se = sm.u.seg.out[sidx + 1]; }
-                const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (x - so);
-                const uint32_t m = min(xe, se) - x;
-                for (uint32_t k = 0; k < m; ++k) gout[x + k] = __ldg(src + k);
-                x += m;
+        uint32_t so = sm.u.seg.out[sidx], se = sm.u.seg.out[sidx + 1];
+        // gather the chunk from its piece(s): unaligned 16-byte loads shifted into place
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        uint32_t x = xb;
+        for (;;) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (x - so);
+            const uint32_t m = min(xe, se) - x;
+            or_shifted(acc, load_unaligned16(src, m), (uint32_t)((int32_t)x - x0s));
+            x += m;
+            if (x >= xe) break;
+            ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
+        }
+        if (xe - xb == 16) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
+        else {  // first / last chunk of the tile: only the bytes that belong to it
+            const uint32_t aw4[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (uint32_t p = xb; p < xe; ++p) {
+                const uint32_t j = (uint32_t)((int32_t)p - x0s);
+                gout[p] = (uint8_t)(aw4[j >> 2] >> (8 * (j & 3)));
             }
         }
     }
