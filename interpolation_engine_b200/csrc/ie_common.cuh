@@ -26,18 +26,23 @@
 // internal per-template status while a batch is in flight
 #define IE_RES_PUNT 0xFF  // fast path declined; the general kernel resolves it
 
+// The first 16 bytes hold everything a hit needs besides the key itself, so a probe is two
+// independent 16-byte loads (header + inline key) = one L2 round trip.
 struct __align__(16) IeSlot {
     uint32_t hash;       // murmur3_32(key)
     uint32_t key_len;    // IE_SLOT_EMPTY when free
-    uint32_t val_len;
-    uint32_t entry;      // index of the insert in the caller's packed arrays (IE_AUX_NONE: clock key)
-    uint32_t key_off16;  // key bytes at base + 16 * key_off16
+    uint32_t vl_tf;      // value length (26 bits) | tag << 26 | value flags << 29
     uint32_t val_off16;  // value bytes at base + 16 * val_off16
-    uint32_t tagflags;   // tag | flags << 8
-    uint32_t pad;
+    uint32_t entry;      // index of the insert in the caller's packed arrays (n, n+1: clock keys)
+    uint32_t key_off16;  // key bytes at base + 16 * key_off16
+    uint32_t pad[2];
     uint8_t key_inline[IE_INLINE_BYTES];
     uint8_t val_inline[IE_INLINE_BYTES];
 };
+#define IE_VLEN_MAX 0x03FFFFFFu
+#define IE_SLOT_VLEN(x) ((x) & IE_VLEN_MAX)
+#define IE_SLOT_TAG(x) (((x) >> 26) & 7u)
+#define IE_SLOT_FLAGS(x) ((x) >> 29)
 static_assert(sizeof(IeSlot) == 64, "slot must be 64 bytes");
 
 struct IeTableView {

@@ -18,7 +18,7 @@ __device__ __forceinline__ const IeSlot* ie_lookup(const IeTableView& tv, const 
     uint32_t idx = h & tv.mask;
     for (;;) {
         const IeSlot* s = slots + idx;
-        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(s));  // hash, key_len, val_len, entry
+        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(s));  // hash, key_len, vl_tf, val_off16
         if (hd.y == IE_SLOT_EMPTY) return nullptr;
         if (hd.x == h && hd.y == len) {
             const uint8_t* stored = tv.base + (size_t)s->key_off16 * 16u;
@@ -120,9 +120,9 @@ __device__ __forceinline__ void fast_traverse(const IeTableView& tv, const uint8
                 s = ie_lookup(tv, key, klen);
                 if (!s) err = is_arg_key(key, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
                 else if (!simple_layer) {
-                    const uint32_t tf = s->tagflags;
-                    if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;
-                    else if ((tf >> 8) & IE_VF_ANY) { status = IE_RES_PUNT; break; }
+                    const uint32_t tf = s->vl_tf;
+                    if (!tag_splices(IE_SLOT_TAG(tf))) err = IE_RES_UNSUPPORTED;
+                    else if (IE_SLOT_FLAGS(tf) & IE_VF_ANY) { status = IE_RES_PUNT; break; }
                 }
             }
             if (err) {
@@ -131,14 +131,14 @@ __device__ __forceinline__ void fast_traverse(const IeTableView& tv, const uint8
                 break;
             }
             ktop = mark;
-            const uint32_t vlen = s->val_len;
+            const uint32_t vlen = IE_SLOT_VLEN(s->vl_tf);
             const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
             if (lvl) {
                 if (ktop < vlen) { status = IE_RES_PUNT; break; }
                 ktop -= vlen;
                 for (uint32_t i = 0; i < vlen; ++i) kbuf[ktop + i] = __ldg(v + i);
             } else if (simple_layer) {
-                status = IE_RES_TYPED | ((s->tagflags & 0xFF) << 8);
+                status = IE_RES_TYPED | (IE_SLOT_TAG(s->vl_tf) << 8);
                 aux = s->entry;
                 olen = vlen;
                 if (WRITE) for (uint32_t i = 0; i < vlen; ++i) wend[(int)i - (int)vlen] = __ldg(v + i);

@@ -178,12 +178,12 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, 
                 if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }
                 const IeSlot* s = ie_lookup(tv, kscr, klen);
                 if (!s) { status = is_arg_key(kscr, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
-                if (!tag_splices(s->tagflags & 0xFF)) { status = IE_RES_UNSUPPORTED; break; }
+                if (!tag_splices(IE_SLOT_TAG(s->vl_tf))) { status = IE_RES_UNSUPPORTED; break; }
                 payload = nullptr; payload_len = 0;
                 ttop = idx + 1; --t_close; --in_open; --f.pos;
                 if (++expansions > max_expansions) { status = IE_RES_LIMIT; break; }
                 if (f.pos == 0) --nf;
-                const uint32_t vlen = s->val_len;
+                const uint32_t vlen = IE_SLOT_VLEN(s->vl_tf);
                 if (vlen) {
                     if (nf == MAXF) { status = IE_RES_LIMIT; break; }
                     const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, 
                         const IeSlot* s = ie_lookup(tv, key, klen);
                         if (!s) { status = is_arg_key(key, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
                         key = tv.base + (size_t)s->val_off16 * 16u;
-                        klen = s->val_len;
+                        klen = IE_SLOT_VLEN(s->vl_tf);
                         payload = key; payload_len = klen;
-                        status = IE_RES_TYPED | ((s->tagflags & 0xFF) << 8);
+                        status = IE_RES_TYPED | (IE_SLOT_TAG(s->vl_tf) << 8);
                         aux = s->entry;
                     }
                 }
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) ie_lookup_kernel(IeTableView tv, const ui
     const uint64_t a = offs[k];
     const uint32_t len = (uint32_t)(offs[k + 1] - a);
     const IeSlot* s = len ? ie_lookup(tv, keys + a, len) : nullptr;
-    tag_out[k] = s ? (int32_t)(s->tagflags & 0xFF) : -1;
+    tag_out[k] = s ? (int32_t)IE_SLOT_TAG(s->vl_tf) : -1;
     entry_out[k] = s ? s->entry : IE_AUX_NONE;
 }
 

@@ -4,12 +4,13 @@
 // IE_RESOLVE_TILE consecutive templates per CTA.  The work is split into phases that keep a warp in
 // ONE kind of work at a time (the thread-per-template v1 kernel ran at 5 of 32 active lanes):
 //
-//   P1  flat scan      all lanes stream the tile's bytes as 16-byte coalesced chunks and emit an
-//                      ordered list of brace events (SIMD-in-register byte compares, warp scan)
-//   P2  structure      one thread per template: bracket matching over its (few) events, simple-path
-//                      layers (interp.rs:45-52), leaf groups pushed on a ready queue
-//   P3  lookups        one thread per READY GROUP, level by level: hash the key (literal pieces +
-//                      already resolved child values), probe the device table, type gate, flags
+//   P1  flat scan      all lanes stream the tile's bytes as 16-byte coalesced chunks; SIMD-in-register
+//                      byte compares give one 32-bit brace mask per chunk (2 bits per byte), stored
+//                      direct-mapped in shared memory — no atomics, no compaction, no search
+//   P2  structure      one thread per template: enumerates the set bits of its chunks, bracket
+//                      matching, simple-path layers (interp.rs:45-52), leaf groups -> ready queue
+//   P3  lookups        one thread per READY GROUP, level by level: key assembled in registers
+//                      (literal pieces + inline child values), murmur3, one L2 round trip per probe
 //   P4  sizes          one thread per template -> CTA scan + decoupled look-back -> compacted offsets,
 //                      plus a tile-wide table of copy segments (literal runs and values)
 //   P5  flat copy      all lanes sweep the tile's output range in 16-byte aligned chunks, gathering
@@ -31,41 +32,45 @@ namespace {
 
 using namespace ie_dev;
 
-constexpr int TT = IE_RESOLVE_TILE;  // templates per tile == threads per CTA
-constexpr int NW = TT / 32;
+constexpr int TT = IE_RESOLVE_TILE;  // templates per tile
+constexpr int NT = 256;              // threads per CTA
+constexpr int NW = NT / 32;
 constexpr int E_CAP = 1536;          // brace events per tile
-constexpr int E_WARP = E_CAP / NW;   // staging capacity per warp in P1
+constexpr int Q_CAP = E_CAP / 2;     // groups per tile
+constexpr int M_CAP = 2304;          // 16-byte chunks per tile (36 KiB of template text)
 constexpr int S_CAP = 1024;          // copy segments per tile
+constexpr int B_CAP = 1024;          // 64-byte output blocks with a segment index (64 KiB of output)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
-enum : uint32_t { EV_OPEN = 0, EV_CLOSE = 1, EV_ESC_OPEN = 2, EV_ESC_CLOSE = 3, EV_PUNT = 4 };
+constexpr uint32_t EV_CLOSE = 1u << 24;
 constexpr uint32_t NONE16 = 0xFFFFu;
 enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2 };
 
 struct Smem {
-    ie_scan::TileSmemT<TT> scan;
-    uint32_t ev_pos[E_CAP];    // position in tile | type << 24 (| EV_SIMPLE on opens)
+    ie_scan::TileSmemT<NT> scan;
+    uint32_t ev_pos[E_CAP];    // position in tile | EV_CLOSE (| EV_SIMPLE on opens)
     uint32_t ev_a[E_CAP];      // open: val_off16 of the resolved value; close: its length
     uint16_t ev_match[E_CAP];  // partner event
     uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level); close: unresolved children
+    uint32_t q[2][Q_CAP];      // P3 ready queues (template << 16 | open event)
     union {
-        uint32_t stage[NW][E_WARP];  // P1: per-warp event staging
-        uint32_t q[2][E_CAP / 2];    // P3: ready queues (template << 16 | open event)
+        uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
         struct {
             uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
             uint64_t src[S_CAP];      //     its source address
+            uint16_t blk[B_CAP];      //     segment covering output byte 64 * b
         } seg;
     } u;
     uint32_t t_start[TT + 1];  // template start, tile-relative
     uint32_t t_err[TT];        // max over failing groups of (open event << 8 | IE_RES_*)
     uint32_t t_aux[TT];        // entry index of a typed (simple path) result
     uint32_t t_flags[TT];
-    uint16_t t_eb[TT + 1];     // first event of the template
-    uint16_t t_ne[TT];         // its events after filtering
+    uint16_t t_eb[TT];         // first event of the template
+    uint16_t t_ne[TT];         // its events
     uint8_t t_tag[TT];
-    uint32_t warp_cnt[NW];
     uint32_t warp_scan[NW];
     uint32_t q_n[2];
+    uint32_t ev_n;             // events allocated
     uint32_t overflow;
 };
 
@@ -74,7 +79,11 @@ __device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 
     const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(t | x) & 0x80808080u;
 }
-
+// 0x80-per-byte flags `o` (open) and `c` (close) of one word -> 8 bits, 2 per byte (open, close)
+__device__ __forceinline__ uint32_t pack2(uint32_t o, uint32_t c) {
+    const uint32_t t = (o >> 7) | (c >> 6);
+    return (t * 0x01041040u) >> 24;
+}
 
 // Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero.
 // Only aligned words that contain at least one requested byte are touched.
@@ -87,7 +96,6 @@ __device__ __forceinline__ uint4 load_unaligned16(const uint8_t* __restrict__ p,
                    w3 = nw > 3 ? __ldg(aw + 3) : 0u, w4 = nw > 4 ? __ldg(aw + 4) : 0u;
     const uint32_t sh = r * 8;
     uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-    // zero the bytes at index >= m
     const uint32_t full = m >> 2, rem = (m & 3) * 8;
     const uint32_t part = rem ? ((1u << rem) - 1u) : 0u;
     v.x &= full > 0 ? 0xFFFFFFFFu : (full == 0 ? part : 0u);
@@ -155,7 +163,7 @@ struct ArgCheck {  // interp.rs:109: "ARG" followed by ASCII digits only
     }
 };
 
-// Calls f(src, len, is_value) for each non-empty piece of group g's key (error payloads).
+// Calls f(src, len) for each non-empty piece of group g's key (error payloads).
 template <class F>
 __device__ __forceinline__ void walk_key_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t g, F& f) {
     uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
@@ -171,7 +179,6 @@ __device__ __forceinline__ void walk_key_pieces(const Smem& sm, const IeTableVie
         e = ce + 1;
     }
 }
-
 // Calls f(src, len) for each non-empty output piece of a successfully resolved template.
 template <class F>
 __device__ __forceinline__ void walk_output_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t t, F& f) {
@@ -189,7 +196,6 @@ __device__ __forceinline__ void walk_output_pieces(const Smem& sm, const IeTable
     }
     if (end > pos) f(tp + pos, end - pos);
 }
-
 struct PieceCount {
     uint32_t bytes = 0, n = 0;
     __device__ __forceinline__ void operator()(const uint8_t*, uint32_t len) { bytes += len; ++n; }
@@ -197,9 +203,12 @@ struct PieceCount {
 struct PieceEmit {
     Smem& sm;
     uint32_t idx, off;
+    bool index_blocks;
     __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
         sm.u.seg.out[idx] = off;
         sm.u.seg.src[idx] = (uint64_t)(uintptr_t)src;
+        if (index_blocks)  // every 64-byte output block start inside this piece points back at it
+            for (uint32_t b = (off + 63) >> 6; (b << 6) < off + len; ++b) sm.u.seg.blk[b] = (uint16_t)idx;
         ++idx;
         off += len;
     }
@@ -252,8 +261,8 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
 __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g, int nxt) {
     const uint32_t c = sm.ev_match[g];
     const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
-    uint32_t err = 0, klen, val_off16 = 0, val_len = 0, tf = 0, entry = 0;
-    bool found = false;
+    uint32_t err = 0, klen, val_off16 = 0, vl_tf = 0;
+    const IeSlot* hit = nullptr;
     uint4 key;
     const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
     if (short_key(sm, tv, tp, g, key, klen)) {
@@ -262,21 +271,21 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
             const uint32_t h = hash_short(key, klen);
             uint32_t idx = h & tv.mask;
             for (;;) {
-                // the three 16-byte pieces of the slot are independent loads: one L2 round trip per probe
+                // header and inline key are independent 16-byte loads: one L2 round trip per probe
                 const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
-                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2);
+                const uint4 q0 = __ldg(sp), q2 = __ldg(sp + 2);
                 if (q0.y == IE_SLOT_EMPTY) break;
                 if (q0.x == h && q0.y == klen && q2.x == key.x && q2.y == key.y && q2.z == key.z && q2.w == key.w) {
-                    found = true; val_len = q0.z; entry = q0.w; val_off16 = q1.y; tf = q1.z;
+                    hit = slots + idx; vl_tf = q0.z; val_off16 = q0.w;
                     break;
                 }
                 idx = (idx + 1) & tv.mask;
             }
-            if (!found) {  // interp.rs:109-116, :136
+            if (!hit) {  // interp.rs:109-116, :136
                 bool arg = klen >= 3 && (key.x & 0x00FFFFFFu) == 0x00475241u;  // "ARG"
-                const uint32_t kw[4] = {key.x, key.y, key.z, key.w};
                 for (uint32_t j = 3; arg && j < klen; ++j) {
-                    const uint32_t b = (kw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const uint32_t wj = j < 4 ? key.x : j < 8 ? key.y : j < 12 ? key.z : key.w;
+                    const uint32_t b = (wj >> (8 * (j & 3))) & 0xFFu;
                     arg = b >= '0' && b <= '9';
                 }
                 err = arg ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
@@ -289,32 +298,32 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
         const uint32_t h = hs.finish();
         uint32_t idx = h & tv.mask;
         for (;;) {
-            const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
-            const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+            const IeSlot* cand = slots + idx;
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(cand));
             if (q0.y == IE_SLOT_EMPTY) break;
             if (q0.x == h && q0.y == klen) {
-                Comparer cmp{tv.base + (size_t)q1.x * 16u};
+                Comparer cmp{tv.base + (size_t)__ldg(&cand->key_off16) * 16u};
                 walk_key(sm, tv, tp, g, cmp);
-                if (cmp.ok) { found = true; val_len = q0.z; entry = q0.w; val_off16 = q1.y; tf = q1.z; break; }
+                if (cmp.ok) { hit = cand; vl_tf = q0.z; val_off16 = q0.w; break; }
             }
             idx = (idx + 1) & tv.mask;
         }
-        if (!found) {
+        if (!hit) {
             ArgCheck ac;
             walk_key(sm, tv, tp, g, ac);
             err = ac.ok ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
         }
     }
-    if (found && !simple) {
-        if (!tag_splices(tf & 0xFF)) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
-        else if ((tf >> 8) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
+    if (hit && !simple) {
+        if (!tag_splices(IE_SLOT_TAG(vl_tf))) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
+        else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
     }
     if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
     sm.ev_a[g] = val_off16;
-    sm.ev_a[c] = val_len;
+    sm.ev_a[c] = IE_SLOT_VLEN(vl_tf);
     const uint32_t parent = sm.ev_c[g];
     if (parent == NONE16) {
-        if (simple) { sm.t_aux[t] = entry; sm.t_tag[t] = (uint8_t)(tf & 0xFF); }
+        if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
         return;
     }
     // one child of `parent` resolved: pending counters are u16, decremented through the enclosing word
@@ -324,11 +333,11 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
     const uint32_t old = atomicSub(word, 1u << shift);
     if (((old >> shift) & 0xFFFFu) == 1u) {
         const uint32_t k = atomicAdd(&sm.q_n[nxt], 1u);
-        sm.u.q[nxt][k] = (t << 16) | parent;
+        sm.q[nxt][k] = (t << 16) | parent;
     }
 }
 
-__global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+__global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
@@ -348,111 +357,172 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
     const uint64_t my_off = active ? __ldg(offs + i) : off_end;
     const uint8_t* __restrict__ tp = tmpl + off0;
     const uint64_t tile_bytes64 = off_end - off0;
-    sm.t_start[tid] = (uint32_t)(my_off - off0);
-    if (tid == 0) {
-        sm.t_start[TT] = (uint32_t)tile_bytes64;
-        sm.q_n[0] = 0; sm.q_n[1] = 0; sm.overflow = 0;
-    }
-    sm.t_err[tid] = 0;
-    sm.t_flags[tid] = 0;
-    __syncthreads();
-    bool fallback = tile_bytes64 > POS_MASK;  // positions are 24-bit: huge tiles use the per-thread path
+    if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
+    if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; }
+    if (tid == 0) { sm.q_n[0] = 0; sm.q_n[1] = 0; sm.overflow = 0; sm.ev_n = 0; }
+    const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
+    const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
     const uint32_t tile_bytes = (uint32_t)tile_bytes64;
+    const uint32_t n_chunks = (lead + tile_bytes + 15) >> 4;
+    const bool too_big = tile_bytes64 + 32 > (uint64_t)M_CAP * 16;  // does not fit the chunk-mask table
 
     // ---- P1: flat brace scan --------------------------------------------------------------------
-    if (!fallback) {
-        const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
-        const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
-        const uint32_t n_chunks = (lead + tile_bytes + 15) >> 4;
-        const uint32_t cw = (n_chunks + NW - 1) / NW;
-        const uint32_t cbeg = warp * cw, cend = min(n_chunks, cbeg + cw);
-        uint32_t wbase = 0;
-        for (uint32_t c0 = cbeg; c0 < cend; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            const bool have = c < cend;
-            uint32_t w[4] = {0, 0, 0, 0};
+    if (!too_big) {
+        for (uint32_t c = tid; c < n_chunks; c += NT) {
             const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;  // tile position of the chunk's first byte
-            if (have) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint32_t keep = 0;
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t keep = 0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int32_t p = p0 + 4 * k + j;
-                            if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
-                        }
-                        w[k] &= keep;
+                    for (int j = 0; j < 4; ++j) {
+                        const int32_t p = p0 + 4 * k + j;
+                        if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
                     }
+                    w[k] &= keep;
                 }
             }
-            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w[3], 1);
-            if (lane == 0) prev = (have && c > 0) ? __ldg(reinterpret_cast<const uint32_t*>(a0 + (size_t)c * 16 - 4)) : 0u;
-            uint32_t mo[4], mc[4], esc[4], mp[4];
-            uint32_t cnt = 0;
-            uint32_t carry = ((prev >> 24) == '\\') ? 0x80u : 0u;  // "previous byte is a backslash", byte 0 of word 0
+            // "previous byte is a backslash" for byte 0 comes from the byte before the chunk (flat
+            // stream; P2 repairs the first byte of each template, which nothing can escape)
+            uint32_t carry = (p0 > 0 && __ldg(tp + p0 - 1) == '\\') ? 0x80u : 0u;
+            uint32_t bits = 0, hi = 0;
+            uint32_t mcs[4], pbs[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                mo[k] = eqmask(w[k], 0x7B7B7B7Bu);
-                mc[k] = eqmask(w[k], 0x7D7D7D7Du);
+                const uint32_t mo = eqmask(w[k], 0x7B7B7B7Bu);
+                const uint32_t mc = eqmask(w[k], 0x7D7D7D7Du);
                 const uint32_t mb = eqmask(w[k], 0x5C5C5C5Cu);
                 const uint32_t pb = (mb << 8) | carry;
                 carry = mb >> 24;
-                esc[k] = (mo[k] | mc[k]) & pb;
-                mp[k] = 0;
-                uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
-                while (me) {  // rare: confirm E3 80 A0 (literal U+3020 collides with the reference's sentinels)
-                    const int bit = __ffs(me) - 1;
-                    me &= me - 1;
-                    const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
-                    if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0) mp[k] |= 1u << bit;
-                }
-                cnt += __popc(mo[k] | mc[k] | mp[k]);
+                mcs[k] = mc; pbs[k] = pb;
+                bits |= pack2(mo & ~pb, mc & ~pb) << (8 * k);
+                hi |= w[k];
             }
-            uint32_t incl = cnt;
+            // rare: escaped '}' preceded by '.' or '}' (".\}" / "}\}": '.' + "〠." reads as ".〠" + '.')
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if ((int)lane >= d) incl += y;
-            }
-            const uint32_t round_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (cnt) {
-                uint32_t idx = wbase + incl - cnt;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t m = mo[k] | mc[k] | mp[k];
-                    while (m) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
-                        uint32_t type;
-                        if ((mp[k] >> bit) & 1u) type = EV_PUNT;
-                        else {
-                            const bool open = (mo[k] >> bit) & 1u, escd = (esc[k] >> bit) & 1u;
-                            type = escd ? (open ? EV_ESC_OPEN : EV_ESC_CLOSE) : (open ? EV_OPEN : EV_CLOSE);
-                            if (type == EV_ESC_CLOSE && p >= 2) {  // ".\}" / "}\}": '.' + "〠." reads as ".〠" + '.'
-                                const uint8_t b2 = __ldg(tp + p - 2);
-                                if (b2 == '.' || b2 == '}') type = EV_PUNT;
-                            }
-                        }
-                        if (idx < (uint32_t)E_WARP) sm.u.stage[warp][idx] = p | (type << 24);
-                        ++idx;
+            for (int k = 0; k < 4; ++k) {
+                uint32_t m = mcs[k] & pbs[k];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int32_t p = p0 + 4 * k + (bit >> 3);
+                    if (p >= 2) {
+                        const uint8_t b2 = __ldg(tp + p - 2);
+                        if (b2 == '.' || b2 == '}') bits |= 3u << (2 * (4 * k + (bit >> 3)));
                     }
                 }
             }
-            wbase += round_total;
-        }
-        if (lane == 0) {
-            sm.warp_cnt[warp] = min(wbase, (uint32_t)E_WARP);
-            if (wbase > (uint32_t)E_WARP) sm.overflow = 1;
+            // rare: literal U+3020 (E3 80 A0) collides with the reference's sentinels
+            if (hi & 0x80808080u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
+                    while (me) {
+                        const int bit = __ffs(me) - 1;
+                        me &= me - 1;
+                        const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
+                        if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0)
+                            bits |= 3u << (2 * (4 * k + (bit >> 3)));
+                    }
+                }
+            }
+            sm.u.cm[c] = bits;
         }
     }
     __syncthreads();
-    fallback = fallback || sm.overflow != 0;
 
-    if (fallback) {
+    // ---- P2: per-template structure -----------------------------------------------------------------
+    if (!too_big && active) {
+        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
+        const uint32_t c_first = (lead + start) >> 4, c_last = (lead + end + 15) >> 4;  // [c_first, c_last)
+        // bit mask of chunk c restricted to this template's bytes; the template's first byte is never
+        // escaped (a '\' ending the previous template does not reach across)
+        uint32_t first_fix = 0;
+        if (end > start && start > 0) {
+            const uint8_t b0 = __ldg(tp + start);
+            if ((b0 == '{' || b0 == '}') && __ldg(tp + start - 1) == '\\') first_fix = (b0 == '{' ? 1u : 2u) << (2 * ((lead + start) & 15));
+        }
+        auto chunk_bits = [&](uint32_t c) -> uint32_t {
+            uint32_t m = sm.u.cm[c];
+            const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;
+            if (c == c_first) {
+                m |= first_fix;
+                const uint32_t skip = start - (uint32_t)max(p0, 0) + (p0 < 0 ? (uint32_t)(-p0) : 0u);  // bytes of the chunk before `start`
+                m &= skip >= 16 ? 0u : (0xFFFFFFFFu << (2 * skip));
+            }
+            if ((uint32_t)(p0 + 16) > end) {
+                const uint32_t keep = end - (uint32_t)p0;  // p0 >= 0 here unless the tile is tiny; clamp below
+                m &= keep >= 16 ? 0xFFFFFFFFu : ((1u << (2 * keep)) - 1u);
+            }
+            return m;
+        };
+        uint32_t cnt = 0;
+        for (uint32_t c = c_first; c < c_last; ++c) cnt += __popc(chunk_bits(c));
+        uint32_t eb = cnt ? atomicAdd(&sm.ev_n, cnt) : 0u;
+        uint32_t flags = 0, ne = 0;
+        if (eb + cnt > (uint32_t)E_CAP) { sm.overflow = 1; flags = TF_PUNT; eb = 0; }
+        else if (cnt) {
+            uint32_t wi = eb, depth = 0, n_open = 0;
+            uint16_t st_idx[MAXLVL], st_pend[MAXLVL];
+            bool punt = false, stray = false;
+            for (uint32_t c = c_first; c < c_last && !punt; ++c) {
+                uint32_t m = chunk_bits(c);
+                const uint32_t pbase = c * 16 - lead;
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    const uint32_t pair = (m >> (bit & ~1)) & 3u;
+                    m &= ~(3u << (bit & ~1));
+                    const uint32_t pos = pbase + (bit >> 1);
+                    if (pair == 3u) { punt = true; break; }
+                    if (pair == 1u) {
+                        ++n_open;
+                        if (depth == MAXLVL) { punt = true; break; }
+                        if (depth) ++st_pend[depth - 1];
+                        sm.ev_pos[wi] = pos;
+                        sm.ev_c[wi] = depth ? st_idx[depth - 1] : (uint16_t)NONE16;
+                        st_idx[depth] = (uint16_t)wi; st_pend[depth] = 0;
+                        ++depth; ++wi;
+                    } else {
+                        if (depth == 0) { stray = true; continue; }
+                        --depth;
+                        const uint32_t o = st_idx[depth];
+                        sm.ev_pos[wi] = pos | EV_CLOSE;
+                        sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
+                        sm.ev_c[wi] = st_pend[depth];
+                        ++wi;
+                    }
+                }
+            }
+            ne = wi - eb;
+            if (punt) flags = TF_PUNT;
+            else if (n_open == 0) flags = TF_VERBATIM;          // the loop at interp.rs:54 is never entered (stray '}' stay)
+            else if (stray || depth != 0) flags = TF_PUNT;      // uneven / improper nesting: general path (exact error text, panic)
+            if (flags == 0) {
+                // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
+                uint32_t ld = 0, tr = 0;
+                while (ld < ne && sm.ev_pos[eb + ld] == start + ld) ++ld;
+                while (tr < ne && sm.ev_pos[eb + ne - 1 - tr] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
+                const uint32_t m0 = min(ld, tr);
+                for (uint32_t j = 0; j < m0; ++j) {
+                    if (sm.ev_match[eb + j] != eb + ne - 1 - j) break;
+                    sm.ev_pos[eb + j] |= EV_SIMPLE;
+                }
+                for (uint32_t e = eb; e < eb + ne; ++e)
+                    if ((sm.ev_pos[e] & EV_CLOSE) && sm.ev_c[e] == 0) {
+                        const uint32_t k = atomicAdd(&sm.q_n[0], 1u);
+                        sm.q[0][k] = (tid << 16) | sm.ev_match[e];
+                    }
+            }
+        } else flags = TF_VERBATIM;
+        sm.t_eb[tid] = (uint16_t)eb;
+        sm.t_ne[tid] = (uint16_t)ne;
+        sm.t_flags[tid] = flags;
+    }
+    __syncthreads();
+
+    if (too_big || sm.overflow) {
         // ---- per-thread exact path for tiles that do not fit the tile tables -----------------------
         uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
         bool verbatim = false;
@@ -485,104 +555,19 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
         return;
     }
 
-    // ---- P1b: compact the per-warp stages into one ordered event list ---------------------------------
-    uint32_t total_ev = 0;
-    {
-        uint32_t base = 0;
-#pragma unroll
-        for (int wv = 0; wv < NW; ++wv) {
-            const uint32_t cntw = sm.warp_cnt[wv];
-            for (uint32_t k = tid; k < cntw; k += TT) sm.ev_pos[base + k] = sm.u.stage[wv][k];
-            base += cntw;
-        }
-        total_ev = base;
-    }
-    __syncthreads();
-
-    // ---- P2: per-template structure -----------------------------------------------------------------
-    {
-        uint32_t lo = 0, hi = total_ev;  // first event at or after this template's start
-        const uint32_t start = sm.t_start[tid];
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ((sm.ev_pos[mid] & POS_MASK) < start) lo = mid + 1; else hi = mid;
-        }
-        sm.t_eb[tid] = (uint16_t)lo;
-        if (tid == 0) sm.t_eb[TT] = (uint16_t)total_ev;
-    }
-    __syncthreads();
-    if (active) {
-        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
-        const uint32_t eb = sm.t_eb[tid], ee = sm.t_eb[tid + 1];
-        uint32_t wi = eb, depth = 0, n_open = 0;
-        uint16_t st_idx[MAXLVL], st_pend[MAXLVL];
-        bool punt = false, stray = false;
-        for (uint32_t e = eb; e < ee; ++e) {
-            const uint32_t x = sm.ev_pos[e];
-            const uint32_t pos = x & POS_MASK;
-            uint32_t type = (x >> 24) & 7u;
-            if (type == EV_PUNT) { punt = true; continue; }
-            if (type >= EV_ESC_OPEN) {  // an escape cannot reach across a template boundary
-                if (pos != start) continue;
-                type -= 2;
-            }
-            if (type == EV_OPEN) {
-                ++n_open;
-                if (depth == MAXLVL) { punt = true; break; }
-                if (depth) ++st_pend[depth - 1];
-                sm.ev_pos[wi] = pos;
-                sm.ev_c[wi] = depth ? st_idx[depth - 1] : (uint16_t)NONE16;
-                st_idx[depth] = (uint16_t)wi; st_pend[depth] = 0;
-                ++depth; ++wi;
-            } else {
-                if (depth == 0) { stray = true; continue; }
-                --depth;
-                const uint32_t o = st_idx[depth];
-                sm.ev_pos[wi] = pos | (EV_CLOSE << 24);
-                sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
-                sm.ev_c[wi] = st_pend[depth];
-                ++wi;
-            }
-        }
-        const uint32_t ne = wi - eb;
-        sm.t_ne[tid] = (uint16_t)ne;
-        uint32_t flags = 0;
-        if (end - start > 0x00FFFFFFu) punt = true;
-        if (punt) flags = TF_PUNT;
-        else if (n_open == 0) flags = TF_VERBATIM;  // the loop at interp.rs:54 is never entered (stray '}' stay)
-        else if (stray || depth != 0) flags = TF_PUNT;  // uneven or improper nesting: general path (exact error text / panic)
-        sm.t_flags[tid] = flags;
-        if (flags == 0) {
-            // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
-            uint32_t lead = 0, trail = 0;
-            while (lead < ne && sm.ev_pos[eb + lead] == start + lead) ++lead;  // type bits 0 = open
-            while (trail < ne && sm.ev_pos[eb + ne - 1 - trail] == ((end - 1 - trail) | (EV_CLOSE << 24))) ++trail;
-            const uint32_t m0 = min(lead, trail);
-            for (uint32_t j = 0; j < m0; ++j) {
-                if (sm.ev_match[eb + j] != eb + ne - 1 - j) break;
-                sm.ev_pos[eb + j] |= EV_SIMPLE;
-            }
-            for (uint32_t e = eb; e < eb + ne; ++e)
-                if ((sm.ev_pos[e] >> 24) == EV_CLOSE && sm.ev_c[e] == 0) {
-                    const uint32_t k = atomicAdd(&sm.q_n[0], 1u);
-                    sm.u.q[0][k] = (tid << 16) | sm.ev_match[e];
-                }
-        }
-    }
-
     // ---- P3: lookups, one thread per ready group, level by level --------------------------------------
     int cur = 0;
     for (;;) {
-        __syncthreads();
         const uint32_t nq = sm.q_n[cur];
         if (nq == 0) break;
-        for (uint32_t k = tid; k < nq; k += TT) {
-            const uint32_t item = sm.u.q[cur][k];
+        for (uint32_t k = tid; k < nq; k += NT) {
+            const uint32_t item = sm.q[cur][k];
             resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu, cur ^ 1);
         }
         __syncthreads();
         if (tid == 0) sm.q_n[cur] = 0;
         cur ^= 1;
+        __syncthreads();
     }
 
     // ---- P4: sizes, offsets, copy segments ---------------------------------------------------------------
@@ -638,13 +623,13 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
         total_seg += sm.warp_scan[wv];
     }
     sbase += sincl - nseg;
-    const uint32_t tile_out = (uint32_t)(tile_end - tile_begin);
-    const bool fits = tile_end <= out_cap;
+    const uint64_t tile_out64 = tile_end - tile_begin;
+    const uint32_t tile_out = (uint32_t)tile_out64;
     if (active) {
         out_offs[i] = off; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
     }
-    if (!fits) { if (tid == 0) *ws.overflow = 1u; return; }
-    if (total_seg > (uint32_t)S_CAP || tile_end - tile_begin > 0xFFFFFFFFull) {
+    if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return; }
+    if (total_seg > (uint32_t)S_CAP || tile_out64 > 0xFFFFFFFFull) {
         // segment table overflow: every thread copies its own pieces
         if (active && olen) {
             PieceCopy cp{out + off};
@@ -654,8 +639,9 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
         }
         return;
     }
+    const bool index_blocks = tile_out <= (uint32_t)B_CAP * 64;
     if (active && nseg) {
-        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin)};
+        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin), index_blocks};
         if (mode == 1) em(tp + sm.t_start[tid], olen);
         else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
         else walk_output_pieces(sm, tv, tp, tid, em);
@@ -669,16 +655,22 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
     const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
     const uint32_t olead = (uint32_t)((uintptr_t)gout - o0);
     const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
-    for (uint32_t c = tid; c < o_chunks; c += TT) {
+    for (uint32_t c = tid; c < o_chunks; c += NT) {
         const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
         const uint32_t xb = x0s < 0 ? 0u : (uint32_t)x0s;
         const uint32_t xe = min(tile_out, (uint32_t)(x0s + 16));
-        uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
+        uint32_t sidx;
+        if (index_blocks) {
+            sidx = sm.u.seg.blk[xb >> 6];  // segment covering the enclosing 64-byte block start, then walk forward
+            while (sm.u.seg.out[sidx + 1] <= xb) ++sidx;
+        } else {
+            uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
+            }
+            sidx = lo;
         }
-        uint32_t sidx = lo;
         uint32_t so = sm.u.seg.out[sidx], se = sm.u.seg.out[sidx + 1];
         // gather the chunk from its piece(s): unaligned 16-byte loads shifted into place
         uint4 acc = make_uint4(0, 0, 0, 0);
@@ -693,10 +685,10 @@ __global__ void __launch_bounds__(TT) ie_resolve_tile_kernel(IeTableView tv, con
         }
         if (xe - xb == 16) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
         else {  // first / last chunk of the tile: only the bytes that belong to it
-            const uint32_t aw4[4] = {acc.x, acc.y, acc.z, acc.w};
             for (uint32_t p = xb; p < xe; ++p) {
                 const uint32_t j = (uint32_t)((int32_t)p - x0s);
-                gout[p] = (uint8_t)(aw4[j >> 2] >> (8 * (j & 3)));
+                const uint32_t wj = j < 4 ? acc.x : j < 8 ? acc.y : j < 12 ? acc.z : acc.w;
+                gout[p] = (uint8_t)(wj >> (8 * (j & 3)));
             }
         }
     }
@@ -708,7 +700,7 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                                     const IeWorkspace& ws, ie_batch_info* d_info, cudaStream_t stream) {
     const uint64_t tiles = (n + TT - 1) / TT;
-    ie_resolve_tile_kernel<<<(unsigned)tiles, TT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
+    ie_resolve_tile_kernel<<<(unsigned)tiles, NT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
                                                               d_aux, ws, d_info);
     return cudaGetLastError();
 }

@@ -43,7 +43,7 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
     entries.reserve(n + 2);
     for (uint64_t i = 0; i < n; ++i) {
         if (key_offs[i + 1] < key_offs[i] || val_offs[i + 1] < val_offs[i]) { *why = "offsets not monotone"; return false; }
-        if (key_offs[i + 1] - key_offs[i] >= 0xFFFFFFFFull || val_offs[i + 1] - val_offs[i] >= 0xFFFFFFFFull) { *why = "key or value too long"; return false; }
+        if (key_offs[i + 1] - key_offs[i] >= 0xFFFFFFFFull || val_offs[i + 1] - val_offs[i] > IE_VLEN_MAX) { *why = "key longer than 4 GiB or value longer than 64 MiB"; return false; }
         if (tags[i] > IE_TAG_OBJECT) { *why = "bad tag"; return false; }
         entries.push_back(Entry{keys + key_offs[i], key_offs[i + 1] - key_offs[i], vals + val_offs[i], val_offs[i + 1] - val_offs[i], tags[i], (uint32_t)i});
     }
@@ -52,8 +52,11 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
     if (hhmm) entries.push_back(Entry{(const uint8_t*)"HH:MM", 5, (const uint8_t*)hhmm, std::strlen(hhmm), IE_TAG_STRING, (uint32_t)n});
     if (hhmmss) entries.push_back(Entry{(const uint8_t*)"HH:MM:SS", 8, (const uint8_t*)hhmmss, std::strlen(hhmmss), IE_TAG_STRING, (uint32_t)n + 1});
 
+    // load factor <= 0.25 (<= 0.5 for very large maps): linear probe chains stay at 1-2 slots, and a
+    // warp waits for its slowest lane
     uint64_t cap = 16;
-    while (cap < entries.size() * 2) cap <<= 1;
+    const uint64_t want = entries.size() <= (1ull << 22) ? entries.size() * 4 : entries.size() * 2;
+    while (cap < want) cap <<= 1;
     if (cap > (1ull << 31)) { *why = "table too large"; return false; }
 
     // arena sizes (16-byte aligned items)
@@ -96,9 +99,8 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
                 kcur += pad16(en.key_len);
             }
         }
-        s->val_len = (uint32_t)en.val_len;
+        s->vl_tf = (uint32_t)en.val_len | (en.tag << 26) | (classify_value(en.val, en.val_len) << 29);
         s->entry = en.index;
-        s->tagflags = en.tag | (classify_value(en.val, en.val_len) << 8);
         if (en.val_len <= IE_INLINE_BYTES) {
             std::memset(s->val_inline, 0, IE_INLINE_BYTES);
             std::memcpy(s->val_inline, en.val, en.val_len);
