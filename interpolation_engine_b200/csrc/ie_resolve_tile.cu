@@ -49,9 +49,9 @@ enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2 };
 struct Smem {
     ie_scan::TileSmemT<NT> scan;
     uint32_t ev_pos[E_CAP];    // position in tile | EV_CLOSE (| EV_SIMPLE on opens)
-    uint32_t ev_a[E_CAP];      // open: val_off16 of the resolved value; close: its length
+    uint32_t ev_a[E_CAP];      // open: unresolved children, then val_off16 of the resolved value; close: its length
     uint16_t ev_match[E_CAP];  // partner event
-    uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level); close: unresolved children
+    uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level)
     uint32_t q[2][Q_CAP];      // P3 ready queues (template << 16 | open event)
     union {
         uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
@@ -326,12 +326,8 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
         if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
         return;
     }
-    // one child of `parent` resolved: pending counters are u16, decremented through the enclosing word
-    const uint32_t pc = sm.ev_match[parent];
-    uint32_t* word = reinterpret_cast<uint32_t*>(sm.ev_c) + (pc >> 1);
-    const uint32_t shift = (pc & 1) * 16;
-    const uint32_t old = atomicSub(word, 1u << shift);
-    if (((old >> shift) & 0xFFFFu) == 1u) {
+    // one child of `parent` resolved; the last one makes the parent ready
+    if (atomicSub(&sm.ev_a[parent], 1u) == 1u) {
         const uint32_t k = atomicAdd(&sm.q_n[nxt], 1u);
         sm.q[nxt][k] = (t << 16) | parent;
     }
@@ -434,71 +430,65 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     __syncthreads();
 
     // ---- P2: per-template structure -----------------------------------------------------------------
+    // One thread per template walks the set bits of its chunk masks in one flat loop (one event per
+    // iteration keeps the lanes of a warp together).  No explicit stack: the innermost open group is
+    // tracked through the parent links; ev_a[open] counts unresolved children until the group resolves.
     if (!too_big && active) {
         const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
-        const uint32_t c_first = (lead + start) >> 4, c_last = (lead + end + 15) >> 4;  // [c_first, c_last)
-        // bit mask of chunk c restricted to this template's bytes; the template's first byte is never
-        // escaped (a '\' ending the previous template does not reach across)
+        const uint32_t c_first = (lead + start) >> 4, c_end = (lead + end + 15) >> 4;  // chunks [c_first, c_end)
+        // the template's first byte is never escaped (a '\' ending the previous template does not reach across)
         uint32_t first_fix = 0;
         if (end > start && start > 0) {
             const uint8_t b0 = __ldg(tp + start);
             if ((b0 == '{' || b0 == '}') && __ldg(tp + start - 1) == '\\') first_fix = (b0 == '{' ? 1u : 2u) << (2 * ((lead + start) & 15));
         }
-        auto chunk_bits = [&](uint32_t c) -> uint32_t {
-            uint32_t m = sm.u.cm[c];
-            const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;
-            if (c == c_first) {
-                m |= first_fix;
-                const uint32_t skip = start - (uint32_t)max(p0, 0) + (p0 < 0 ? (uint32_t)(-p0) : 0u);  // bytes of the chunk before `start`
-                m &= skip >= 16 ? 0u : (0xFFFFFFFFu << (2 * skip));
-            }
-            if ((uint32_t)(p0 + 16) > end) {
-                const uint32_t keep = end - (uint32_t)p0;  // p0 >= 0 here unless the tile is tiny; clamp below
-                m &= keep >= 16 ? 0xFFFFFFFFu : ((1u << (2 * keep)) - 1u);
-            }
+        const uint32_t smask = 0xFFFFFFFFu << (2 * ((lead + start) & 15));
+        const uint32_t ekeep = (lead + end) & 15;
+        const uint32_t emask = ekeep ? ((1u << (2 * ekeep)) - 1u) : 0xFFFFFFFFu;
+        auto bits_at = [&](uint32_t cc) -> uint32_t {
+            uint32_t m = sm.u.cm[cc];
+            if (cc == c_first) m = (m | first_fix) & smask;
+            if (cc + 1 == c_end) m &= emask;
             return m;
         };
-        uint32_t cnt = 0;
-        for (uint32_t c = c_first; c < c_last; ++c) cnt += __popc(chunk_bits(c));
+        uint32_t cnt = first_fix ? 1u : 0u;  // upper bound: boundary chunks may include the neighbours' bits
+        for (uint32_t c = c_first; c < c_end; ++c) cnt += __popc(sm.u.cm[c]);
         uint32_t eb = cnt ? atomicAdd(&sm.ev_n, cnt) : 0u;
         uint32_t flags = 0, ne = 0;
         if (eb + cnt > (uint32_t)E_CAP) { sm.overflow = 1; flags = TF_PUNT; eb = 0; }
         else if (cnt) {
-            uint32_t wi = eb, depth = 0, n_open = 0;
-            uint16_t st_idx[MAXLVL], st_pend[MAXLVL];
+            uint32_t wi = eb, n_open = 0, cur_open = NONE16;
             bool punt = false, stray = false;
-            for (uint32_t c = c_first; c < c_last && !punt; ++c) {
-                uint32_t m = chunk_bits(c);
-                const uint32_t pbase = c * 16 - lead;
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    const uint32_t pair = (m >> (bit & ~1)) & 3u;
-                    m &= ~(3u << (bit & ~1));
-                    const uint32_t pos = pbase + (bit >> 1);
-                    if (pair == 3u) { punt = true; break; }
-                    if (pair == 1u) {
-                        ++n_open;
-                        if (depth == MAXLVL) { punt = true; break; }
-                        if (depth) ++st_pend[depth - 1];
-                        sm.ev_pos[wi] = pos;
-                        sm.ev_c[wi] = depth ? st_idx[depth - 1] : (uint16_t)NONE16;
-                        st_idx[depth] = (uint16_t)wi; st_pend[depth] = 0;
-                        ++depth; ++wi;
-                    } else {
-                        if (depth == 0) { stray = true; continue; }
-                        --depth;
-                        const uint32_t o = st_idx[depth];
-                        sm.ev_pos[wi] = pos | EV_CLOSE;
-                        sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
-                        sm.ev_c[wi] = st_pend[depth];
-                        ++wi;
-                    }
+            uint32_t c = c_first;
+            uint32_t m = c < c_end ? bits_at(c) : 0u;
+            for (;;) {
+                while (m == 0 && ++c < c_end) m = bits_at(c);
+                if (m == 0) break;
+                const int bit = (__ffs(m) - 1) & ~1;
+                const uint32_t pair = (m >> bit) & 3u;
+                m &= ~(3u << bit);
+                const uint32_t pos = c * 16 - lead + (bit >> 1);
+                if (pair == 3u) { punt = true; break; }
+                if (pair == 1u) {
+                    ++n_open;
+                    sm.ev_pos[wi] = pos;
+                    sm.ev_c[wi] = (uint16_t)cur_open;
+                    sm.ev_a[wi] = 0;
+                    if (cur_open != NONE16) sm.ev_a[cur_open] += 1;
+                    cur_open = wi++;
+                } else if (cur_open == NONE16) stray = true;
+                else {
+                    const uint32_t o = cur_open;
+                    sm.ev_pos[wi] = pos | EV_CLOSE;
+                    sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
+                    cur_open = sm.ev_c[o];
+                    ++wi;
                 }
             }
             ne = wi - eb;
             if (punt) flags = TF_PUNT;
-            else if (n_open == 0) flags = TF_VERBATIM;          // the loop at interp.rs:54 is never entered (stray '}' stay)
-            else if (stray || depth != 0) flags = TF_PUNT;      // uneven / improper nesting: general path (exact error text, panic)
+            else if (n_open == 0) flags = TF_VERBATIM;                // the loop at interp.rs:54 is never entered (stray '}' stay)
+            else if (stray || cur_open != NONE16) flags = TF_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
             if (flags == 0) {
                 // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
                 uint32_t ld = 0, tr = 0;
@@ -509,11 +499,9 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
                     if (sm.ev_match[eb + j] != eb + ne - 1 - j) break;
                     sm.ev_pos[eb + j] |= EV_SIMPLE;
                 }
+                // leaf groups are ready (only now: a punted template may hold unmatched groups)
                 for (uint32_t e = eb; e < eb + ne; ++e)
-                    if ((sm.ev_pos[e] & EV_CLOSE) && sm.ev_c[e] == 0) {
-                        const uint32_t k = atomicAdd(&sm.q_n[0], 1u);
-                        sm.q[0][k] = (tid << 16) | sm.ev_match[e];
-                    }
+                    if (!(sm.ev_pos[e] & EV_CLOSE) && sm.ev_a[e] == 0) sm.q[0][atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | e;
             }
         } else flags = TF_VERBATIM;
         sm.t_eb[tid] = (uint16_t)eb;
@@ -650,6 +638,9 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     __syncthreads();
 
     // ---- P5: flat 16-byte output sweep -----------------------------------------------------------------
+    // Pass A: every chunk that lies inside ONE segment (constant source misalignment): 5 aligned words,
+    // 4 funnel shifts, one 16-byte store.  Pass B: one thread per segment start handles the chunk that
+    // contains it (pieces shifted and OR-ed in registers); the ragged first / last chunk of the tile too.
     if (tile_out == 0) return;
     uint8_t* gout = out + tile_begin;
     const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
@@ -657,8 +648,8 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
     for (uint32_t c = tid; c < o_chunks; c += NT) {
         const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
-        const uint32_t xb = x0s < 0 ? 0u : (uint32_t)x0s;
-        const uint32_t xe = min(tile_out, (uint32_t)(x0s + 16));
+        if (x0s < 0 || (uint32_t)x0s + 16 > tile_out) continue;   // ragged edge chunk: pass B
+        const uint32_t xb = (uint32_t)x0s;
         uint32_t sidx;
         if (index_blocks) {
             sidx = sm.u.seg.blk[xb >> 6];  // segment covering the enclosing 64-byte block start, then walk forward
@@ -671,8 +662,41 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
             }
             sidx = lo;
         }
+        if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
+        const uintptr_t src = (uintptr_t)sm.u.seg.src[sidx] + (xb - sm.u.seg.out[sidx]);
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(src & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(src & 3) * 8;
+        const uint32_t w0 = __ldg(aw), w1 = __ldg(aw + 1), w2 = __ldg(aw + 2), w3 = __ldg(aw + 3);
+        const uint32_t w4 = sh ? __ldg(aw + 4) : 0u;  // only touched when it holds requested bytes
+        *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) =
+            make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    // pass B: item 0 = the tile's first chunk, item j >= 1 = the chunk holding the start of segment j when
+    // segment j-1 starts at or before that chunk's first byte (the first boundary inside the chunk owns it),
+    // item total_seg = the ragged last chunk when no segment start owns it
+    for (uint32_t j = tid; j <= total_seg; j += NT) {
+        uint32_t c;
+        if (j == 0) {
+            c = 0;
+            if (olead == 0 && sm.u.seg.out[1] >= 16 && tile_out >= 16) continue;  // aligned interior chunk: pass A had it
+        } else if (j == total_seg) {
+            c = o_chunks - 1;
+            const int32_t x0l = (int32_t)(c * 16) - (int32_t)olead;
+            if ((uint32_t)(x0l + 16) <= tile_out) continue;                       // last chunk is full: pass A or a boundary item
+            if (c == 0 || (int32_t)sm.u.seg.out[j - 1] > x0l) continue;           // item 0 or a boundary item owns it
+        } else {
+            const uint32_t xo = sm.u.seg.out[j];
+            c = (olead + xo) >> 4;
+            const int32_t x0j = (int32_t)(c * 16) - (int32_t)olead;
+            if (c == 0 || (int32_t)xo == x0j) continue;                            // chunk 0 is item 0's; an aligned start is no boundary
+            if ((int32_t)sm.u.seg.out[j - 1] > x0j) continue;                      // an earlier boundary in the same chunk owns it
+        }
+        const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;
+        const uint32_t xb = x0s < 0 ? 0u : (uint32_t)x0s;
+        const uint32_t xe = min(tile_out, (uint32_t)(x0s + 16));
+        uint32_t sidx = j ? j - 1 : 0;
+        if (j == total_seg) { while (sm.u.seg.out[sidx] > xb) --sidx; }
         uint32_t so = sm.u.seg.out[sidx], se = sm.u.seg.out[sidx + 1];
-        // gather the chunk from its piece(s): unaligned 16-byte loads shifted into place
         uint4 acc = make_uint4(0, 0, 0, 0);
         uint32_t x = xb;
         for (;;) {
@@ -684,11 +708,11 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
             ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
         }
         if (xe - xb == 16) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
-        else {  // first / last chunk of the tile: only the bytes that belong to it
+        else {
             for (uint32_t p = xb; p < xe; ++p) {
-                const uint32_t j = (uint32_t)((int32_t)p - x0s);
-                const uint32_t wj = j < 4 ? acc.x : j < 8 ? acc.y : j < 12 ? acc.z : acc.w;
-                gout[p] = (uint8_t)(wj >> (8 * (j & 3)));
+                const uint32_t q = (uint32_t)((int32_t)p - x0s);
+                const uint32_t wq = q < 4 ? acc.x : q < 8 ? acc.y : q < 12 ? acc.z : acc.w;
+                gout[p] = (uint8_t)(wq >> (8 * (q & 3)));
             }
         }
     }

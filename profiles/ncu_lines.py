@@ -55,3 +55,32 @@ def main(rep, cubin, top=40, kernel='ie_resolve_tile_kernel'):
 
 if __name__ == '__main__':
     main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40, sys.argv[4] if len(sys.argv) > 4 else 'ie_resolve_tile_kernel')
+
+
+def phase_table(rep, cubin, ranges, kernel='ie_resolve_tile_kernel'):
+    """ranges: list of (name, file, lo, hi) -> share of warp instructions and samples."""
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+    hdr = rows[hdr_i]
+    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    lines = sass_lines(cubin, kernel)
+    ci = {h: i for i, h in enumerate(hdr)}
+    acc = collections.defaultdict(lambda: [0, 0, 0])
+    for k in range(min(len(body), len(lines))):
+        key = lines[k]
+        name = 'other'
+        if key:
+            for nm, f, lo, hi in ranges:
+                if key[0] == f and lo <= key[1] <= hi:
+                    name = nm
+                    break
+            else:
+                name = key[0]
+        a = acc[name]
+        a[0] += int(body[k][ci['Instructions Executed']] or 0)
+        a[1] += int(body[k][ci['Thread Instructions Executed']] or 0)
+        a[2] += int(body[k][ci['# Samples']] or 0)
+    ti = sum(a[0] for a in acc.values()); ts = sum(a[2] for a in acc.values())
+    for nm, a in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+        print(f"{nm:28s} inst {a[0]:>11d} ({100*a[0]/ti:5.1f}%)  lanes {a[1]/max(a[0],1):5.1f}  samples {100*a[2]/ts:5.1f}%")
