@@ -52,7 +52,7 @@ struct Smem {
     uint32_t ev_a[E_CAP];      // open: unresolved children, then val_off16 of the resolved value; close: its length
     uint16_t ev_match[E_CAP];  // partner event
     uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level)
-    uint32_t q[2][Q_CAP];      // P3 ready queues (template << 16 | open event)
+    uint32_t q[1][Q_CAP];      // P3 work list: leaf groups (template << 16 | open event)
     union {
         uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
         struct {
@@ -69,7 +69,7 @@ struct Smem {
     uint16_t t_ne[TT];         // its events
     uint8_t t_tag[TT];
     uint32_t warp_scan[NW];
-    uint32_t q_n[2];
+    uint32_t q_n[1];
     uint32_t ev_n;             // events allocated
     uint32_t overflow;
 };
@@ -83,6 +83,66 @@ __device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 
 __device__ __forceinline__ uint32_t pack2(uint32_t o, uint32_t c) {
     const uint32_t t = (o >> 7) | (c >> 6);
     return (t * 0x01041040u) >> 24;
+}
+
+constexpr int P1_BATCH = 3;
+
+// One 16-byte chunk of template text -> 32 bits, 2 per byte: bit 2j = unescaped '{' at byte j,
+// bit 2j+1 = unescaped '}', both = punt marker.  `prev` is the byte before the chunk ("previous byte is
+// a backslash" is evaluated on the flat stream; P2 repairs the first byte of each template).
+__device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, int32_t p0, uint32_t tile_bytes,
+                                               const uint8_t* __restrict__ tp) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t keep = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int32_t p = p0 + 4 * k + j;
+                if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
+            }
+            w[k] &= keep;
+        }
+    }
+    uint32_t carry = prev == '\\' ? 0x80u : 0u;
+    uint32_t bits = 0, hi = 0, esc_close = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t mo = eqmask(w[k], 0x7B7B7B7Bu);
+        const uint32_t mc = eqmask(w[k], 0x7D7D7D7Du);
+        const uint32_t mb = eqmask(w[k], 0x5C5C5C5Cu);
+        const uint32_t pb = (mb << 8) | carry;
+        carry = mb >> 24;
+        bits |= pack2(mo & ~pb, mc & ~pb) << (8 * k);
+        esc_close |= pack2(0u, mc & pb) << (8 * k);
+        hi |= w[k];
+    }
+    // rare: escaped '}' preceded by '.' or '}' (".\}" / "}\}": '.' + "〠." reads as ".〠" + '.')
+    while (esc_close) {
+        const int bit = __ffs(esc_close) - 1;  // odd bit 2j+1
+        esc_close &= esc_close - 1;
+        const int32_t p = p0 + (bit >> 1);
+        if (p >= 2) {
+            const uint8_t b2 = __ldg(tp + p - 2);
+            if (b2 == '.' || b2 == '}') bits |= 3u << (bit & ~1);
+        }
+    }
+    // rare: literal U+3020 (E3 80 A0) collides with the reference's sentinels
+    if (hi & 0x80808080u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
+            while (me) {
+                const int bit = __ffs(me) - 1;
+                me &= me - 1;
+                const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
+                if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0)
+                    bits |= 3u << (2 * (4 * k + (bit >> 3)));
+            }
+        }
+    }
+    return bits;
 }
 
 // Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero.
@@ -258,7 +318,10 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
     return ie_fmix32(h ^ klen);
 }
 
-__device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g, int nxt) {
+// Resolves group g and then, while g was the last unresolved child of its parent, the parent too
+// (a `{q-{idx-{slot-A}}}` chain is one thread's work instead of one queue round per level).
+__device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
+  for (;;) {
     const uint32_t c = sm.ev_match[g];
     const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
     uint32_t err = 0, klen, val_off16 = 0, vl_tf = 0;
@@ -326,11 +389,12 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
         if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
         return;
     }
-    // one child of `parent` resolved; the last one makes the parent ready
-    if (atomicSub(&sm.ev_a[parent], 1u) == 1u) {
-        const uint32_t k = atomicAdd(&sm.q_n[nxt], 1u);
-        sm.q[nxt][k] = (t << 16) | parent;
-    }
+    // one child of `parent` resolved; whoever resolves the last one carries on with the parent
+    __threadfence_block();
+    if (atomicSub(&sm.ev_a[parent], 1u) != 1u) return;
+    __threadfence_block();  // the siblings' results (written before their decrements) are visible from here on
+    g = parent;
+  }
 }
 
 __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
@@ -355,7 +419,7 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     const uint64_t tile_bytes64 = off_end - off0;
     if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
     if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; }
-    if (tid == 0) { sm.q_n[0] = 0; sm.q_n[1] = 0; sm.overflow = 0; sm.ev_n = 0; }
+    if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; }
     const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
     const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
     const uint32_t tile_bytes = (uint32_t)tile_bytes64;
@@ -363,68 +427,26 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     const bool too_big = tile_bytes64 + 32 > (uint64_t)M_CAP * 16;  // does not fit the chunk-mask table
 
     // ---- P1: flat brace scan --------------------------------------------------------------------
+    // Loads are issued P1_BATCH chunks ahead of the compares so that a thread keeps several HBM
+    // requests in flight.
     if (!too_big) {
-        for (uint32_t c = tid; c < n_chunks; c += NT) {
-            const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;  // tile position of the chunk's first byte
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
+        for (uint32_t cb = tid; cb < n_chunks; cb += NT * P1_BATCH) {
+            uint4 v[P1_BATCH];
+            uint32_t pv[P1_BATCH];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t keep = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int32_t p = p0 + 4 * k + j;
-                        if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
-                    }
-                    w[k] &= keep;
+            for (int u = 0; u < P1_BATCH; ++u) {
+                const uint32_t c = cb + u * NT;
+                if (c < n_chunks) {
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
+                    const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;
+                    pv[u] = p0 > 0 ? __ldg(tp + p0 - 1) : 0u;  // the byte before the chunk (flat stream)
                 }
             }
-            // "previous byte is a backslash" for byte 0 comes from the byte before the chunk (flat
-            // stream; P2 repairs the first byte of each template, which nothing can escape)
-            uint32_t carry = (p0 > 0 && __ldg(tp + p0 - 1) == '\\') ? 0x80u : 0u;
-            uint32_t bits = 0, hi = 0;
-            uint32_t mcs[4], pbs[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t mo = eqmask(w[k], 0x7B7B7B7Bu);
-                const uint32_t mc = eqmask(w[k], 0x7D7D7D7Du);
-                const uint32_t mb = eqmask(w[k], 0x5C5C5C5Cu);
-                const uint32_t pb = (mb << 8) | carry;
-                carry = mb >> 24;
-                mcs[k] = mc; pbs[k] = pb;
-                bits |= pack2(mo & ~pb, mc & ~pb) << (8 * k);
-                hi |= w[k];
+            for (int u = 0; u < P1_BATCH; ++u) {
+                const uint32_t c = cb + u * NT;
+                if (c < n_chunks) sm.u.cm[c] = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
             }
-            // rare: escaped '}' preceded by '.' or '}' (".\}" / "}\}": '.' + "〠." reads as ".〠" + '.')
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t m = mcs[k] & pbs[k];
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int32_t p = p0 + 4 * k + (bit >> 3);
-                    if (p >= 2) {
-                        const uint8_t b2 = __ldg(tp + p - 2);
-                        if (b2 == '.' || b2 == '}') bits |= 3u << (2 * (4 * k + (bit >> 3)));
-                    }
-                }
-            }
-            // rare: literal U+3020 (E3 80 A0) collides with the reference's sentinels
-            if (hi & 0x80808080u) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
-                    while (me) {
-                        const int bit = __ffs(me) - 1;
-                        me &= me - 1;
-                        const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
-                        if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0)
-                            bits |= 3u << (2 * (4 * k + (bit >> 3)));
-                    }
-                }
-            }
-            sm.u.cm[c] = bits;
         }
     }
     __syncthreads();
@@ -543,20 +565,15 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
         return;
     }
 
-    // ---- P3: lookups, one thread per ready group, level by level --------------------------------------
-    int cur = 0;
-    for (;;) {
-        const uint32_t nq = sm.q_n[cur];
-        if (nq == 0) break;
+    // ---- P3: lookups, one thread per leaf group (and up its parent chain) ------------------------------
+    {
+        const uint32_t nq = sm.q_n[0];
         for (uint32_t k = tid; k < nq; k += NT) {
-            const uint32_t item = sm.q[cur][k];
-            resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu, cur ^ 1);
+            const uint32_t item = sm.q[0][k];
+            resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
-        __syncthreads();
-        if (tid == 0) sm.q_n[cur] = 0;
-        cur ^= 1;
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- P4: sizes, offsets, copy segments ---------------------------------------------------------------
     uint32_t olen = 0, nseg = 0, status = IE_RES_STRING, aux = 0, err_g = 0;
