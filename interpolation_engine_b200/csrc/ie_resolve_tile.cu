@@ -52,9 +52,11 @@ struct Smem {
     uint32_t ev_a[E_CAP];      // open: unresolved children, then val_off16 of the resolved value; close: its length
     uint16_t ev_match[E_CAP];  // partner event
     uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level)
-    uint32_t q[1][Q_CAP];      // P3 work list: leaf groups (template << 16 | open event)
     union {
-        uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
+        struct {
+            uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
+            uint32_t q[Q_CAP];   // P2/P3: leaf groups (template << 16 | open event)
+        } scan;
         struct {
             uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
             uint64_t src[S_CAP];      //     its source address
@@ -397,7 +399,7 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   }
 }
 
-__global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+__global__ void __launch_bounds__(NT, 5) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
 #pragma unroll
             for (int u = 0; u < P1_BATCH; ++u) {
                 const uint32_t c = cb + u * NT;
-                if (c < n_chunks) sm.u.cm[c] = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
+                if (c < n_chunks) sm.u.scan.cm[c] = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
             }
         }
     }
@@ -468,13 +470,13 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
         const uint32_t ekeep = (lead + end) & 15;
         const uint32_t emask = ekeep ? ((1u << (2 * ekeep)) - 1u) : 0xFFFFFFFFu;
         auto bits_at = [&](uint32_t cc) -> uint32_t {
-            uint32_t m = sm.u.cm[cc];
+            uint32_t m = sm.u.scan.cm[cc];
             if (cc == c_first) m = (m | first_fix) & smask;
             if (cc + 1 == c_end) m &= emask;
             return m;
         };
         uint32_t cnt = first_fix ? 1u : 0u;  // upper bound: boundary chunks may include the neighbours' bits
-        for (uint32_t c = c_first; c < c_end; ++c) cnt += __popc(sm.u.cm[c]);
+        for (uint32_t c = c_first; c < c_end; ++c) cnt += __popc(sm.u.scan.cm[c]);
         uint32_t eb = cnt ? atomicAdd(&sm.ev_n, cnt) : 0u;
         uint32_t flags = 0, ne = 0;
         if (eb + cnt > (uint32_t)E_CAP) { sm.overflow = 1; flags = TF_PUNT; eb = 0; }
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
                 }
                 // leaf groups are ready (only now: a punted template may hold unmatched groups)
                 for (uint32_t e = eb; e < eb + ne; ++e)
-                    if (!(sm.ev_pos[e] & EV_CLOSE) && sm.ev_a[e] == 0) sm.q[0][atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | e;
+                    if (!(sm.ev_pos[e] & EV_CLOSE) && sm.ev_a[e] == 0) sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | e;
             }
         } else flags = TF_VERBATIM;
         sm.t_eb[tid] = (uint16_t)eb;
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(NT) ie_resolve_tile_kernel(IeTableView tv, con
     {
         const uint32_t nq = sm.q_n[0];
         for (uint32_t k = tid; k < nq; k += NT) {
-            const uint32_t item = sm.q[0][k];
+            const uint32_t item = sm.u.scan.q[k];
             resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
     }
