@@ -262,7 +262,8 @@ def main():
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         h2d = int(sh.bytes.nbytes + sh.offs.nbytes)
-        d2h = int(res.info.out_bytes) + n * (8 + 4 + 4 + 4) + 32
+        lens = np.frombuffer((ctypes.c_char * (n * 4)).from_address(res.out_lens), dtype=np.uint32)
+        d2h = int(lens.sum(dtype=np.uint64)) + n * (8 + 4 + 4 + 4) + 32  # result bytes + offs/lens/status/aux + info
         e2e = {"s": e2e_s, "h2d": h2d, "d2h": d2h, "steps": e2e_steps, "kernel_ms": float(res.info.kernel_ms)}
         lib.ie_host_free(h_t)
         lib.ie_host_free(h_o)

@@ -58,6 +58,9 @@ constexpr uint32_t kDefaultResultBytes = 64u << 10;
 struct ie_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy engines of the pipelined host-buffer path
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    double expand = 2.0;  // output bytes per input byte the pipelined path provisions (adapts upward)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // workspace
     DevBuf ws_zero, ws_list, ws_scratch;
@@ -135,6 +138,8 @@ ie_status_t ie_engine_create(int device, ie_engine** out) {
     if (!e) return fail(IE_E_NOMEM, "ie_engine_create: out of host memory");
     e->device = device;
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
     if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
     if (err != cudaSuccess) { ie_engine_destroy(e); return cuda_fail(err, "ie_engine_create"); }
@@ -152,6 +157,10 @@ void ie_engine_destroy(ie_engine* e) {
     for (PinBuf* b : {&e->h_out, &e->h_out_offs, &e->h_out_lens, &e->h_status, &e->h_aux, &e->h_info}) b->release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -201,6 +210,20 @@ void ie_table_free(ie_table* t) {
 
 uint64_t ie_table_device_bytes(const ie_table* t) { return t ? t->bytes : 0; }
 
+static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
+                                  const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
+                                  uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, uint64_t out_bias,
+                                  cudaStream_t s) {
+    uint32_t max_exp, tcap;
+    resolve_limits(limits, &max_exp, &tcap);
+    IeWorkspace ws;
+    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws);
+    if (st != IE_OK) return st;
+    CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+                         max_exp, tcap, out_bias, s));
+    return IE_OK;
+}
+
 ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
                                     const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
                                     uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, void* stream) {
@@ -208,14 +231,109 @@ ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8
         return fail(IE_E_INVALID, "ie_resolve_batch_device: NULL argument");
     if (n >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "ie_resolve_batch_device: at most 2^32-2 templates per batch");
     CU(cudaSetDevice(e->device));
-    uint32_t max_exp, tcap;
-    resolve_limits(limits, &max_exp, &tcap);
-    IeWorkspace ws;
-    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws);
-    if (st != IE_OK) return st;
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                         max_exp, tcap, s));
+    return resolve_device(e, t, d_tmpl, d_tmpl_offs, n, limits, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, d_info, 0,
+                          stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Host-buffer batches of at least this many templates are cut into chunks whose H2D copy, kernels and
+// D2H copies overlap on three streams (PCIe is full duplex; the kernels hide behind the copies).
+static constexpr uint64_t kPipeChunk = 1u << 16;
+
+// Returns IE_OK with *done = false when a chunk's provisioned output region was too small (the caller
+// then reruns the batch unpipelined with exact sizes, and e->expand has been raised).
+static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs, uint64_t n,
+                                     const ie_limits* limits, ie_result* res, bool* done) {
+    *done = false;
+    const uint64_t K = (n + kPipeChunk - 1) / kPipeChunk;
+    const uint64_t in_bytes = tmpl_offs[n];
+    cudaStream_t sc = e->stream;
+    while (e->ev_in.size() < K) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        e->ev_in.push_back(a);
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->ev_done.push_back(b);
+    }
+    // per-chunk output regions at fixed bases: the results need not be contiguous, every template has (offset, length)
+    std::vector<uint64_t> base(K + 1, 0);
+    for (uint64_t k = 0; k < K; ++k) {
+        const uint64_t lo = k * kPipeChunk, hi = std::min(n, lo + kPipeChunk);
+        const uint64_t cap = (uint64_t)((double)(tmpl_offs[hi] - tmpl_offs[lo]) * e->expand) + (64u << 10);
+        base[k + 1] = base[k] + ((cap + 255) & ~uint64_t(255));
+    }
+    CU(e->d_in.ensure(in_bytes + 64, sc));
+    CU(e->d_in_offs.ensure((n + 1) * 8, sc));
+    CU(e->d_out.ensure(base[K] + 64, sc));
+    CU(e->d_out_offs.ensure(n * 8 + 8, sc));
+    CU(e->d_out_lens.ensure(n * 4 + 4, sc));
+    CU(e->d_status.ensure(n * 4 + 4, sc));
+    CU(e->d_aux.ensure(n * 4 + 4, sc));
+    CU(e->d_info.ensure(K * sizeof(ie_batch_info), sc));
+    CU(e->h_info.ensure(K * sizeof(ie_batch_info)));
+    CU(e->h_out.ensure(base[K] + 1));
+    CU(e->h_out_offs.ensure(n * 8 + 8));
+    CU(e->h_out_lens.ensure(n * 4 + 4));
+    CU(e->h_status.ensure(n * 4 + 4));
+    CU(e->h_aux.ensure(n * 4 + 4));
+    {   // size the workspace once for the largest chunk so that no launch reallocates while others are in flight
+        uint32_t max_exp, tcap;
+        resolve_limits(limits, &max_exp, &tcap);
+        IeWorkspace ws;
+        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws);
+        if (st != IE_OK) return st;
+    }
+    ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
+    CU(cudaMemcpyAsync(e->d_in_offs.p, tmpl_offs, (n + 1) * 8, cudaMemcpyHostToDevice, e->s_in));
+    CU(cudaEventRecord(e->ev0, sc));
+    for (uint64_t k = 0; k < K; ++k) {
+        const uint64_t lo = k * kPipeChunk, hi = std::min(n, lo + kPipeChunk);
+        const uint64_t b0 = tmpl_offs[lo], b1 = tmpl_offs[hi];
+        if (b1 > b0) CU(cudaMemcpyAsync((uint8_t*)e->d_in.p + b0, tmpl + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(e->ev_in[k], e->s_in));
+        CU(cudaStreamWaitEvent(sc, e->ev_in[k], 0));
+        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
+                                        (uint8_t*)e->d_out.p + base[k], base[k + 1] - base[k], (uint64_t*)e->d_out_offs.p + lo,
+                                        (uint32_t*)e->d_out_lens.p + lo, (int32_t*)e->d_status.p + lo, (uint32_t*)e->d_aux.p + lo,
+                                        (ie_batch_info*)e->d_info.p + k, base[k], sc);
+        if (st != IE_OK) return st;
+        CU(cudaMemcpyAsync(hinfo + k, (ie_batch_info*)e->d_info.p + k, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, sc));
+        CU(cudaEventRecord(e->ev_done[k], sc));
+    }
+    CU(cudaEventRecord(e->ev1, sc));
+    bool overflow = false;
+    uint64_t n_general = 0;
+    double worst = 0.0;
+    for (uint64_t k = 0; k < K; ++k) {
+        const uint64_t lo = k * kPipeChunk, hi = std::min(n, lo + kPipeChunk);
+        CU(cudaEventSynchronize(e->ev_done[k]));
+        const uint64_t ob = hinfo[k].out_bytes;
+        const uint64_t ib = tmpl_offs[hi] - tmpl_offs[lo];
+        if (ib) worst = std::max(worst, (double)ob / (double)ib);
+        n_general += hinfo[k].n_general;
+        if (ob > base[k + 1] - base[k]) { overflow = true; continue; }
+        if (overflow) continue;
+        if (ob) CU(cudaMemcpyAsync((uint8_t*)e->h_out.p + base[k], (uint8_t*)e->d_out.p + base[k], ob, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync((uint64_t*)e->h_out_offs.p + lo, (uint64_t*)e->d_out_offs.p + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync((uint32_t*)e->h_out_lens.p + lo, (uint32_t*)e->d_out_lens.p + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync((int32_t*)e->h_status.p + lo, (int32_t*)e->d_status.p + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync((uint32_t*)e->h_aux.p + lo, (uint32_t*)e->d_aux.p + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, e->s_out));
+    }
+    CU(cudaStreamSynchronize(e->s_out));
+    CU(cudaStreamSynchronize(sc));
+    if (worst * 1.1 > e->expand) e->expand = worst * 1.25;
+    if (overflow) return IE_OK;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    res->out = (const uint8_t*)e->h_out.p;
+    res->out_offs = (const uint64_t*)e->h_out_offs.p;
+    res->out_lens = (const uint32_t*)e->h_out_lens.p;
+    res->status = (const int32_t*)e->h_status.p;
+    res->aux = (const uint32_t*)e->h_aux.p;
+    res->info.n = n;
+    res->info.out_bytes = base[K];
+    res->info.n_general = n_general;
+    res->info.kernel_ms = ms;  // first launch to last kernel end, copies overlapped
+    *done = true;
     return IE_OK;
 }
 
@@ -227,6 +345,11 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     const uint64_t in_bytes = n ? tmpl_offs[n] : 0;
     if (in_bytes && !tmpl) return fail(IE_E_INVALID, "ie_resolve_batch: NULL template arena");
     cudaStream_t s = e->stream;
+    if (n >= 2 * kPipeChunk) {
+        bool done = false;
+        ie_status_t st = resolve_pipelined(e, t, tmpl, tmpl_offs, n, limits, res, &done);
+        if (st != IE_OK || done) return st;
+    }
     CU(e->d_in.ensure(in_bytes + 16, s));
     CU(e->d_in_offs.ensure((n + 1) * 8, s));
     CU(e->d_out_offs.ensure(n * 8 + 8, s));

@@ -25,11 +25,11 @@ struct IeWorkspace {
 cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              cudaStream_t stream);
+                              uint64_t out_bias, cudaStream_t stream);
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, cudaStream_t stream);
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, cudaStream_t stream);
 
 // tag_out[i] = value tag or -1 on a miss; entry_out[i] = insert index (>= n_entries: clock key)
 cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,

@@ -33,13 +33,14 @@ namespace {
 using namespace ie_dev;
 
 constexpr int TT = IE_RESOLVE_TILE;  // templates per tile
-constexpr int NT = 256;              // threads per CTA
+constexpr int NT = 2 * TT;           // threads per CTA
 constexpr int NW = NT / 32;
-constexpr int E_CAP = 1536;          // brace events per tile
+constexpr int CTAS_PER_SM = 640 / TT;  // resident CTAs the register budget is tuned for (48 registers)
+constexpr int E_CAP = 12 * TT;       // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
-constexpr int M_CAP = 2304;          // 16-byte chunks per tile (36 KiB of template text)
-constexpr int S_CAP = 1024;          // copy segments per tile
-constexpr int B_CAP = 1024;          // 64-byte output blocks with a segment index (64 KiB of output)
+constexpr int M_CAP = 18 * TT;       // 16-byte chunks per tile (288 bytes of template text per template)
+constexpr int S_CAP = 8 * TT;        // copy segments per tile
+constexpr int B_CAP = 8 * TT;        // 64-byte output blocks with a segment index (512 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
 constexpr uint32_t EV_CLOSE = 1u << 24;
@@ -399,11 +400,11 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   }
 }
 
-__global__ void __launch_bounds__(NT, 5) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
-                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info) {
+                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias) {
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = ie_scan::acquire_tile(sm.scan, ws.tile_counter);
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(NT, 5) ie_resolve_tile_kernel(IeTableView tv, 
             atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
         }
         if (!active) return;
-        out_offs[i] = off; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+        out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
         if (olen == 0) return;
         if (off + olen > out_cap) { *ws.overflow = 1u; return; }
         if (verbatim) { uint8_t* wr = out + off; for (uint32_t k = 0; k < len; ++k) wr[k] = __ldg(t + k); }
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(NT, 5) ie_resolve_tile_kernel(IeTableView tv, 
     const uint64_t tile_out64 = tile_end - tile_begin;
     const uint32_t tile_out = (uint32_t)tile_out64;
     if (active) {
-        out_offs[i] = off; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+        out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
     }
     if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return; }
     if (total_seg > (uint32_t)S_CAP || tile_out64 > 0xFFFFFFFFull) {
@@ -741,9 +742,9 @@ __global__ void __launch_bounds__(NT, 5) ie_resolve_tile_kernel(IeTableView tv, 
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, cudaStream_t stream) {
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, cudaStream_t stream) {
     const uint64_t tiles = (n + TT - 1) / TT;
     ie_resolve_tile_kernel<<<(unsigned)tiles, NT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
-                                                              d_aux, ws, d_info);
+                                                              d_aux, ws, d_info, out_bias);
     return cudaGetLastError();
 }

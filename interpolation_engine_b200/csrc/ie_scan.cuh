@@ -69,7 +69,8 @@ __device__ __forceinline__ uint64_t exclusive_prefix(TileSmemT<NT>& sm, uint64_t
                 const int64_t idx = j - (int64_t)lane;
                 uint64_t sv = FLAG_INC;  // before tile 0: inclusive prefix 0
                 if (idx >= 0) {
-                    do { sv = ld_state(tile_state + idx); } while ((sv >> 62) == 0);
+                    sv = ld_state(tile_state + idx);
+                    while ((sv >> 62) == 0) { __nanosleep(40); sv = ld_state(tile_state + idx); }
                 }
                 const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (sv >> 62) == 2);
                 const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
