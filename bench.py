@@ -269,10 +269,9 @@ def main():
         lib.ie_host_free(h_o)
 
     # ---- reduce over ranks: max time, summed work ----
-    t = torch.tensor([total_ms, e2e["s"] if e2e else 0.0], dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    from interpolation_engine_b200 import sharding
+    total_ms_max, _ = sharding.reduce_timing(dist if world > 1 else None, total_ms, n * args.steps)
+    e2e_s_max, _ = sharding.reduce_timing(dist if world > 1 else None, e2e["s"] if e2e else 0.0, n)
 
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
