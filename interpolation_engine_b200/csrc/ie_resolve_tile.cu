@@ -40,7 +40,7 @@ constexpr int E_CAP = 12 * TT;       // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
 constexpr int M_CAP = 18 * TT;       // 16-byte chunks per tile (288 bytes of template text per template)
 constexpr int S_CAP = 8 * TT;        // copy segments per tile
-constexpr int B_CAP = 8 * TT;        // 64-byte output blocks with a segment index (512 bytes of output per template)
+constexpr int C_CAP = 16 * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
 constexpr uint32_t EV_CLOSE = 1u << 24;
@@ -61,7 +61,7 @@ struct Smem {
         struct {
             uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
             uint64_t src[S_CAP];      //     its source address
-            uint16_t blk[B_CAP];      //     segment covering output byte 64 * b
+            uint16_t cs[C_CAP + 2];   //     segment holding the first byte of each 32-byte aligned output block
         } seg;
     } u;
     uint32_t t_start[TT + 1];  // template start, tile-relative
@@ -109,7 +109,8 @@ __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, in
         }
     }
     uint32_t carry = prev == '\\' ? 0x80u : 0u;
-    uint32_t bits = 0, hi = 0, esc_close = 0;
+    uint32_t bits = 0, hi = 0, any_esc_close = 0;
+    uint32_t ecs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t mo = eqmask(w[k], 0x7B7B7B7Bu);
@@ -118,17 +119,24 @@ __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, in
         const uint32_t pb = (mb << 8) | carry;
         carry = mb >> 24;
         bits |= pack2(mo & ~pb, mc & ~pb) << (8 * k);
-        esc_close |= pack2(0u, mc & pb) << (8 * k);
+        ecs[k] = mc & pb;
+        any_esc_close |= ecs[k];
         hi |= w[k];
     }
     // rare: escaped '}' preceded by '.' or '}' (".\}" / "}\}": '.' + "〠." reads as ".〠" + '.')
-    while (esc_close) {
-        const int bit = __ffs(esc_close) - 1;  // odd bit 2j+1
-        esc_close &= esc_close - 1;
-        const int32_t p = p0 + (bit >> 1);
-        if (p >= 2) {
-            const uint8_t b2 = __ldg(tp + p - 2);
-            if (b2 == '.' || b2 == '}') bits |= 3u << (bit & ~1);
+    if (any_esc_close) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t m = ecs[k];
+            while (m) {
+                const int byte = (__ffs(m) - 1) >> 3;
+                m &= m - 1;
+                const int32_t p = p0 + 4 * k + byte;
+                if (p >= 2) {
+                    const uint8_t b2 = __ldg(tp + p - 2);
+                    if (b2 == '.' || b2 == '}') bits |= 3u << (2 * (4 * k + byte));
+                }
+            }
         }
     }
     // rare: literal U+3020 (E3 80 A0) collides with the reference's sentinels
@@ -266,12 +274,13 @@ struct PieceCount {
 struct PieceEmit {
     Smem& sm;
     uint32_t idx, off;
-    bool index_blocks;
+    uint32_t olead;  // bytes between the 16-byte aligned floor of the tile's output address and that address
+    bool index_chunks;
     __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
         sm.u.seg.out[idx] = off;
         sm.u.seg.src[idx] = (uint64_t)(uintptr_t)src;
-        if (index_blocks)  // every 64-byte output block start inside this piece points back at it
-            for (uint32_t b = (off + 63) >> 6; (b << 6) < off + len; ++b) sm.u.seg.blk[b] = (uint16_t)idx;
+        if (index_chunks)  // every 32-byte aligned output block whose first byte lies in this piece points back at it
+            for (uint32_t c = (off + olead + 31) >> 5; (c << 5) < off + olead + len; ++c) sm.u.seg.cs[c] = (uint16_t)idx;
         ++idx;
         off += len;
     }
@@ -647,14 +656,18 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         }
         return;
     }
-    const bool index_blocks = tile_out <= (uint32_t)B_CAP * 64;
+    uint8_t* gout = out + tile_begin;
+    const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
+    const uint32_t olead = (uint32_t)((uintptr_t)gout - o0);
+    const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
+    const bool index_chunks = o_chunks <= 2 * (uint32_t)C_CAP;
     if (active && nseg) {
-        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin), index_blocks};
+        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin), olead, index_chunks};
         if (mode == 1) em(tp + sm.t_start[tid], olen);
         else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
         else walk_output_pieces(sm, tv, tp, tid, em);
     }
-    if (tid == 0) sm.u.seg.out[total_seg] = tile_out;
+    if (tid == 0) { sm.u.seg.out[total_seg] = tile_out; sm.u.seg.cs[0] = 0; }
     __syncthreads();
 
     // ---- P5: flat 16-byte output sweep -----------------------------------------------------------------
@@ -662,19 +675,16 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     // 4 funnel shifts, one 16-byte store.  Pass B: one thread per segment start handles the chunk that
     // contains it (pieces shifted and OR-ed in registers); the ragged first / last chunk of the tile too.
     if (tile_out == 0) return;
-    uint8_t* gout = out + tile_begin;
-    const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
-    const uint32_t olead = (uint32_t)((uintptr_t)gout - o0);
-    const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
     for (uint32_t c = tid; c < o_chunks; c += NT) {
         const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
         if (x0s < 0 || (uint32_t)x0s + 16 > tile_out) continue;   // ragged edge chunk: pass B
         const uint32_t xb = (uint32_t)x0s;
         uint32_t sidx;
-        if (index_blocks) {
-            sidx = sm.u.seg.blk[xb >> 6];  // segment covering the enclosing 64-byte block start, then walk forward
+        if (index_chunks) {
+            sidx = sm.u.seg.cs[c >> 1];  // segment at the enclosing 32-byte block start, then at most a short walk
             while (sm.u.seg.out[sidx + 1] <= xb) ++sidx;
-        } else {
+        }
+        else {
             uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
