@@ -28,6 +28,15 @@
 #include "ie_kernels.h"
 #include "ie_scan.cuh"
 
+#ifdef IE_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
+#define PHASE_INIT() long long t_phase_ = clock64()
+#else
+#define PHASE_MARK(k) do { } while (0)
+#define PHASE_INIT() do { } while (0)
+#endif
+
 namespace {
 
 using namespace ie_dev;
@@ -416,7 +425,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
                                                              uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias) {
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    PHASE_INIT();
     const uint32_t tile = ie_scan::acquire_tile(sm.scan, ws.tile_counter);
+    PHASE_MARK(0);
     const uint64_t i0 = (uint64_t)tile * TT;
     const uint32_t nt = (uint32_t)min((uint64_t)TT, n - i0);
     const uint64_t i = i0 + tid;
@@ -461,7 +472,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             }
         }
     }
+    PHASE_MARK(1);
     __syncthreads();
+    PHASE_MARK(2);
 
     // ---- P2: per-template structure -----------------------------------------------------------------
     // One thread per template walks the set bits of its chunk masks in one flat loop (one event per
@@ -542,7 +555,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         sm.t_ne[tid] = (uint16_t)ne;
         sm.t_flags[tid] = flags;
     }
+    PHASE_MARK(3);
     __syncthreads();
+    PHASE_MARK(4);
 
     if (too_big || sm.overflow) {
         // ---- per-thread exact path for tiles that do not fit the tile tables -----------------------
@@ -562,11 +577,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             }
             if (status == IE_RES_PUNT) { olen = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i; }
         }
-        uint64_t tile_end;
-        const uint64_t off = ie_scan::exclusive_prefix(sm.scan, ws.tile_state, tile, olen, &tile_end);
+        uint64_t tile_total16;
+        const uint64_t loc = ie_scan::publish(sm.scan, ws.tile_state, tile, olen, 15, &tile_total16);
+        const uint64_t off = ie_scan::lookback(sm.scan, ws.tile_state, tile, tile_total16) + loc;
         if (tid == 0 && last_tile) {
             info->n = n;
-            atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)(off - loc + tile_total16));
         }
         if (!active) return;
         out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
@@ -585,7 +601,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
     }
+    PHASE_MARK(5);
     __syncthreads();
+    PHASE_MARK(6);
 
     // ---- P4: sizes, offsets, copy segments ---------------------------------------------------------------
     uint32_t olen = 0, nseg = 0, status = IE_RES_STRING, aux = 0, err_g = 0;
@@ -618,12 +636,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             }
         }
     }
-    uint64_t tile_end, tile_begin;
-    const uint64_t off = ie_scan::exclusive_prefix(sm.scan, ws.tile_state, tile, olen, &tile_end, &tile_begin);
-    if (tid == 0 && last_tile) {
-        info->n = n;
-        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
-    }
+    PHASE_MARK(7);
+    // Every tile's output starts 16-byte aligned (totals are rounded up), so the chunk structure of the
+    // copy sweep does not depend on the tile's global offset: the total is published first, the segment
+    // table is built from tile-local offsets, and only then does the look-back collect the predecessors.
+    uint64_t tile_pad64, tile_out64;  // rounded up to 16 (what successors skip) / bytes actually produced
+    const uint32_t loc = (uint32_t)ie_scan::publish(sm.scan, ws.tile_state, tile, olen, 15, &tile_pad64, &tile_out64);
     // tile-local exclusive scan of segment counts
     uint32_t sincl = nseg;
 #pragma unroll
@@ -640,13 +658,33 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         total_seg += sm.warp_scan[wv];
     }
     sbase += sincl - nseg;
-    const uint64_t tile_out64 = tile_end - tile_begin;
     const uint32_t tile_out = (uint32_t)tile_out64;
+    const uint32_t olead = (uint32_t)((uintptr_t)out & 15);  // tile offsets are multiples of 16
+    const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
+    const bool seg_ok = total_seg <= (uint32_t)S_CAP && tile_out64 <= 0xFFFFFFFFull;
+    const bool index_chunks = o_chunks <= 2 * (uint32_t)C_CAP;
+    if (seg_ok) {
+        if (active && nseg) {
+            PieceEmit em{sm, sbase, loc, olead, index_chunks};
+            if (mode == 1) em(tp + sm.t_start[tid], olen);
+            else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
+            else walk_output_pieces(sm, tv, tp, tid, em);
+        }
+        if (tid == 0) { sm.u.seg.cs[0] = 0; sm.u.seg.out[total_seg] = tile_out; }
+    }
+    PHASE_MARK(8);
+    const uint64_t tile_begin = ie_scan::lookback(sm.scan, ws.tile_state, tile, tile_pad64);
+    const uint64_t tile_end = tile_begin + tile_pad64;
+    const uint64_t off = tile_begin + loc;
+    if (tid == 0 && last_tile) {
+        info->n = n;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
+    }
     if (active) {
         out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
     }
     if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return; }
-    if (total_seg > (uint32_t)S_CAP || tile_out64 > 0xFFFFFFFFull) {
+    if (!seg_ok) {
         // segment table overflow: every thread copies its own pieces
         if (active && olen) {
             PieceCopy cp{out + off};
@@ -658,18 +696,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     }
     uint8_t* gout = out + tile_begin;
     const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
-    const uint32_t olead = (uint32_t)((uintptr_t)gout - o0);
-    const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
-    const bool index_chunks = o_chunks <= 2 * (uint32_t)C_CAP;
-    if (active && nseg) {
-        PieceEmit em{sm, sbase, (uint32_t)(off - tile_begin), olead, index_chunks};
-        if (mode == 1) em(tp + sm.t_start[tid], olen);
-        else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
-        else walk_output_pieces(sm, tv, tp, tid, em);
-    }
-    if (tid == 0) { sm.u.seg.out[total_seg] = tile_out; sm.u.seg.cs[0] = 0; }
-    __syncthreads();
 
+    PHASE_MARK(9);
     // ---- P5: flat 16-byte output sweep -----------------------------------------------------------------
     // Pass A: every chunk that lies inside ONE segment (constant source misalignment): 5 aligned words,
     // 4 funnel shifts, one 16-byte store.  Pass B: one thread per segment start handles the chunk that
@@ -701,6 +729,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) =
             make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
     }
+    PHASE_MARK(10);
     // pass B: item 0 = the tile's first chunk, item j >= 1 = the chunk holding the start of segment j when
     // segment j-1 starts at or before that chunk's first byte (the first boundary inside the chunk owns it),
     // item total_seg = the ragged last chunk when no segment start owns it
@@ -746,6 +775,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             }
         }
     }
+    PHASE_MARK(11);
 }
 
 }  // namespace
@@ -758,3 +788,12 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl
                                                               d_aux, ws, d_info, out_bias);
     return cudaGetLastError();
 }
+
+#ifdef IE_PHASE_TIMING
+extern "C" int ie_debug_phase_cycles(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+    return 0;
+}
+#endif
