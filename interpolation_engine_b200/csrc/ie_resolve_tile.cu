@@ -673,6 +673,14 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         if (tid == 0) { sm.u.seg.cs[0] = 0; sm.u.seg.out[total_seg] = tile_out; }
     }
     PHASE_MARK(8);
+#ifdef IE_UNORDERED_EXPERIMENT
+    if (tid == 0) sm.scan.base = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_pad64);
+    __syncthreads();
+    const uint64_t tile_begin = sm.scan.base;
+    const uint64_t tile_end = tile_begin + tile_pad64;
+    const uint64_t off = tile_begin + loc;
+    if (tid == 0 && last_tile) info->n = n;
+#else
     const uint64_t tile_begin = ie_scan::lookback(sm.scan, ws.tile_state, tile, tile_pad64);
     const uint64_t tile_end = tile_begin + tile_pad64;
     const uint64_t off = tile_begin + loc;
@@ -680,6 +688,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         info->n = n;
         atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
     }
+#endif
     if (active) {
         out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
     }
