@@ -42,12 +42,12 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fast resolve kernel on this workload, taken
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tile resolve kernel on this workload, taken
     from the committed ncu capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("ie_resolve_fast_kernel_dram_bytes_per_launch")
+            return json.load(f).get("ie_resolve_tile_kernel_dram_bytes_per_launch")
     return None
 
 
@@ -293,7 +293,7 @@ def main():
             "clocks": clocks,
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "ie_resolve_fast_kernel (+ general kernel and two memsets in the same step)",
+                         "kernel": "ie_resolve_tile_kernel (+ the general kernel and two small memsets in the same step)",
                          "algorithmic_bytes_per_launch": alg_mean, "peak_source": peak_src + ", of measured"},
         }
         if e2e:

@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's contract line — that is bench.py): the other configs of
+BASELINE.json on one B200, one JSON line each, same roofline / cpu_baseline conventions.
+
+    python bench_aux.py [--which c5,escape,c3]
+
+  c5      wildcard delete sweep over 10 M keys x 64 pattern sets (runtime.rs:1198-1239, 1633-1647)
+  escape  recursive_escape / recursive_unescape over the 1 Mi C4 templates (interp.rs:147-177)
+  c3      text_adventure-derived templates over cloned states (one table per state, small batches)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bench import measured_peak  # noqa: E402
+
+
+def device_time_ms(torch, stream, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_c5(eng, ie, workloads, torch, dev, orc):
+    keys = workloads.c5_keys()
+    sets = workloads.c5_pattern_sets()
+    n = keys.n
+    d_k = torch.from_numpy(keys.bytes).to(dev)
+    d_o = torch.from_numpy(keys.offs.view(np.int64)).to(dev)
+    d_m = torch.empty((n + 31) // 32 + 1, dtype=torch.int32, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    arenas = [ie.Arena.from_strings(p) for p in sets]
+    state = {"k": 0}
+
+    def step():
+        pa = arenas[state["k"] % len(arenas)]
+        eng.glob_sweep_device(d_k.data_ptr(), d_o.data_ptr(), n, pa, state["k"] & 1, d_m.data_ptr(), d_n.data_ptr(), stream=stream.cuda_stream)
+        state["k"] += 1
+    ms = device_time_ms(torch, stream, step, 2 * len(arenas))
+    alg = keys.bytes.nbytes + (n + 1) * 8 + (n + 7) // 8
+    peak, src = measured_peak()
+    # e2e through the host-buffer call
+    t0 = time.perf_counter()
+    reps = 4
+    for k in range(reps):
+        eng.glob_sweep(keys, arenas[k], invert=bool(k & 1))
+    e2e_s = (time.perf_counter() - t0) / reps
+    threads = os.cpu_count() or 1
+    sub = 1 << 21
+    ksub = ie.Arena(keys.bytes[:int(keys.offs[sub])], keys.offs[:sub + 1])
+    t0 = time.perf_counter()
+    for k in range(4):
+        orc.glob_sweep(ksub.bytes, ksub.offs, arenas[k].bytes, arenas[k].offs, bool(k & 1), threads=threads)
+    cpu = 4 * sub / (time.perf_counter() - t0)
+    return {
+        "metric": "wildcard delete sweep keys/sec (10 M keys, 64 pattern sets of 1-9 wildcards)", "value": n / (ms * 1e-3), "unit": "keys/s",
+        "n_gpus": 1, "ms_per_step": ms, "higher_is_better": True, "dtype": "u8", "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": "C5: 10M keys persona-<p>/field-<f>, one sweep = one (pattern set, delete|delete_except) pair", "keys": n,
+                   "l2": "key arena + offsets 0.31 GB > 126 MB L2"},
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                     "traffic": None, "kernel": "ie_glob_kernel", "algorithmic_bytes_per_launch": alg, "peak_source": src + ", of measured"},
+        "e2e": {"value": n / e2e_s, "unit": "keys/s", "h2d_bytes_per_step": int(keys.bytes.nbytes + keys.offs.nbytes), "d2h_bytes_per_step": int((n + 31) // 32 * 4 + 8),
+                "ms_per_step": e2e_s * 1e3},
+        "cpu_baseline": {"value": cpu, "unit": "keys/s", "cores": threads, "kind": "port",
+                         "sample": f"first {sub} keys x 4 pattern sets; direct '*' matcher (faster than the reference's regex-compile-per-pair, favours the CPU)"},
+        "gpu_launches": 2 * len(arenas),
+    }
+
+
+def bench_escape(eng, ie, workloads, torch, dev, orc):
+    tmpl = workloads.c4_templates(1 << 20)
+    n = tmpl.n
+    d_t = torch.from_numpy(tmpl.bytes).to(dev)
+    d_o = torch.from_numpy(tmpl.offs.view(np.int64)).to(dev)
+    cap = tmpl.bytes.nbytes * 2 + 64
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_oo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    peak, src = measured_peak()
+    res = {}
+    for mode, name in ((1, "escape"), (0, "unescape")):
+        def step():
+            eng._check(eng.lib.ie_escape_batch_device(eng.handle, mode, d_t.data_ptr(), d_o.data_ptr(), n, d_out.data_ptr(), cap, d_oo.data_ptr(), stream.cuda_stream))
+        ms = device_time_ms(torch, stream, step, 10)
+        ob = int(d_oo[-1].item())
+        alg = tmpl.bytes.nbytes + ob + 2 * (n + 1) * 8
+        res[name] = {"ms": ms, "strings_per_s": n / (ms * 1e-3), "achieved_GBs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak}
+    return {"metric": "recursive_escape / recursive_unescape strings/sec (1 Mi C4 templates)", "value": res["unescape"]["strings_per_s"], "unit": "strings/s",
+            "n_gpus": 1, "higher_is_better": True, "dtype": "u8", "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": "the C4 template arena through ie_escape_batch_device", "detail": res},
+            "roofline": {"bound": "hbm", "achieved": res["unescape"]["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": res["unescape"]["frac"], "traffic": None,
+                         "kernel": "ie_escape_kernel", "peak_source": src + ", of measured"}}
+
+
+def bench_c3(eng, ie, workloads, torch, dev, orc):
+    rng = np.random.default_rng(0xC3)
+    arena = ie.Arena.from_strings(workloads.C3_TEMPLATES)
+    states = [ie.PackedInserts.from_dict(workloads.c3_state(s, rng)) for s in range(512)]
+    t0 = time.perf_counter()
+    n_general = 0
+    for st in states:
+        r = eng.resolve_batch(eng.pack(st), arena)
+        n_general += r.n_general
+    gpu_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for st in states[:128]:
+        orc.build_table(st).resolve_batch(arena.bytes, arena.offs, threads=1)
+    cpu_s = (time.perf_counter() - t0) * len(states) / 128
+    n = len(states) * arena.n
+    return {"metric": "C3 text_adventure-derived templates/sec, one table + one launch per cloned state (latency-bound small batches)", "value": n / gpu_s,
+            "unit": "strings/s", "n_gpus": 1, "higher_is_better": True, "dtype": "u8", "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": f"{len(states)} states x {arena.n} templates, pack + H2D + kernels + D2H per state", "general_path_templates": int(n_general)},
+            "cpu_baseline": {"value": n / cpu_s, "unit": "strings/s", "cores": 1, "kind": "port", "sample": "128 states, 1 thread (table build included on both sides)"},
+            "note": "small batches: the CPU is expected to win or tie here; reported as measured"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="c5,escape,c3")
+    args = ap.parse_args()
+    import torch
+
+    import interpolation_engine_b200 as ie
+    from interpolation_engine_b200 import workloads
+    from tests import oracle_lib
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    eng = ie.Engine(0)
+    orc = oracle_lib.load()
+    for name in args.which.split(","):
+        fn = {"c5": bench_c5, "escape": bench_escape, "c3": bench_c3}[name]
+        print(json.dumps(fn(eng, ie, workloads, torch, dev, orc)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,9 @@ typedef struct {
     uint32_t max_expansions;   /* lookups per template on the general path (default 4096)       */
     uint32_t max_result_bytes; /* bytes of intermediate/final text per template on the general
                                   path (default 64 KiB)                                         */
+    uint32_t avg_template_bytes; /* device-buffer calls only: mean template length, used to size the
+                                  CTA tiles (0 = short templates, <= 230 bytes); the host-buffer
+                                  calls measure it themselves                                   */
 } ie_limits;
 
 typedef struct {

@@ -80,8 +80,8 @@ struct ie_table {
 namespace {
 
 // Lays the per-batch workspace out for n items; returns the kernel-side view.
-ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws) {
-    const uint64_t tiles = (n + IE_RESOLVE_TILE - 1) / IE_RESOLVE_TILE;
+ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws, uint32_t tt = IE_RESOLVE_TILE) {
+    const uint64_t tiles = (n + tt - 1) / tt;
     const size_t zero_bytes = 64 + (size_t)(tiles + 1) * sizeof(uint64_t);
     CU(e->ws_zero.ensure(zero_bytes, e->stream));
     ws->zero_base = (uint8_t*)e->ws_zero.p;
@@ -213,14 +213,16 @@ uint64_t ie_table_device_bytes(const ie_table* t) { return t ? t->bytes : 0; }
 static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
                                   const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
                                   uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, uint64_t out_bias,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, uint64_t avg_bytes = 0) {
     uint32_t max_exp, tcap;
     resolve_limits(limits, &max_exp, &tcap);
+    if (!avg_bytes && limits) avg_bytes = limits->avg_template_bytes;
+    const uint32_t tt = ie_pick_tile(avg_bytes);
     IeWorkspace ws;
-    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws);
+    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws, tt);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                         max_exp, tcap, out_bias, s));
+                         max_exp, tcap, out_bias, tt, s));
     return IE_OK;
 }
 
@@ -279,7 +281,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         uint32_t max_exp, tcap;
         resolve_limits(limits, &max_exp, &tcap);
         IeWorkspace ws;
-        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws);
+        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, ie_pick_tile(in_bytes / n));
         if (st != IE_OK) return st;
     }
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
@@ -294,7 +296,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
                                         (uint8_t*)e->d_out.p + base[k], base[k + 1] - base[k], (uint64_t*)e->d_out_offs.p + lo,
                                         (uint32_t*)e->d_out_lens.p + lo, (int32_t*)e->d_status.p + lo, (uint32_t*)e->d_aux.p + lo,
-                                        (ie_batch_info*)e->d_info.p + k, base[k], sc);
+                                        (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n);
         if (st != IE_OK) return st;
         CU(cudaMemcpyAsync(hinfo + k, (ie_batch_info*)e->d_info.p + k, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, sc));
         CU(cudaEventRecord(e->ev_done[k], sc));
@@ -365,10 +367,10 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     float kernel_ms = 0.f;
     for (int attempt = 0; attempt < 3; ++attempt) {
         CU(cudaEventRecord(e->ev0, s));
-        ie_status_t st = ie_resolve_batch_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
-                                                 (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p,
-                                                 (uint32_t*)e->d_out_lens.p, (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p,
-                                                 (ie_batch_info*)e->d_info.p, s);
+        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
+                                        (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p,
+                                        (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, (ie_batch_info*)e->d_info.p, 0, s,
+                                        n ? in_bytes / n : 0);
         if (st != IE_OK) return st;
         CU(cudaEventRecord(e->ev1, s));
         CU(cudaMemcpyAsync(hinfo, e->d_info.p, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, s));

@@ -5,7 +5,8 @@
 #include "ie_common.cuh"
 
 #define IE_TILE 256           // strings per CTA in the escape kernel
-#define IE_RESOLVE_TILE 128   // templates per CTA in the resolve tile kernel (sizes the tile-state array)
+#define IE_RESOLVE_TILE 128   // templates per CTA tile of the resolve kernel at most
+#define IE_TILE_TEXT_BYTES 36000u  // template text one tile can hold (chunk-mask table); longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
 #define IE_GENERAL_WORKERS 2048u
 
@@ -25,11 +26,19 @@ struct IeWorkspace {
 cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, cudaStream_t stream);
+                              uint64_t out_bias, uint32_t tt, cudaStream_t stream);
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, cudaStream_t stream);
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream);
+
+// Templates per tile for a batch whose templates average `avg_bytes` (0 = unknown, assume short): the
+// largest power of two <= IE_RESOLVE_TILE whose expected text fits a tile with 25 % headroom.
+inline uint32_t ie_pick_tile(uint64_t avg_bytes) {
+    uint32_t tt = IE_RESOLVE_TILE;
+    while (tt > 4 && (uint64_t)tt * avg_bytes * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
+    return tt;
+}
 
 // tag_out[i] = value tag or -1 on a miss; entry_out[i] = insert index (>= n_entries: clock key)
 cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,

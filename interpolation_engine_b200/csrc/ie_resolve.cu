@@ -286,13 +286,13 @@ cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const
 cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, cudaStream_t stream) {
+                              uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
     if ((err = ie_launch_resolve_tiles(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                                       out_bias, stream)) != cudaSuccess)
+                                       out_bias, tt, stream)) != cudaSuccess)
         return err;
     ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(tv, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap, out_bias);

@@ -41,7 +41,7 @@ namespace {
 
 using namespace ie_dev;
 
-constexpr int TT = IE_RESOLVE_TILE;  // templates per tile
+constexpr int TT = IE_RESOLVE_TILE;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
 constexpr int NT = 2 * TT;           // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int CTAS_PER_SM = 640 / TT;  // resident CTAs the register budget is tuned for (48 registers)
@@ -422,17 +422,18 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
-                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias) {
+                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias,
+                                                             uint32_t tt) {
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
     const uint32_t tile = ie_scan::acquire_tile(sm.scan, ws.tile_counter);
     PHASE_MARK(0);
-    const uint64_t i0 = (uint64_t)tile * TT;
-    const uint32_t nt = (uint32_t)min((uint64_t)TT, n - i0);
+    const uint64_t i0 = (uint64_t)tile * tt;
+    const uint32_t nt = (uint32_t)min((uint64_t)tt, n - i0);
     const uint64_t i = i0 + tid;
     const bool active = tid < nt;
-    const bool last_tile = (uint64_t)tile + 1 == (n + TT - 1) / TT;
+    const bool last_tile = (uint64_t)tile + 1 == (n + tt - 1) / tt;
 
     // ---- P0: tile extent ----------------------------------------------------------------------
     const uint64_t off0 = __ldg(offs + i0);
@@ -791,10 +792,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, cudaStream_t stream) {
-    const uint64_t tiles = (n + TT - 1) / TT;
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
+    const uint64_t tiles = (n + tt - 1) / tt;
     ie_resolve_tile_kernel<<<(unsigned)tiles, NT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
-                                                              d_aux, ws, d_info, out_bias);
+                                                              d_aux, ws, d_info, out_bias, tt);
     return cudaGetLastError();
 }
 
