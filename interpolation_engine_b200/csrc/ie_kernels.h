@@ -5,7 +5,9 @@
 #include "ie_common.cuh"
 
 #define IE_TILE 256           // strings per CTA in the escape kernel
+#ifndef IE_RESOLVE_TILE
 #define IE_RESOLVE_TILE 128   // templates per CTA tile of the resolve kernel at most
+#endif
 #define IE_TILE_TEXT_BYTES 36000u  // template text one tile can hold (chunk-mask table); longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
 #define IE_GENERAL_WORKERS 2048u

@@ -42,9 +42,15 @@ namespace {
 using namespace ie_dev;
 
 constexpr int TT = IE_RESOLVE_TILE;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
-constexpr int NT = 2 * TT;           // threads per CTA
+#ifndef IE_TILE_NT
+#define IE_TILE_NT (2 * IE_RESOLVE_TILE)
+#endif
+#ifndef IE_TILE_CTAS
+#define IE_TILE_CTAS (640 / IE_RESOLVE_TILE)
+#endif
+constexpr int NT = IE_TILE_NT;       // threads per CTA
 constexpr int NW = NT / 32;
-constexpr int CTAS_PER_SM = 640 / TT;  // resident CTAs the register budget is tuned for (48 registers)
+constexpr int CTAS_PER_SM = IE_TILE_CTAS;  // resident CTAs the register budget is tuned for (48 registers)
 constexpr int E_CAP = 12 * TT;       // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
 constexpr int M_CAP = 18 * TT;       // 16-byte chunks per tile (288 bytes of template text per template)
@@ -304,8 +310,10 @@ struct PieceCopy {  // per-thread byte copy (segment-table overflow fallback)
 
 // Assembles group g's key into 16 bytes of registers (literal pieces + inline child values).
 // Returns false when the key is longer than 16 bytes (the byte-walking path handles those).
+// `carry_e` / `carry_v`: a child whose inline value the caller already holds in registers (the group it
+// resolved just before walking up to g), saving the dependent reload of the slot.
 __device__ __forceinline__ bool short_key(const Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t g, uint4& key,
-                                          uint32_t& klen) {
+                                          uint32_t& klen, uint32_t carry_e, const uint4& carry_v) {
     key = make_uint4(0, 0, 0, 0);
     klen = 0;
     uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
@@ -321,7 +329,7 @@ __device__ __forceinline__ bool short_key(const Smem& sm, const IeTableView& tv,
         const uint32_t vl = sm.ev_a[ce];
         if (klen + vl > 16) return false;
         if (vl) {  // values of <= 16 bytes live zero-padded in their slot's 16-byte aligned inline area
-            or_shifted(key, __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[e] * 16u)), klen);
+            or_shifted(key, e == carry_e ? carry_v : __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[e] * 16u)), klen);
             klen += vl;
         }
         pos = (sm.ev_pos[ce] & POS_MASK) + 1;
@@ -342,6 +350,8 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
 // Resolves group g and then, while g was the last unresolved child of its parent, the parent too
 // (a `{q-{idx-{slot-A}}}` chain is one thread's work instead of one queue round per level).
 __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
+  uint32_t carry_e = NONE16;
+  uint4 carry_v = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
   for (;;) {
     const uint32_t c = sm.ev_match[g];
     const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
@@ -349,7 +359,7 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
     const IeSlot* hit = nullptr;
     uint4 key;
     const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
-    if (short_key(sm, tv, tp, g, key, klen)) {
+    if (short_key(sm, tv, tp, g, key, klen, carry_e, carry_v)) {
         if (klen == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
         else {
             const uint32_t h = hash_short(key, klen);
@@ -358,6 +368,7 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
                 // header and inline key are independent 16-byte loads: one L2 round trip per probe
                 const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
                 const uint4 q0 = __ldg(sp), q2 = __ldg(sp + 2);
+                q3 = __ldg(sp + 3);  // inline value: same 32-byte sector as the inline key
                 if (q0.y == IE_SLOT_EMPTY) break;
                 if (q0.x == h && q0.y == klen && q2.x == key.x && q2.y == key.y && q2.z == key.z && q2.w == key.w) {
                     hit = slots + idx; vl_tf = q0.z; val_off16 = q0.w;
@@ -414,6 +425,9 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
     __threadfence_block();
     if (atomicSub(&sm.ev_a[parent], 1u) != 1u) return;
     __threadfence_block();  // the siblings' results (written before their decrements) are visible from here on
+    // short-key hits leave the slot's inline value in q3 (valid when the value is inline)
+    carry_e = (klen <= 16 && IE_SLOT_VLEN(vl_tf) <= IE_INLINE_BYTES) ? g : NONE16;
+    carry_v = q3;
     g = parent;
   }
 }
@@ -427,8 +441,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
-    const uint32_t tile = ie_scan::acquire_tile(sm.scan, ws.tile_counter);
-    PHASE_MARK(0);
+    const uint32_t tile = blockIdx.x;
     const uint64_t i0 = (uint64_t)tile * tt;
     const uint32_t nt = (uint32_t)min((uint64_t)tt, n - i0);
     const uint64_t i = i0 + tid;
@@ -442,6 +455,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     const uint8_t* __restrict__ tp = tmpl + off0;
     const uint64_t tile_bytes64 = off_end - off0;
     if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
+    if (NT == TT && tid == 0) sm.t_start[TT] = (uint32_t)(off_end - off0);
     if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; }
     if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; }
     const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
@@ -579,12 +593,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
             if (status == IE_RES_PUNT) { olen = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i; }
         }
         uint64_t tile_total16;
-        const uint64_t loc = ie_scan::publish(sm.scan, ws.tile_state, tile, olen, 15, &tile_total16);
-        const uint64_t off = ie_scan::lookback(sm.scan, ws.tile_state, tile, tile_total16) + loc;
-        if (tid == 0 && last_tile) {
-            info->n = n;
-            atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)(off - loc + tile_total16));
-        }
+        const uint64_t loc = ie_scan::local_scan(sm.scan, olen, 15, &tile_total16);
+        const uint64_t off = ie_scan::allocate(sm.scan, &info->out_bytes, tile_total16) + loc;
+        if (tid == 0 && last_tile) info->n = n;
         if (!active) return;
         out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
         if (olen == 0) return;
@@ -642,7 +653,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     // copy sweep does not depend on the tile's global offset: the total is published first, the segment
     // table is built from tile-local offsets, and only then does the look-back collect the predecessors.
     uint64_t tile_pad64, tile_out64;  // rounded up to 16 (what successors skip) / bytes actually produced
-    const uint32_t loc = (uint32_t)ie_scan::publish(sm.scan, ws.tile_state, tile, olen, 15, &tile_pad64, &tile_out64);
+    const uint32_t loc = (uint32_t)ie_scan::local_scan(sm.scan, olen, 15, &tile_pad64, &tile_out64);
     // tile-local exclusive scan of segment counts
     uint32_t sincl = nseg;
 #pragma unroll
@@ -674,22 +685,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         if (tid == 0) { sm.u.seg.cs[0] = 0; sm.u.seg.out[total_seg] = tile_out; }
     }
     PHASE_MARK(8);
-#ifdef IE_UNORDERED_EXPERIMENT
-    if (tid == 0) sm.scan.base = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_pad64);
-    __syncthreads();
-    const uint64_t tile_begin = sm.scan.base;
+    // The tile's output range is claimed with one atomic add on the batch's byte counter: tiles land in
+    // the arena in completion order (out_offs[] carries every template's position), so no tile ever
+    // waits for a predecessor.
+    const uint64_t tile_begin = ie_scan::allocate(sm.scan, &info->out_bytes, tile_pad64);
     const uint64_t tile_end = tile_begin + tile_pad64;
     const uint64_t off = tile_begin + loc;
     if (tid == 0 && last_tile) info->n = n;
-#else
-    const uint64_t tile_begin = ie_scan::lookback(sm.scan, ws.tile_state, tile, tile_pad64);
-    const uint64_t tile_end = tile_begin + tile_pad64;
-    const uint64_t off = tile_begin + loc;
-    if (tid == 0 && last_tile) {
-        info->n = n;
-        atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)tile_end);
-    }
-#endif
     if (active) {
         out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
     }

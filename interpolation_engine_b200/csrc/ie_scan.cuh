@@ -120,6 +120,40 @@ __device__ __forceinline__ uint64_t publish(TileSmemT<NT>& sm, uint64_t* tile_st
     *tile_total_rounded = tile_total;
     return warp_off + incl - len;
 }
+// Tile-local half of publish() for kernels that do not order their tiles: the thread's exclusive prefix
+// within the tile, the tile total rounded up to round_mask + 1 and (optionally) the exact total.
+template <int NT>
+__device__ __forceinline__ uint64_t local_scan(TileSmemT<NT>& sm, uint64_t len, uint64_t round_mask, uint64_t* tile_total_rounded,
+                                               uint64_t* tile_total_raw = nullptr) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += y;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    uint64_t warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const uint64_t x = sm.warp_tot[w];
+        if (w < (int)warp) warp_off += x;
+        tile_total += x;
+    }
+    if (tile_total_raw) *tile_total_raw = tile_total;
+    *tile_total_rounded = (tile_total + round_mask) & ~round_mask;
+    return warp_off + incl - len;
+}
+// Claims `bytes` of the output arena for this tile (completion order) and returns the range's start on
+// every thread.  Must be called by all NT threads.
+template <int NT>
+__device__ __forceinline__ uint64_t allocate(TileSmemT<NT>& sm, uint64_t* counter, uint64_t bytes) {
+    if (threadIdx.x == 0) sm.base = atomicAdd(reinterpret_cast<unsigned long long*>(counter), (unsigned long long)bytes);
+    __syncthreads();
+    return sm.base;
+}
+
 template <int NT>
 __device__ __forceinline__ uint64_t lookback(TileSmemT<NT>& sm, uint64_t* tile_state, uint32_t tile, uint64_t tile_total_rounded) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -219,4 +219,13 @@ int orc_glob_sweep(const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
     return 0;
 }
 
+// Test helper: string i of arena A lives at a[a_offs[i] .. + lens[i]), of arena B at b[b_offs[i] .. + lens[i]).
+// Returns the first index whose bytes differ, or n when all are equal.
+uint64_t orc_compare_ragged(const uint8_t* a, const uint64_t* a_offs, const uint8_t* b, const uint64_t* b_offs,
+                            const uint32_t* lens, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i)
+        if (lens[i] && std::memcmp(a + a_offs[i], b + b_offs[i], lens[i]) != 0) return i;
+    return n;
+}
+
 }  // extern "C"

@@ -42,6 +42,18 @@ class Oracle:
         lib.orc_glob_sweep.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 
+        lib.orc_compare_ragged.restype = ctypes.c_uint64
+        lib.orc_compare_ragged.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_uint64]
+
+    def first_mismatch(self, a, a_offs, b, b_offs, lens):
+        """Index of the first string that differs between two (arena, offsets) pairs sharing `lens`, or None."""
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        a_offs = np.ascontiguousarray(a_offs, dtype=np.uint64)
+        b_offs = np.ascontiguousarray(b_offs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        i = self.lib.orc_compare_ragged(a.ctypes.data, a_offs.ctypes.data, b.ctypes.data, b_offs.ctypes.data, lens.ctypes.data, len(lens))
+        return None if i == len(lens) else int(i)
+
     def call(self, fn, **kw):
         """Returns ("ok", value) or ("err", {"code", "message", "payload"})."""
         kw["fn"] = fn
