@@ -97,7 +97,7 @@ def bench_escape(eng, ie, workloads, torch, dev, orc):
     res = {}
     for mode, name in ((1, "escape"), (0, "unescape")):
         def step():
-            eng._check(eng.lib.ie_escape_batch_device(eng.handle, mode, d_t.data_ptr(), d_o.data_ptr(), n, d_out.data_ptr(), cap, d_oo.data_ptr(), stream.cuda_stream))
+            eng._check(eng.lib.ie_escape_batch_device(eng.handle, mode, d_t.data_ptr(), d_o.data_ptr(), n, tmpl.bytes.nbytes, d_out.data_ptr(), cap, d_oo.data_ptr(), stream.cuda_stream))
         ms = device_time_ms(torch, stream, step, 10)
         ob = int(d_oo[-1].item())
         alg = tmpl.bytes.nbytes + ob + 2 * (n + 1) * 8

@@ -127,8 +127,11 @@ ie_status_t ie_lookup_batch(ie_engine* e, const ie_table* t, const uint8_t* keys
  * mode 0: unescape ("\{" -> "{", then "\}" -> "}");  mode 1: escape ("{" -> "\{", "}" -> "\}"). */
 ie_status_t ie_escape_batch(ie_engine* e, int mode, const uint8_t* in, const uint64_t* in_offs, uint64_t n,
                             const uint8_t** out, const uint64_t** out_offs);
+/* device arenas: in_bytes >= d_in_offs[n] - d_in_offs[0] (the caller knows its arena; it sizes the
+ * tile bookkeeping without a device->host read); d_out_offs gets n + 1 entries */
 ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n,
-                                   uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs, void* stream);
+                                   uint64_t in_bytes, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
+                                   void* stream);
 
 /* ---- wildcard_match over a key set: `delete` / `delete_except` (runtime.rs:1198-1239, 1633-1647)
  * mask bit k (uint32 words, LSB first) = key k is deleted, i.e. (any pattern matches) != invert.

@@ -61,7 +61,7 @@ ABI = {
     "ie_resolve_batch_device": (_i, [_vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_Limits), _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ie_lookup_batch": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "ie_escape_batch": (_i, [_vp, _i, _vp, _vp, _u64, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
-    "ie_escape_batch_device": (_i, [_vp, _i, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "ie_escape_batch_device": (_i, [_vp, _i, _vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
     "ie_glob_sweep": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _i, _vp, ctypes.POINTER(_u64)]),
     "ie_glob_sweep_device": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _i, _vp, _vp, _vp]),
     "ie_device_alloc": (_i, [_vp, _u64, ctypes.POINTER(_vp)]),

@@ -80,8 +80,7 @@ struct ie_table {
 namespace {
 
 // Lays the per-batch workspace out for n items; returns the kernel-side view.
-ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws, uint32_t tt = IE_RESOLVE_TILE) {
-    const uint64_t tiles = (n + tt - 1) / tt;
+ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws, uint64_t tiles) {
     const size_t zero_bytes = 64 + (size_t)(tiles + 1) * sizeof(uint64_t);
     CU(e->ws_zero.ensure(zero_bytes, e->stream));
     ws->zero_base = (uint8_t*)e->ws_zero.p;
@@ -89,6 +88,9 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     ws->tile_counter = (uint32_t*)e->ws_zero.p;
     ws->general_count = ws->tile_counter + 1;
     ws->overflow = ws->tile_counter + 2;
+    ws->fix_count = ws->tile_counter + 3;
+    ws->fix_list = nullptr;
+    ws->tile_first = nullptr;
     ws->tile_state = (uint64_t*)((uint8_t*)e->ws_zero.p + 64);
     ws->general_list = nullptr;
     ws->scratch = nullptr;
@@ -219,7 +221,7 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     if (!avg_bytes && limits) avg_bytes = limits->avg_template_bytes;
     const uint32_t tt = ie_pick_tile(avg_bytes);
     IeWorkspace ws;
-    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws, tt);
+    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws, 0);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                          max_exp, tcap, out_bias, tt, s));
@@ -281,7 +283,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         uint32_t max_exp, tcap;
         resolve_limits(limits, &max_exp, &tcap);
         IeWorkspace ws;
-        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, ie_pick_tile(in_bytes / n));
+        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, 0);
         if (st != IE_OK) return st;
     }
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
@@ -426,15 +428,18 @@ ie_status_t ie_lookup_batch(ie_engine* e, const ie_table* t, const uint8_t* keys
     return IE_OK;
 }
 
-ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint8_t* d_out,
-                                   uint64_t out_capacity, uint64_t* d_out_offs, void* stream) {
+ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint64_t in_bytes,
+                                   uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs, void* stream) {
     if (!e || !d_out_offs || (n && !d_in_offs) || (mode != 0 && mode != 1)) return fail(IE_E_INVALID, "ie_escape_batch_device: bad argument");
     CU(cudaSetDevice(e->device));
     IeWorkspace ws;
-    ie_status_t st = prepare_workspace(e, n, 0, false, &ws);
+    ie_status_t st = prepare_workspace(e, n, 0, false, &ws, ie_escape_tiles(in_bytes));
     if (st != IE_OK) return st;
+    CU(e->ws_list.ensure(((size_t)IE_ESCAPE_FIX_CAP + ie_escape_tiles(in_bytes) + 1) * sizeof(uint64_t), e->stream));
+    ws.fix_list = (uint64_t*)e->ws_list.p;
+    ws.tile_first = ws.fix_list + IE_ESCAPE_FIX_CAP;
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    CU(ie_launch_escape(mode, d_in, d_in_offs, n, d_out, out_capacity, d_out_offs, ws, s));
+    CU(ie_launch_escape(mode, d_in, d_in_offs, n, in_bytes, d_out, out_capacity, d_out_offs, ws, s));
     return IE_OK;
 }
 
@@ -453,8 +458,8 @@ ie_status_t ie_escape_batch(ie_engine* e, int mode, const uint8_t* in, const uin
     CU(e->h_out_offs.ensure((n + 1) * 8));
     if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
     if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, in_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    ie_status_t st = ie_escape_batch_device(e, mode, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (uint8_t*)e->d_out.p,
-                                            cap, (uint64_t*)e->d_out_offs.p, s);
+    ie_status_t st = ie_escape_batch_device(e, mode, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, in_bytes,
+                                            (uint8_t*)e->d_out.p, cap, (uint64_t*)e->d_out_offs.p, s);
     if (st != IE_OK) return st;
     CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

@@ -4,7 +4,6 @@
 
 #include "ie_common.cuh"
 
-#define IE_TILE 256           // strings per CTA in the escape kernel
 #ifndef IE_RESOLVE_TILE
 #define IE_RESOLVE_TILE 128   // templates per CTA tile of the resolve kernel at most
 #endif
@@ -19,6 +18,9 @@ struct IeWorkspace {
     uint32_t* tile_counter;   // dynamic tile ids (look-back forward progress)
     uint32_t* general_count;  // templates handed to the general kernel
     uint32_t* overflow;       // set when the out arena was too small
+    uint32_t* fix_count;      // escape kernel: entries of fix_list (may exceed IE_ESCAPE_FIX_CAP)
+    uint64_t* fix_list;       // escape kernel: [IE_ESCAPE_FIX_CAP] positions of string-final backslashes
+    uint64_t* tile_first;     // escape kernel: [tiles + 1] first string starting at or after each tile
     uint64_t* tile_state;     // [tiles] flag << 62 | bytes
     uint32_t* general_list;   // [n]
     uint8_t* scratch;         // general_workers * (tcap + IE_KEY_SCRATCH)
@@ -46,8 +48,12 @@ inline uint32_t ie_pick_tile(uint64_t avg_bytes) {
 cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,
                              uint32_t* d_entry, cudaStream_t stream);
 
-// mode 0 unescape, 1 escape (interp.rs:147-177).  d_tile_state: [(n + IE_TILE - 1) / IE_TILE + 1] zeroed words.
-cudaError_t ie_launch_escape(int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint8_t* d_out,
+// mode 0 unescape, 1 escape (interp.rs:147-177).  in_bytes >= d_in_offs[n] - d_in_offs[0]; the workspace holds
+// ie_escape_tiles(in_bytes) + 1 zeroed look-back words.
+#define IE_ESCAPE_TILE_BYTES 8192u
+#define IE_ESCAPE_FIX_CAP 1024u
+inline uint64_t ie_escape_tiles(uint64_t in_bytes) { return (in_bytes + 15 + IE_ESCAPE_TILE_BYTES - 1) / IE_ESCAPE_TILE_BYTES + 1; }
+cudaError_t ie_launch_escape(int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint64_t in_bytes, uint8_t* d_out,
                              uint64_t out_cap, uint64_t* d_out_offs, const IeWorkspace& ws, cudaStream_t stream);
 
 struct IeGlobPatterns {  // passed by value as a kernel parameter (<= 4 KiB)

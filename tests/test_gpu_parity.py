@@ -197,6 +197,57 @@ def test_escape_unescape(eng, oracle):
     assert [b.decode() for b in back] == strings
 
 
+def _two_pass(b, mode):
+    """interp.rs:149 / :165 verbatim: two sequential non-overlapping replaces (bytes.replace == str::replace)."""
+    if mode == 0:
+        return b.replace(b"\\{", b"{").replace(b"\\}", b"}")
+    return b.replace(b"{", b"\\{").replace(b"}", b"\\}")
+
+
+def test_escape_flat_stream_edges(eng):
+    """The escape kernel treats the arena as one byte stream cut into 8 KiB tiles: string boundaries, tile
+    boundaries and 16-byte chunk boundaries must not leak ('\\' ending one string + '{' starting the next)."""
+    rng = random.Random(11)
+    alpha = [b"{", b"}", b"\\", b"\\{", b"\\}", b"a", b"bc", b" ", b"\xc3\xa9"]
+    strings = []
+    for k in range(6000):
+        r = rng.random()
+        if r < 0.15:
+            n = 0
+        elif r < 0.85:
+            n = rng.randint(1, 60)
+        elif r < 0.99:
+            n = rng.randint(60, 700)
+        else:
+            n = rng.randint(8000, 20000)  # longer than a tile
+        body = b"".join(rng.choice(alpha) for _ in range(n))
+        if rng.random() < 0.3:
+            body += b"\\"                       # ends with a backslash ...
+        if strings and rng.random() < 0.3:
+            body = rng.choice([b"{", b"}"]) + body  # ... and the next one starts with a brace
+        strings.append(body)
+    strings += [b"", b"", b"\\", b"{", b""]         # trailing empties
+    for sub in (strings, strings[:1], [b""], [b"", b""], strings[100:164], [b"\\", b"{"], [b"x" * 8192], [b"{" * 8191 + b"\\", b"}"]):
+        arena = ie.Arena.from_strings(sub)
+        for mode in (0, 1):
+            got = eng.escape_batch(arena, mode).strings()
+            want = [_two_pass(x, mode) for x in sub]
+            assert len(got) == len(want)
+            for i, (g, w) in enumerate(zip(got, want)):
+                assert g == w, (mode, i, sub[i][:80], g[:80], w[:80])
+
+
+def test_escape_full_size_roundtrip(eng):
+    """BASELINE-size property: the 1 Mi C4 templates escaped then unescaped are the original arena, and the
+    escaped arena grows by exactly one byte per brace."""
+    tmpl = workloads.c4_templates(1 << 20)
+    esc = eng.escape_batch(tmpl, 1)
+    braces = int(np.count_nonzero((tmpl.bytes == ord("{")) | (tmpl.bytes == ord("}"))))
+    assert int(esc.offs[-1]) == tmpl.bytes.nbytes + braces
+    back = eng.escape_batch(esc, 0)
+    assert np.array_equal(back.offs, tmpl.offs) and np.array_equal(back.bytes[:int(back.offs[-1])], tmpl.bytes)
+
+
 # ---- wildcard sweeps -------------------------------------------------------------------------------
 def test_wildcard_match_and_delete(eng, oracle):
     with open(GOLDEN) as f:
