@@ -479,6 +479,7 @@ static ie_status_t pack_patterns(const uint8_t* pats, const uint64_t* pat_offs, 
     gp->invert = invert ? 1u : 0u;
     for (uint32_t i = 0; i <= n_pat && n_pat; ++i) gp->off[i] = (uint16_t)pat_offs[i];
     if (n_pat && pat_offs[n_pat]) std::memcpy(gp->bytes, pats, pat_offs[n_pat]);
+    ie_glob_compile(gp);
     return IE_OK;
 }
 

@@ -6,7 +6,15 @@
 // gaps", matched here directly on bytes (equivalent on valid UTF-8).  One thread per key,
 // 32 keys per warp -> one coalesced mask word per warp via ballot.  Patterns ride in the kernel
 // parameter block (constant bank, broadcast reads).
+//
+// Patterns with at most one '*' (after collapsing runs of stars) and literal pieces of <= 32 bytes —
+// every shape the reference's examples use ("persona/*", "*/field", "a*b", plain literals) — are compiled
+// on the host into masked 32-byte prefix / suffix images: a key matches iff its length fits and its first
+// and last 32 bytes agree under the masks, i.e. a handful of word compares on registers instead of a byte
+// loop.  Anything else runs the generic byte matcher.
 #include <cuda_runtime.h>
+
+#include <cstring>
 
 #include "ie_kernels.h"
 
@@ -24,60 +32,228 @@ __device__ __forceinline__ bool glob_match(const uint8_t* __restrict__ p, uint32
     return pi == pn;
 }
 
-constexpr int GLOB_CTA = 256;           // keys per CTA
-constexpr uint32_t STAGE_BYTES = 24576;  // key text of one CTA staged in shared memory (96 bytes per key on average)
+constexpr int GLOB_CTA = 256;            // threads per CTA
+constexpr int MAX_KPT = 4;               // keys per thread and tile, picked from the mean key length
+constexpr uint32_t STAGE_BYTES = 24576;  // key text of one tile staged in shared memory
+constexpr uint32_t FRONT_PAD = 32, BACK_PAD = 48;  // the 32-byte windows of the first / last key may overhang the text
+constexpr uint32_t BUF_BYTES = FRONT_PAD + STAGE_BYTES + BACK_PAD;
+constexpr int GLOB_CTAS_PER_SM = 4;      // two stage buffers per CTA
 
-// The 256 keys of a CTA are contiguous in the arena: their text is staged with coalesced 16-byte loads,
-// then every thread matches its own key out of shared memory (tiles whose text exceeds the stage read
-// global memory directly).
-__global__ void __launch_bounds__(GLOB_CTA) ie_glob_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ offs, uint64_t n,
-                                                           const __grid_constant__ IeGlobPatterns pats, uint32_t* __restrict__ mask,
-                                                           unsigned long long* __restrict__ n_deleted) {
-    __shared__ __align__(16) uint8_t stage[STAGE_BYTES + 32];
-    __shared__ unsigned int s_deleted;
-    const uint64_t k0 = (uint64_t)blockIdx.x * GLOB_CTA;
-    const uint64_t k = k0 + threadIdx.x;
-    const uint32_t nk = (uint32_t)min((uint64_t)GLOB_CTA, n - k0);
-    const uint64_t b0 = __ldg(offs + k0), b1 = __ldg(offs + k0 + nk);
-    const uint64_t a = k < n ? __ldg(offs + k) : b1;
-    const uint64_t a_next = k < n ? __ldg(offs + k + 1) : b1;
-    if (threadIdx.x == 0) s_deleted = 0;
-    const uintptr_t g0 = (uintptr_t)(keys + b0) & ~(uintptr_t)15;   // aligned floor of the tile's first byte
-    const uint32_t lead = (uint32_t)((uintptr_t)(keys + b0) - g0);
-    const bool staged = (b1 - b0) + lead <= STAGE_BYTES;
-    if (staged) {
-        const uint32_t chunks = (uint32_t)((b1 - b0) + lead + 15) >> 4;
-        for (uint32_t c = threadIdx.x; c < chunks; c += GLOB_CTA)
-            *reinterpret_cast<uint4*>(stage + 16 * c) = __ldg(reinterpret_cast<const uint4*>(g0) + c);
+// 32 bytes starting at p (shared memory, any alignment) as 8 little-endian words
+__device__ __forceinline__ void load_window(const uint8_t* p, uint32_t (&w)[8]) {
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+    uint32_t x[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = aw[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
+}
+
+__device__ __forceinline__ bool match_key(const IeGlobPatterns& pats, const uint8_t* s, uint32_t len, bool staged) {
+    // Per pattern, a PROBE first: the last word of the prefix image and the last word of the key against
+    // the last word of the suffix image (the most discriminating ones: "persona-123/" differs from most
+    // keys in "123/", "/field-42" in "d-42").  Only keys that pass the probe of a pattern with longer pieces
+    // load their full 32-byte windows.
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>((uintptr_t)s & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)s & 3) * 8;
+    uint32_t t7 = 0;
+    if (staged && pats.any_suf) {
+        const uint8_t* e4 = s + len - 4;
+        const uint32_t* ew = reinterpret_cast<const uint32_t*>((uintptr_t)e4 & ~(uintptr_t)3);
+        t7 = __funnelshift_r(ew[0], ew[1], (uint32_t)((uintptr_t)e4 & 3) * 8);
     }
-    __syncthreads();
-    bool del = false;
-    if (k < n) {
-        const uint32_t len = (uint32_t)(a_next - a);
-        const uint8_t* s = staged ? stage + lead + (uint32_t)(a - b0) : keys + a;
-        bool any = false;
-        for (uint32_t q = 0; q < pats.n_pat && !any; ++q)
+    bool any = false;
+    for (uint32_t q = 0; q < pats.n_pat && !any; ++q) {
+        const IeGlobFast& f = pats.fast[q];
+        if (staged && f.kind != IE_GLOB_GENERIC) {
+            const uint32_t pi = f.probe;
+            const uint32_t hw = __funnelshift_r(aw[pi], aw[pi + 1], sh);
+            bool cand = (((hw ^ f.pre[pi]) & f.pre_mask[pi]) | ((t7 ^ f.suf[7]) & f.suf_mask[7])) == 0 &&
+                        (f.exact ? len == f.min_len : len >= f.min_len);
+            if (cand && (!f.complete || f.kind == IE_GLOB_MID)) {
+                uint32_t H[8], T[8];  // the key's first / last 32 bytes (bytes outside the key are masked out)
+                load_window(s, H);
+                if (!f.complete) {
+                    load_window(s + len - 32, T);
+                    uint32_t diff = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) diff |= ((H[w] ^ f.pre[w]) & f.pre_mask[w]) | ((T[w] ^ f.suf[w]) & f.suf_mask[w]);
+                    cand = diff == 0;
+                }
+                if (cand && f.kind == IE_GLOB_MID) {
+                    if (len > 32) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
+                    else {
+                        // positions of the window where the middle piece's first bytes occur, between prefix and suffix
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t lo = H[i >> 2], hi = (i >> 2) < 7 ? H[(i >> 2) + 1] : 0u;
+                            const uint32_t wv = (i & 3) ? __funnelshift_r(lo, hi, 8 * (i & 3)) : lo;
+                            hits |= (((wv ^ f.mid) & f.mid_mask) == 0 ? 1u : 0u) << i;
+                        }
+                        const uint32_t first = f.mid_lo, last = len - f.mid_hi;  // allowed start positions [first, last]
+                        const uint32_t range = (last >= 31 ? 0xFFFFFFFFu : (2u << last) - 1u) & ~((1u << first) - 1u);
+                        hits &= range;
+                        cand = hits != 0;
+                        if (cand && f.mid_len > 4) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
+                    }
+                }
+            }
+            any = cand;
+        } else {
             any = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
-        del = any != (pats.invert != 0);
+        }
     }
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, del);
-    if ((threadIdx.x & 31) == 0) {
-        if (k < n) mask[k >> 5] = word;
-        if (word) atomicAdd(&s_deleted, (unsigned int)__popc(word));
+    return any;
+}
+
+// Persistent CTAs, grid-stride over tiles of 256 * kpt consecutive keys.  The text of a tile is contiguous in
+// the arena: it is brought into shared memory by 16-byte cp.async copies, double buffered, so the copies of
+// tile i+1 (and the offset loads of tile i+2's bounds) are in flight while tile i is matched out of shared
+// memory.  Tiles whose text exceeds the stage are matched from global memory by the generic matcher.
+__global__ void __launch_bounds__(GLOB_CTA, GLOB_CTAS_PER_SM) ie_glob_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ offs,
+                                                                             uint64_t n, const __grid_constant__ IeGlobPatterns pats,
+                                                                             uint32_t* __restrict__ mask, unsigned long long* __restrict__ n_deleted) {
+    extern __shared__ __align__(16) uint8_t stage_raw[];  // [2][BUF_BYTES]
+    __shared__ unsigned int s_deleted;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_deleted = 0;
+    // keys per thread: the largest of 1, 2, 4 whose expected tile text fits the stage with 25 % headroom
+    const uint64_t total = __ldg(offs + n) - __ldg(offs);
+    uint32_t kpt = MAX_KPT;
+    while (kpt > 1 && (total / n + 1) * 5 / 4 * (GLOB_CTA * kpt) > STAGE_BYTES) kpt >>= 1;
+    const uint32_t tile_keys = GLOB_CTA * kpt;
+    const uint64_t n_tiles = (n + tile_keys - 1) / tile_keys;
+
+    struct Bounds { uint64_t b0, b1; };
+    auto bounds_of = [&](uint64_t tile) {
+        const uint64_t k0 = tile * tile_keys;
+        const uint64_t k1 = min(n, k0 + tile_keys);
+        return Bounds{__ldg(offs + k0), __ldg(offs + k1)};
+    };
+    auto issue_copy = [&](const Bounds& bd, uint32_t buf) {  // returns nothing; oversized tiles are not staged
+        const uintptr_t g0 = (uintptr_t)(keys + bd.b0) & ~(uintptr_t)15;
+        const uint32_t lead = (uint32_t)((uintptr_t)(keys + bd.b0) - g0);
+        if ((bd.b1 - bd.b0) + lead <= STAGE_BYTES) {
+            const uint32_t chunks = (uint32_t)((bd.b1 - bd.b0) + lead + 15) >> 4;
+            const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(stage_raw + buf * BUF_BYTES + FRONT_PAD);
+            for (uint32_t c = tid; c < chunks; c += GLOB_CTA)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16 * c), "l"(g0 + 16 * (uintptr_t)c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint64_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    Bounds cur = bounds_of(tile);
+    issue_copy(cur, 0);
+    uint32_t buf = 0, my_deleted = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t next = tile + gridDim.x;
+        const uint64_t k0 = tile * tile_keys;
+        // this tile's key offsets and the next tile's bounds travel while the text copies are in flight
+        uint64_t a[MAX_KPT], a_next[MAX_KPT];
+#pragma unroll
+        for (int j = 0; j < MAX_KPT; ++j) {
+            const uint64_t k = k0 + (uint64_t)j * GLOB_CTA + tid;
+            a[j] = a_next[j] = 0;
+            if (j < (int)kpt && k < n) { a[j] = __ldg(offs + k); a_next[j] = __ldg(offs + k + 1); }
+        }
+        Bounds nxt = cur;
+        if (next < n_tiles) nxt = bounds_of(next);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (next < n_tiles) issue_copy(nxt, buf ^ 1);
+        const uint32_t lead = (uint32_t)((uintptr_t)(keys + cur.b0) & 15);
+        const bool staged = (cur.b1 - cur.b0) + lead <= STAGE_BYTES;
+        const uint8_t* text = stage_raw + buf * BUF_BYTES + FRONT_PAD + lead;
+#pragma unroll
+        for (int j = 0; j < MAX_KPT; ++j) {
+            if (j >= (int)kpt) break;
+            const uint64_t k = k0 + (uint64_t)j * GLOB_CTA + tid;
+            if (k0 + (uint64_t)j * GLOB_CTA >= n) break;  // uniform: nothing left in this row
+            bool del = false;
+            if (k < n) {
+                const uint32_t len = (uint32_t)(a_next[j] - a[j]);
+                const uint8_t* s = staged ? text + (uint32_t)(a[j] - cur.b0) : keys + a[j];
+                del = match_key(pats, s, len, staged) != (pats.invert != 0);
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, del);
+            if ((tid & 31) == 0 && k < n) { mask[k >> 5] = word; my_deleted += __popc(word); }
+        }
+        cur = nxt;  // stage[buf] is overwritten only after the next iteration's barrier, which every thread reaches after this point
+        buf ^= 1;
     }
+    if (my_deleted) atomicAdd(&s_deleted, my_deleted);
     __syncthreads();
-    if (threadIdx.x == 0 && s_deleted) atomicAdd(n_deleted, (unsigned long long)s_deleted);
+    if (tid == 0 && s_deleted) atomicAdd(n_deleted, (unsigned long long)s_deleted);
 }
 
 }  // namespace
+
+// Host: fills pats->fast[] from pats->bytes / off (see the header comment).
+void ie_glob_compile(IeGlobPatterns* pats) {
+    pats->any_pre = pats->any_suf = 0;
+    for (uint32_t q = 0; q < pats->n_pat; ++q) {
+        IeGlobFast& f = pats->fast[q];
+        std::memset(&f, 0, sizeof f);
+        f.kind = IE_GLOB_GENERIC;
+        f.suf_first = 8;
+        const uint8_t* p = pats->bytes + pats->off[q];
+        const uint32_t pn = (uint32_t)pats->off[q + 1] - pats->off[q];
+        // split at the star runs: at most two of them
+        uint32_t run_lo[2] = {0, 0}, run_hi[2] = {0, 0}, runs = 0;  // [lo, hi) of each run of stars
+        for (uint32_t i = 0; i < pn; ++i)
+            if (p[i] == '*') {
+                if (i == 0 || p[i - 1] != '*') { if (runs < 2) run_lo[runs] = i; ++runs; }
+                if (runs <= 2) run_hi[runs - 1] = i + 1;
+            }
+        if (runs > 2) continue;
+        const uint32_t pre_len = runs ? run_lo[0] : pn;
+        const uint32_t suf_len = runs ? pn - run_hi[runs - 1] : 0;
+        const uint32_t mid_len = runs == 2 ? run_lo[1] - run_hi[0] : 0;
+        if (pre_len > 32 || suf_len > 32 || mid_len > 32) continue;
+        f.kind = runs == 2 ? IE_GLOB_MID : IE_GLOB_FAST;
+        f.exact = runs == 0;
+        f.min_len = (uint16_t)(pre_len + mid_len + suf_len);
+        uint8_t img[32], msk[32];
+        std::memset(img, 0, 32); std::memset(msk, 0, 32);
+        for (uint32_t j = 0; j < pre_len; ++j) { img[j] = p[j]; msk[j] = 0xFF; }
+        std::memcpy(f.pre, img, 32); std::memcpy(f.pre_mask, msk, 32);
+        f.pre_words = (uint8_t)((pre_len + 3) / 4);
+        std::memset(img, 0, 32); std::memset(msk, 0, 32);
+        for (uint32_t j = 0; j < suf_len; ++j) { img[32 - suf_len + j] = p[pn - suf_len + j]; msk[32 - suf_len + j] = 0xFF; }
+        std::memcpy(f.suf, img, 32); std::memcpy(f.suf_mask, msk, 32);
+        f.suf_first = (uint8_t)(8 - (suf_len + 3) / 4);
+        f.probe = (uint8_t)(f.pre_words ? f.pre_words - 1 : 0);
+        f.complete = pre_len <= 4 && suf_len <= 4;
+        if (runs == 2) {
+            std::memset(img, 0, 4); std::memset(msk, 0, 4);
+            for (uint32_t j = 0; j < mid_len && j < 4; ++j) { img[j] = p[run_hi[0] + j]; msk[j] = 0xFF; }
+            std::memcpy(&f.mid, img, 4); std::memcpy(&f.mid_mask, msk, 4);
+            f.mid_len = mid_len;
+            f.mid_lo = (uint8_t)pre_len;               // the middle piece may start at pre_len ...
+            f.mid_hi = (uint8_t)(suf_len + mid_len);   // ... up to len - suf_len - mid_len
+        }
+        if (pre_len) pats->any_pre = 1;
+        if (suf_len) pats->any_suf = 1;
+    }
+}
 
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
                            uint32_t* d_mask, uint64_t* d_n_deleted, cudaStream_t stream) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(d_n_deleted, 0, sizeof(uint64_t), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
-    const uint64_t blocks = (n + GLOB_CTA - 1) / GLOB_CTA;
-    ie_glob_kernel<<<(unsigned)blocks, GLOB_CTA, 0, stream>>>(d_keys, d_key_offs, n, pats, d_mask,
-                                                        reinterpret_cast<unsigned long long*>(d_n_deleted));
+    if ((err = cudaFuncSetAttribute(ie_glob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * BUF_BYTES))) != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t min_tiles = (n + GLOB_CTA * MAX_KPT - 1) / (GLOB_CTA * MAX_KPT);  // the kernel may pick smaller tiles: more of them
+    const uint64_t resident = (uint64_t)sms * GLOB_CTAS_PER_SM;
+    const uint64_t blocks = min_tiles < resident ? min_tiles : resident;
+    ie_glob_kernel<<<(unsigned)blocks, GLOB_CTA, 2 * BUF_BYTES, stream>>>(d_keys, d_key_offs, n, pats, d_mask,
+                                                                          reinterpret_cast<unsigned long long*>(d_n_deleted));
     return cudaGetLastError();
 }

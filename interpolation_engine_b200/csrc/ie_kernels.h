@@ -56,11 +56,28 @@ inline uint64_t ie_escape_tiles(uint64_t in_bytes) { return (in_bytes + 15 + IE_
 cudaError_t ie_launch_escape(int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n, uint64_t in_bytes, uint8_t* d_out,
                              uint64_t out_cap, uint64_t* d_out_offs, const IeWorkspace& ws, cudaStream_t stream);
 
-struct IeGlobPatterns {  // passed by value as a kernel parameter (<= 4 KiB)
+#define IE_GLOB_GENERIC 0
+#define IE_GLOB_FAST 1  // prefix * suffix (either may be empty; no star at all: exact)
+#define IE_GLOB_MID 2   // prefix * middle * suffix: the middle piece is searched between the two
+struct IeGlobFast {  // a pattern with at most two '*' runs and literal pieces of <= 32 bytes, compiled by ie_glob_compile
+    uint32_t pre[8], pre_mask[8];  // image / mask of the key's first 32 bytes
+    uint32_t suf[8], suf_mask[8];  // image / mask of the key's last 32 bytes (right aligned)
+    uint16_t min_len;              // prefix + suffix bytes
+    uint8_t kind, exact;           // exact: no star, the key must be exactly min_len long
+    uint8_t pre_words, suf_first;  // words [0, pre_words) of pre and [suf_first, 8) of suf carry mask bits
+    uint8_t probe, complete;       // probe: the prefix word tested first; complete: the probe already is the whole test
+    uint32_t mid, mid_mask;        // IE_GLOB_MID: image / mask of the first (up to 4) bytes of the middle piece
+    uint16_t mid_len;
+    uint8_t mid_lo, mid_hi;        // allowed start positions of the middle piece: [mid_lo, len - mid_hi]
+};
+struct IeGlobPatterns {  // passed by value as a kernel parameter (about 12 KiB; CUDA >= 12.1 allows 32 KiB)
     uint32_t n_pat;
     uint32_t invert;
+    uint32_t any_pre, any_suf;
     uint16_t off[IE_MAX_PATTERNS + 1];
     uint8_t bytes[3584];
+    IeGlobFast fast[IE_MAX_PATTERNS];
 };
+void ie_glob_compile(IeGlobPatterns* pats);  // host: fills fast[] / any_pre / any_suf from bytes / off
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
                            uint32_t* d_mask, uint64_t* d_n_deleted, cudaStream_t stream);

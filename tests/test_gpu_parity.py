@@ -281,6 +281,29 @@ def test_glob_sweep_random_and_ragged(eng, oracle):
             assert nd == int(sum(bin(int(w)).count("1") for w in want))
 
 
+def test_glob_compiled_patterns_edges(eng, oracle):
+    """Patterns with at most one '*' run and pieces of <= 32 bytes are compiled to masked 32-byte prefix /
+    suffix compares; everything around those limits must still agree with the oracle, pattern by pattern."""
+    rng = random.Random(23)
+    words = ["persona-1", "persona-12/", "/field-7", "field", "x" * 31, "y" * 32, "z" * 33, "ab", "ba", "a", ""]
+    keys = ["", "a", "ab", "aba", "abba", "ab" * 20, "persona-1", "persona-12/field-7", "persona-123/field-77", "x" * 31, "x" * 32,
+            "x" * 33, "y" * 32 + "q" + "y" * 32, "z" * 33, "z" * 66, "y" * 64, "y" * 63, "/field-7", "persona-12//field-7"]
+    keys += ["".join(rng.choice(words) for _ in range(rng.randint(0, 4))) for _ in range(3000)]
+    pats = ["", "*", "**", "a*", "*a", "ab*ba", "a**a", "a*b*a", "persona-12/*", "*/field-7", "persona-1*/field-7", "persona-12/field-7",
+            "x" * 31 + "*", "x" * 32 + "*", "x" * 33 + "*", "*" + "y" * 32, "*" + "z" * 33, "y" * 32 + "*" + "y" * 32, "y" * 32 + "y" * 32,
+            "z" * 33, "ab*", "*ab*", "***ab", "ab***"]
+    ka = ie.Arena.from_strings(keys)
+    for pat in pats:
+        pa = ie.Arena.from_strings([pat])
+        for invert in (False, True):
+            mask, nd = eng.glob_sweep(ka, pa, invert)
+            want = oracle.glob_sweep(ka.bytes, ka.offs, pa.bytes, pa.offs, invert, threads=2)
+            assert np.array_equal(mask, want), (pat, invert)
+    pa = ie.Arena.from_strings(pats)
+    mask, nd = eng.glob_sweep(ka, pa, False)
+    assert np.array_equal(mask, oracle.glob_sweep(ka.bytes, ka.offs, pa.bytes, pa.offs, False, threads=2))
+
+
 def test_c5_sweep_reduced_and_full(eng, oracle):
     """C5: reduced size bit-exact vs oracle for every pattern set; full 10 M keys for one set vs the
     oracle plus the invert-complement property for the rest."""
