@@ -91,8 +91,18 @@ ie_status_t ie_engine_sync(ie_engine* e);
 ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const uint64_t* key_offs,
                           const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags,
                           const char* hhmm, const char* hhmmss, ie_table** out);
+/* Many snapshots at once (the cloned states of one program, runtime.rs:700 called once per state):
+ * snapshot s owns the inserts [state_offs[s], state_offs[s+1]) of the packed arrays.  One device
+ * allocation and one upload; the images are built on several host threads.  A table that holds S
+ * snapshots makes every ie_resolve_batch* call a cross product: all n templates are resolved against
+ * every snapshot, result index = s * n + template, and every result array holds S * n entries.
+ * `aux` entry indices are relative to the snapshot's first insert. */
+ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys,
+                               const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
+                               const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out);
 void ie_table_free(ie_table* t);
 uint64_t ie_table_device_bytes(const ie_table* t);
+uint32_t ie_table_states(const ie_table* t); /* snapshots held (1 for ie_table_pack) */
 
 /* ---- interpolate_inserts, batched (interp.rs:31-89) -----------------------------------------
  * Host-buffer form: copies the template arena to the device, resolves all n templates against
@@ -100,7 +110,8 @@ uint64_t ie_table_device_bytes(const ie_table* t);
  * next call on the same engine. */
 typedef struct {
     const uint8_t* out;       /* result bytes */
-    const uint64_t* out_offs; /* [n] start of result i in `out` */
+    const uint64_t* out_offs; /* [n] start of result i in `out` (tiles claim arena ranges in completion
+                                 order: positions are not monotone in i, and gaps of < 16 bytes separate tiles) */
     const uint32_t* out_lens; /* [n] length of result i */
     const int32_t* status;    /* [n] IE_RES_* | tag << 8 */
     const uint32_t* aux;      /* [n] insert entry index for IE_RES_TYPED */

@@ -55,6 +55,8 @@ ABI = {
     "ie_engine_stream": (_vp, [_vp]),
     "ie_engine_sync": (_i, [_vp]),
     "ie_table_pack": (_i, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "ie_table_pack_many": (_i, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "ie_table_states": (_u32, [_vp]),
     "ie_table_free": (None, [_vp]),
     "ie_table_device_bytes": (_u64, [_vp]),
     "ie_resolve_batch": (_i, [_vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_Limits), ctypes.POINTER(_Result)]),
@@ -284,6 +286,34 @@ class Engine:
                                            hhmm.encode() if hhmm else None, hhmmss.encode() if hhmmss else None, ctypes.byref(h)))
         return Table(self, h, packed)
 
+    def pack_many(self, states, hhmm=None, hhmmss=None):
+        """Packs a list of snapshots (dicts or PackedInserts) into ONE table; resolve_batch on it resolves every
+        template against every snapshot (result index = snapshot * n_templates + template)."""
+        packs = [st if isinstance(st, PackedInserts) else PackedInserts.from_dict(st) for st in states]
+        state_offs = np.zeros(len(packs) + 1, dtype=np.uint64)
+        state_offs[1:] = np.cumsum([pk.n for pk in packs], dtype=np.uint64)
+        kb = np.concatenate([pk.keys for pk in packs]) if packs else np.zeros(0, np.uint8)
+        vb = np.concatenate([pk.vals for pk in packs]) if packs else np.zeros(0, np.uint8)
+        tags = np.concatenate([pk.tags for pk in packs]) if packs else np.zeros(0, np.uint8)
+
+        def cat_offs(arrs):
+            out = np.zeros(int(state_offs[-1]) + 1, dtype=np.uint64)
+            base, pos = 0, 0
+            for a in arrs:
+                m = len(a) - 1
+                out[pos:pos + m + 1] = a + np.uint64(base)
+                base += int(a[-1])
+                pos += m
+            return out
+        ko, vo = cat_offs([pk.key_offs for pk in packs]), cat_offs([pk.val_offs for pk in packs])
+        merged = PackedInserts(kb, ko, vb, vo, tags)
+        h = ctypes.c_void_p()
+        self._check(self.lib.ie_table_pack_many(self.handle, len(packs), _ptr(state_offs), _ptr(kb), _ptr(ko), _ptr(vb), _ptr(vo), _ptr(tags),
+                                                hhmm.encode() if hhmm else None, hhmmss.encode() if hhmmss else None, ctypes.byref(h)))
+        t = Table(self, h, merged)
+        t.n_states = len(packs)
+        return t
+
     # ---- interpolate_inserts, batched (interp.rs:31-89) ----------------------------------------
     def resolve_batch(self, table, templates, limits=None):
         arena = templates if isinstance(templates, Arena) else Arena.from_strings(templates)
@@ -291,7 +321,7 @@ class Engine:
         lim = _Limits(*limits) if limits else None
         self._check(self.lib.ie_resolve_batch(self.handle, table.handle, _ptr(arena.bytes), _ptr(arena.offs), arena.n,
                                               ctypes.byref(lim) if lim else None, ctypes.byref(res)))
-        n, ob = arena.n, int(res.info.out_bytes)
+        n, ob = arena.n * getattr(table, "n_states", 1), int(res.info.out_bytes)
 
         def view(p, dtype, count):
             if not count:

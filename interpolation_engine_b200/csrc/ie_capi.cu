@@ -8,6 +8,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "ie_host.hpp"
@@ -72,9 +74,11 @@ struct ie_engine {
 
 struct ie_table {
     ie_engine* e = nullptr;
-    void* d_base = nullptr;
+    void* d_base = nullptr;       // every snapshot's image, back to back, followed by the view array
     size_t bytes = 0;
-    IeTableView view{};
+    IeTableView view{};           // snapshot 0 (ie_lookup_batch)
+    const IeTableView* d_views = nullptr;
+    uint32_t n_states = 1;
 };
 
 namespace {
@@ -176,31 +180,96 @@ ie_status_t ie_engine_sync(ie_engine* e) {
     return IE_OK;
 }
 
+// Uploads the images of n_states snapshots (one allocation: images at 256-byte aligned offsets, then the
+// IeTableView array the kernels index by snapshot) and fills *out.
+static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uint8_t>>& images, const std::vector<uint32_t>& caps,
+                                 const std::vector<uint32_t>& counts, ie_table** out, const char* who) {
+    const size_t S = images.size();
+    std::vector<size_t> at(S + 1, 0);
+    for (size_t s = 0; s < S; ++s) at[s + 1] = at[s] + ((images[s].size() + 255) & ~size_t(255));
+    const size_t views_at = at[S], total = views_at + S * sizeof(IeTableView);
+    CU(cudaSetDevice(e->device));
+    ie_table* t = new (std::nothrow) ie_table();
+    if (!t) return fail(IE_E_NOMEM, std::string(who) + ": out of host memory");
+    t->e = e;
+    t->bytes = total;
+    t->n_states = (uint32_t)S;
+    cudaError_t err = cudaMalloc(&t->d_base, total);
+    if (err != cudaSuccess) { delete t; return cuda_fail(err, who); }
+    std::vector<IeTableView> views(S);
+    for (size_t s = 0; s < S; ++s) {
+        views[s].base = (const uint8_t*)t->d_base + at[s];
+        views[s].mask = caps[s] - 1;
+        views[s].n_entries = counts[s];
+    }
+    if (S == 1) {
+        err = cudaMemcpyAsync(t->d_base, images[0].data(), images[0].size(), cudaMemcpyHostToDevice, e->stream);
+    } else {  // one staged copy instead of thousands of small ones
+        std::vector<uint8_t> all(views_at, 0);
+        for (size_t s = 0; s < S; ++s) std::memcpy(all.data() + at[s], images[s].data(), images[s].size());
+        err = cudaMemcpyAsync(t->d_base, all.data(), all.size(), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    }
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, views.data(), S * sizeof(IeTableView), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) { cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
+    t->view = views[0];
+    t->d_views = (const IeTableView*)((uint8_t*)t->d_base + views_at);
+    *out = t;
+    return IE_OK;
+}
+
 ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals,
                           const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out) {
     if (!e || !out || (n && (!keys || !key_offs || !vals || !val_offs || !tags)))
         return fail(IE_E_INVALID, "ie_table_pack: NULL argument");
     *out = nullptr;
-    std::vector<uint8_t> image;
-    uint32_t capacity = 0;
+    std::vector<std::vector<uint8_t>> images(1);
+    std::vector<uint32_t> caps(1, 0), counts(1, (uint32_t)n);
     std::string why;
-    if (!ie_host::build_table_image(n, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, &image, &capacity, &why))
+    if (!ie_host::build_table_image(n, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, &images[0], &caps[0], &why))
         return fail(IE_E_INVALID, "ie_table_pack: " + why);
-    CU(cudaSetDevice(e->device));
-    ie_table* t = new (std::nothrow) ie_table();
-    if (!t) return fail(IE_E_NOMEM, "ie_table_pack: out of host memory");
-    t->e = e;
-    t->bytes = image.size();
-    cudaError_t err = cudaMalloc(&t->d_base, image.size());
-    if (err == cudaSuccess) err = cudaMemcpyAsync(t->d_base, image.data(), image.size(), cudaMemcpyHostToDevice, e->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    if (err != cudaSuccess) { if (t->d_base) cudaFree(t->d_base); delete t; return cuda_fail(err, "ie_table_pack"); }
-    t->view.base = (const uint8_t*)t->d_base;
-    t->view.mask = capacity - 1;
-    t->view.n_entries = (uint32_t)n;
-    *out = t;
-    return IE_OK;
+    return upload_tables(e, images, caps, counts, out, "ie_table_pack");
 }
+
+ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys, const uint64_t* key_offs,
+                               const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss,
+                               ie_table** out) {
+    if (!e || !out || !n_states || !state_offs) return fail(IE_E_INVALID, "ie_table_pack_many: NULL argument or no snapshots");
+    if (n_states > 0x7FFFFFFFull) return fail(IE_E_INVALID, "ie_table_pack_many: too many snapshots");
+    if (state_offs[n_states] && (!keys || !key_offs || !vals || !val_offs || !tags)) return fail(IE_E_INVALID, "ie_table_pack_many: NULL argument");
+    *out = nullptr;
+    std::vector<std::vector<uint8_t>> images(n_states);
+    std::vector<uint32_t> caps(n_states, 0), counts(n_states, 0);
+    std::vector<std::string> whys(n_states);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t s = next.fetch_add(1);
+            if (s >= n_states) return;
+            const uint64_t lo = state_offs[s], hi = state_offs[s + 1];
+            if (hi < lo) { whys[s] = "state offsets not monotone"; bad = 1; continue; }
+            counts[s] = (uint32_t)(hi - lo);
+            if (!ie_host::build_table_image(hi - lo, keys, key_offs + lo, vals, val_offs + lo, tags + lo, hhmm, hhmmss, &images[s], &caps[s],
+                                            &whys[s], /*compact=*/true))
+                bad = 1;
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = n_states >= 256 ? hw : 1;
+    std::vector<std::thread> pool;
+    for (unsigned k = 1; k < nthreads; ++k) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (bad)
+        for (uint64_t s = 0; s < n_states; ++s)
+            if (!whys[s].empty()) return fail(IE_E_INVALID, "ie_table_pack_many: snapshot " + std::to_string(s) + ": " + whys[s]);
+    return upload_tables(e, images, caps, counts, out, "ie_table_pack_many");
+}
+
+uint32_t ie_table_states(const ie_table* t) { return t ? t->n_states : 0; }
 
 void ie_table_free(ie_table* t) {
     if (!t) return;
@@ -221,9 +290,10 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     if (!avg_bytes && limits) avg_bytes = limits->avg_template_bytes;
     const uint32_t tt = ie_pick_tile(avg_bytes);
     IeWorkspace ws;
-    ie_status_t st = prepare_workspace(e, n, tcap, true, &ws, 0);
+    if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
+    ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0);
     if (st != IE_OK) return st;
-    CU(ie_launch_resolve(t->view, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+    CU(ie_launch_resolve(t->d_views, t->n_states, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                          max_exp, tcap, out_bias, tt, s));
     return IE_OK;
 }
@@ -349,20 +419,21 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     const uint64_t in_bytes = n ? tmpl_offs[n] : 0;
     if (in_bytes && !tmpl) return fail(IE_E_INVALID, "ie_resolve_batch: NULL template arena");
     cudaStream_t s = e->stream;
-    if (n >= 2 * kPipeChunk) {
+    const uint64_t S = t->n_states, nr = n * S;  // every snapshot resolves all n templates: nr results, index = snapshot * n + template
+    if (S == 1 && n >= 2 * kPipeChunk) {
         bool done = false;
         ie_status_t st = resolve_pipelined(e, t, tmpl, tmpl_offs, n, limits, res, &done);
         if (st != IE_OK || done) return st;
     }
     CU(e->d_in.ensure(in_bytes + 16, s));
     CU(e->d_in_offs.ensure((n + 1) * 8, s));
-    CU(e->d_out_offs.ensure(n * 8 + 8, s));
-    CU(e->d_out_lens.ensure(n * 4 + 4, s));
-    CU(e->d_status.ensure(n * 4 + 4, s));
-    CU(e->d_aux.ensure(n * 4 + 4, s));
+    CU(e->d_out_offs.ensure(nr * 8 + 8, s));
+    CU(e->d_out_lens.ensure(nr * 4 + 4, s));
+    CU(e->d_status.ensure(nr * 4 + 4, s));
+    CU(e->d_aux.ensure(nr * 4 + 4, s));
     CU(e->d_info.ensure(sizeof(ie_batch_info), s));
     CU(e->h_info.ensure(sizeof(ie_batch_info)));
-    CU(e->d_out.ensure(std::max<uint64_t>(in_bytes * 2 + (1u << 16), 1u << 20), s));
+    CU(e->d_out.ensure(std::max<uint64_t>(in_bytes * 2 * S + (1u << 16), 1u << 20), s));
     if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, tmpl, in_bytes, cudaMemcpyHostToDevice, s));
     if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, tmpl_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
@@ -384,16 +455,16 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     }
     const uint64_t ob = hinfo->out_bytes;
     CU(e->h_out.ensure(ob + 1));
-    CU(e->h_out_offs.ensure(n * 8 + 8));
-    CU(e->h_out_lens.ensure(n * 4 + 4));
-    CU(e->h_status.ensure(n * 4 + 4));
-    CU(e->h_aux.ensure(n * 4 + 4));
+    CU(e->h_out_offs.ensure(nr * 8 + 8));
+    CU(e->h_out_lens.ensure(nr * 4 + 4));
+    CU(e->h_status.ensure(nr * 4 + 4));
+    CU(e->h_aux.ensure(nr * 4 + 4));
     if (ob) CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, ob, cudaMemcpyDeviceToHost, s));
     if (n) {
-        CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, n * 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(e->h_out_lens.p, e->d_out_lens.p, n * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(e->h_aux.p, e->d_aux.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, nr * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_out_lens.p, e->d_out_lens.p, nr * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, nr * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_aux.p, e->d_aux.p, nr * 4, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
     res->out = (const uint8_t*)e->h_out.p;
@@ -402,7 +473,7 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     res->status = (const int32_t*)e->h_status.p;
     res->aux = (const uint32_t*)e->h_aux.p;
     res->info = *hinfo;
-    res->info.n = n;
+    res->info.n = nr;
     res->info.kernel_ms = kernel_ms;
     return IE_OK;
 }

@@ -27,12 +27,14 @@ struct IeWorkspace {
     uint32_t general_workers;
 };
 
-cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+// Resolves the n templates against each of the n_states packed snapshots (d_views[s], device array): result
+// index = s * n + template; every output array holds n_states * n entries.
+cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
                               uint64_t out_bias, uint32_t tt, cudaStream_t stream);
 
-cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                                     const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream);
 

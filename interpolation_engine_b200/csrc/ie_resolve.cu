@@ -115,7 +115,8 @@ __device__ uint8_t* reserve_out(uint8_t* out, uint64_t out_cap, ie_batch_info* i
     return out + off;
 }
 
-__global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+__global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableView* __restrict__ views, uint64_t per_state,
+                                                                const uint8_t* __restrict__ tmpl,
                                                                 const uint64_t* __restrict__ offs, uint8_t* __restrict__ out,
                                                                 uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                                 uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, 
     uint8_t* kscr = T + tcap;
 
     for (uint32_t q = worker; q < count; q += n_workers) {
-        const uint32_t i = ws.general_list[q];
+        const uint32_t r = ws.general_list[q];             // result index = state * per_state + template
+        const uint32_t i = (uint32_t)(r % per_state);
+        const IeTableView tv = views[r / per_state];
         const uint8_t* t = tmpl + offs[i];
         const uint32_t n = (uint32_t)(offs[i + 1] - offs[i]);
 
@@ -255,10 +258,10 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(IeTableView tv, 
                 if (w) for (uint32_t k = 0; k < olen; ++k) w[k] = payload[k];
             }
         }
-        out_offs[i] = off + out_bias;
-        out_lens[i] = olen;
-        status_out[i] = (int32_t)status;
-        aux_out[i] = aux;
+        out_offs[r] = off + out_bias;
+        out_lens[r] = olen;
+        status_out[r] = (int32_t)status;
+        aux_out[r] = aux;
     }
 }
 
@@ -283,7 +286,7 @@ cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const
     return cudaGetLastError();
 }
 
-cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
                               uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
@@ -291,10 +294,10 @@ cudaError_t ie_launch_resolve(const IeTableView& tv, const uint8_t* d_tmpl, cons
     if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
-    if ((err = ie_launch_resolve_tiles(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+    if ((err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                                        out_bias, tt, stream)) != cudaSuccess)
         return err;
-    ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(tv, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+    ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap, out_bias);
     return cudaGetLastError();
 }

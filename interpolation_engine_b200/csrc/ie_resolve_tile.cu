@@ -432,7 +432,8 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   }
 }
 
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTableView tv, const uint8_t* __restrict__ tmpl,
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const IeTableView* __restrict__ views, uint32_t tiles_per_state,
+                                                             const uint8_t* __restrict__ tmpl,
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
@@ -441,12 +442,15 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
-    const uint32_t tile = blockIdx.x;
+    // a tile = up to tt consecutive templates resolved against ONE snapshot: the table is tile-uniform
+    const uint32_t state = blockIdx.x / tiles_per_state, tile = blockIdx.x - state * tiles_per_state;
+    const IeTableView tv = views[state];
     const uint64_t i0 = (uint64_t)tile * tt;
     const uint32_t nt = (uint32_t)min((uint64_t)tt, n - i0);
-    const uint64_t i = i0 + tid;
+    const uint64_t i = i0 + tid;                    // template
+    const uint64_t r = (uint64_t)state * n + i;      // result index
     const bool active = tid < nt;
-    const bool last_tile = (uint64_t)tile + 1 == (n + tt - 1) / tt;
+    const bool last_tile = blockIdx.x + 1 == gridDim.x;
 
     // ---- P0: tile extent ----------------------------------------------------------------------
     const uint64_t off0 = __ldg(offs + i0);
@@ -590,14 +594,14 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
                 else if (ps.n_open == 0) { verbatim = true; olen = len; }
                 else fast_traverse<false>(tv, t, len, m0, nullptr, 0, olen, status, aux);
             }
-            if (status == IE_RES_PUNT) { olen = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i; }
+            if (status == IE_RES_PUNT) { olen = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r; }
         }
         uint64_t tile_total16;
         const uint64_t loc = ie_scan::local_scan(sm.scan, olen, 15, &tile_total16);
         const uint64_t off = ie_scan::allocate(sm.scan, &info->out_bytes, tile_total16) + loc;
-        if (tid == 0 && last_tile) info->n = n;
+        if (tid == 0 && last_tile) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
         if (!active) return;
-        out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+        out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
         if (olen == 0) return;
         if (off + olen > out_cap) { *ws.overflow = 1u; return; }
         if (verbatim) { uint8_t* wr = out + off; for (uint32_t k = 0; k < len; ++k) wr[k] = __ldg(t + k); }
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
         const uint32_t err = sm.t_err[tid];
         if (flags & TF_PUNT) {
             status = IE_RES_PUNT;
-            ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)i;
+            ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r;
         } else if (flags & TF_VERBATIM) {
             olen = sm.t_start[tid + 1] - sm.t_start[tid];
             nseg = olen ? 1 : 0;
@@ -691,9 +695,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
     const uint64_t tile_begin = ie_scan::allocate(sm.scan, &info->out_bytes, tile_pad64);
     const uint64_t tile_end = tile_begin + tile_pad64;
     const uint64_t off = tile_begin + loc;
-    if (tid == 0 && last_tile) info->n = n;
+    if (tid == 0 && last_tile) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
     if (active) {
-        out_offs[i] = off + out_bias; out_lens[i] = olen; status_out[i] = (int32_t)status; aux_out[i] = aux;
+        out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
     }
     if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return; }
     if (!seg_ok) {
@@ -792,11 +796,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(IeTabl
 
 }  // namespace
 
-cudaError_t ie_launch_resolve_tiles(const IeTableView& tv, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                                     const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
     const uint64_t tiles = (n + tt - 1) / tt;
-    ie_resolve_tile_kernel<<<(unsigned)tiles, NT, 0, stream>>>(tv, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
+    ie_resolve_tile_kernel<<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
                                                               d_aux, ws, d_info, out_bias, tt);
     return cudaGetLastError();
 }

@@ -37,7 +37,7 @@ struct Entry {
 
 bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
                        const uint8_t* tags, const char* hhmm, const char* hhmmss, std::vector<uint8_t>* image, uint32_t* capacity,
-                       std::string* why) {
+                       std::string* why, bool compact) {
     if (n > 0x3FFFFFFFull) { *why = "too many inserts (max 2^30 - 1)"; return false; }
     std::vector<Entry> entries;
     entries.reserve(n + 2);
@@ -55,7 +55,8 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
     // load factor <= 0.25 (<= 0.5 for very large maps): linear probe chains stay at 1-2 slots, and a
     // warp waits for its slowest lane
     uint64_t cap = 16;
-    const uint64_t want = entries.size() <= (1ull << 22) ? entries.size() * 4 : entries.size() * 2;
+    // (`compact`: <= 0.5 always — thousands of small snapshots packed side by side, ie_table_pack_many)
+    const uint64_t want = (!compact && entries.size() <= (1ull << 22)) ? entries.size() * 4 : entries.size() * 2;
     while (cap < want) cap <<= 1;
     if (cap > (1ull << 31)) { *why = "table too large"; return false; }
 

@@ -248,6 +248,40 @@ def test_escape_full_size_roundtrip(eng):
     assert np.array_equal(back.offs, tmpl.offs) and np.array_equal(back.bytes[:int(back.offs[-1])], tmpl.bytes)
 
 
+def test_c3_many_states_one_launch(eng, oracle):
+    """C3 as one batch: the cloned states are packed into ONE table (ie_table_pack_many) and every template is
+    resolved against every state in a single launch; result s * n + j must equal the per-state oracle."""
+    rng = np.random.default_rng(0xC3)
+    arena = ie.Arena.from_strings(workloads.C3_TEMPLATES + ["{question-{i}} / {persona_name}", "{{stage}}", "{history_list}", "{i}"])
+    states = [workloads.c3_state(s, rng) for s in range(1500)]
+    states[7] = {}                                     # an empty snapshot among them
+    states[8] = {"i": "{loop}", "loop": "x", "stage": 3}  # a value the general path has to rescan
+    packs = [ie.PackedInserts.from_dict(st) for st in states]
+    table = eng.pack_many(packs)
+    got = eng.resolve_batch(table, arena)
+    n = arena.n
+    assert len(got.status) == len(states) * n
+    for s, pk in enumerate(packs):
+        if s % 10 and s > 20:
+            continue  # every tenth state (and the first twenty) against the oracle; the rest below by property
+        out, offs, status, aux = oracle.build_table(pk).resolve_batch(arena.bytes, arena.offs)
+        assert np.array_equal(got.status[s * n:(s + 1) * n], status), s
+        for j in range(n):
+            assert got.get(s * n + j) == out[int(offs[j]):int(offs[j + 1])].tobytes(), (s, j)
+    # every state answers {question-{i}} with its own question
+    j = workloads.C3_TEMPLATES.index("{question-{i}}")
+    for s, st in enumerate(states):
+        if "i" in st and isinstance(st["i"], int):
+            assert got.get(s * n + j).decode() == st[f"question-{st['i']}"], s
+    # same answers as one table per state
+    for s in (0, 1, 99, 1499):
+        one = eng.resolve_batch(eng.pack(packs[s]), arena)
+        assert [one.get(j) for j in range(n)] == [got.get(s * n + j) for j in range(n)]
+        assert np.array_equal(one.status_raw, got.status_raw[s * n:(s + 1) * n])
+        typed = (one.status_raw & 0xFF) == ie.RES_TYPED
+        assert np.array_equal(one.aux[typed], got.aux[s * n:(s + 1) * n][typed])  # entry index within the state's own inserts
+
+
 # ---- wildcard sweeps -------------------------------------------------------------------------------
 def test_wildcard_match_and_delete(eng, oracle):
     with open(GOLDEN) as f:
