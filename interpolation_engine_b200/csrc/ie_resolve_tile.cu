@@ -53,25 +53,32 @@ constexpr int NW = NT / 32;
 constexpr int CTAS_PER_SM = IE_TILE_CTAS;  // resident CTAs the register budget is tuned for (48 registers)
 constexpr int E_CAP = 12 * TT;       // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
+constexpr int E_PAD = E_CAP + E_CAP / 32 + 2;
 constexpr int M_CAP = 18 * TT;       // 16-byte chunks per tile (288 bytes of template text per template)
 constexpr int S_CAP = 8 * TT;        // copy segments per tile
 constexpr int C_CAP = 16 * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
 constexpr uint32_t EV_CLOSE = 1u << 24;
+constexpr uint32_t EV_PUNT = 1u << 25;   // a byte the tile kernel does not interpret (sentinel collisions): the template is punted
 constexpr uint32_t NONE16 = 0xFFFFu;
 enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2 };
 
+__device__ __forceinline__ uint32_t EI(uint32_t e) { return e + (e >> 5); }  // padded event index
+
 struct Smem {
     ie_scan::TileSmemT<NT> scan;
-    uint32_t ev_pos[E_CAP];    // position in tile | EV_CLOSE (| EV_SIMPLE on opens)
-    uint32_t ev_a[E_CAP];      // open: unresolved children, then val_off16 of the resolved value; close: its length
-    uint16_t ev_match[E_CAP];  // partner event
-    uint16_t ev_c[E_CAP];      // open: parent open (NONE16 = top level)
+    // Event arrays are indexed through EI(): one pad slot per 32 events, so that lanes walking their own
+    // templates' events (about 8 apart) fall into different banks.
+    uint32_t ev_pos[E_PAD];    // position in tile | EV_CLOSE (| EV_SIMPLE on opens)
+    uint32_t ev_a[E_PAD];      // open: unresolved children, then val_off16 of the resolved value; close: its length
+    uint16_t ev_match[E_PAD];  // partner event
+    uint16_t ev_c[E_PAD];      // open: parent open (NONE16 = top level)
     union {
         struct {
             uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
             uint32_t q[Q_CAP];   // P2/P3: leaf groups (template << 16 | open event)
+            uint16_t cbase[M_CAP];  // P2: events of the tile before each chunk
         } scan;
         struct {
             uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
@@ -171,17 +178,25 @@ __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, in
     return bits;
 }
 
-// Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero.
-// Only aligned words that contain at least one requested byte are touched.
-__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* __restrict__ p, uint32_t m) {
+// 16 bytes from an arbitrary address through ALIGNED 16-byte loads (the second one only when the m requested
+// bytes reach into it) and register selects.  The kernel is bound by L1 wavefronts, not by ALU work: two
+// vector loads per lane replace five scalar ones.  Bytes at index >= m are unspecified.
+__device__ __forceinline__ uint4 load16_any(const uint8_t* __restrict__ p, uint32_t m) {
     const uintptr_t a = (uintptr_t)p;
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t r = (uint32_t)(a & 3);
-    const uint32_t nw = (r + m + 3) >> 2;  // aligned words covering [p, p + m), <= 5
-    const uint32_t w0 = nw > 0 ? __ldg(aw) : 0u, w1 = nw > 1 ? __ldg(aw + 1) : 0u, w2 = nw > 2 ? __ldg(aw + 2) : 0u,
-                   w3 = nw > 3 ? __ldg(aw + 3) : 0u, w4 = nw > 4 ? __ldg(aw + 4) : 0u;
-    const uint32_t sh = r * 8;
-    uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    const uint4* ap = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint32_t r = (uint32_t)(a & 15);
+    const uint4 A = __ldg(ap);
+    uint4 B = make_uint4(0, 0, 0, 0);
+    if (r + m > 16) B = __ldg(ap + 1);
+    uint32_t w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z;
+    if (r & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = B.w; }
+    if (r & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    const uint32_t sh = (r & 3) * 8;
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero (m >= 1).
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* __restrict__ p, uint32_t m) {
+    uint4 v = load16_any(p, m);
     const uint32_t full = m >> 2, rem = (m & 3) * 8;
     const uint32_t part = rem ? ((1u << rem) - 1u) : 0u;
     v.x &= full > 0 ? 0xFFFFFFFFu : (full == 0 ? part : 0u);
@@ -204,18 +219,18 @@ __device__ __forceinline__ void or_shifted(uint4& acc, const uint4& v, uint32_t 
 // Iterates the bytes of group g's key: literal template bytes and the values of its (resolved) children.
 template <class F>
 __device__ __forceinline__ void walk_key(const Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t g, F& f) {
-    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
-    const uint32_t c = sm.ev_match[g];
+    uint32_t pos = (sm.ev_pos[EI(g)] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[EI(g)];
     uint32_t e = g + 1;
     for (;;) {
-        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        const uint32_t stop = sm.ev_pos[EI(e)] & POS_MASK;
         for (; pos < stop; ++pos) if (!f(__ldg(tp + pos))) return;
         if (e == c) return;
-        const uint32_t ce = sm.ev_match[e];
-        const uint8_t* v = tv.base + (size_t)sm.ev_a[e] * 16u;
-        const uint32_t vl = sm.ev_a[ce];
+        const uint32_t ce = sm.ev_match[EI(e)];
+        const uint8_t* v = tv.base + (size_t)sm.ev_a[EI(e)] * 16u;
+        const uint32_t vl = sm.ev_a[EI(ce)];
         for (uint32_t k = 0; k < vl; ++k) if (!f(__ldg(v + k))) return;
-        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        pos = (sm.ev_pos[EI(ce)] & POS_MASK) + 1;
         e = ce + 1;
     }
 }
@@ -252,16 +267,16 @@ struct ArgCheck {  // interp.rs:109: "ARG" followed by ASCII digits only
 // Calls f(src, len) for each non-empty piece of group g's key (error payloads).
 template <class F>
 __device__ __forceinline__ void walk_key_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t g, F& f) {
-    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
-    const uint32_t c = sm.ev_match[g];
+    uint32_t pos = (sm.ev_pos[EI(g)] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[EI(g)];
     uint32_t e = g + 1;
     for (;;) {
-        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        const uint32_t stop = sm.ev_pos[EI(e)] & POS_MASK;
         if (stop > pos) f(tp + pos, stop - pos);
         if (e == c) return;
-        const uint32_t ce = sm.ev_match[e];
-        if (sm.ev_a[ce]) f(tv.base + (size_t)sm.ev_a[e] * 16u, sm.ev_a[ce]);
-        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        const uint32_t ce = sm.ev_match[EI(e)];
+        if (sm.ev_a[EI(ce)]) f(tv.base + (size_t)sm.ev_a[EI(e)] * 16u, sm.ev_a[EI(ce)]);
+        pos = (sm.ev_pos[EI(ce)] & POS_MASK) + 1;
         e = ce + 1;
     }
 }
@@ -273,11 +288,11 @@ __device__ __forceinline__ void walk_output_pieces(const Smem& sm, const IeTable
     uint32_t e = sm.t_eb[t];
     const uint32_t ee = e + sm.t_ne[t];
     while (e < ee) {
-        const uint32_t o = sm.ev_pos[e] & POS_MASK;
+        const uint32_t o = sm.ev_pos[EI(e)] & POS_MASK;
         if (o > pos) f(tp + pos, o - pos);
-        const uint32_t ce = sm.ev_match[e];
-        if (sm.ev_a[ce]) f(tv.base + (size_t)sm.ev_a[e] * 16u, sm.ev_a[ce]);
-        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        const uint32_t ce = sm.ev_match[EI(e)];
+        if (sm.ev_a[EI(ce)]) f(tv.base + (size_t)sm.ev_a[EI(e)] * 16u, sm.ev_a[EI(ce)]);
+        pos = (sm.ev_pos[EI(ce)] & POS_MASK) + 1;
         e = ce + 1;
     }
     if (end > pos) f(tp + pos, end - pos);
@@ -316,23 +331,23 @@ __device__ __forceinline__ bool short_key(const Smem& sm, const IeTableView& tv,
                                           uint32_t& klen, uint32_t carry_e, const uint4& carry_v) {
     key = make_uint4(0, 0, 0, 0);
     klen = 0;
-    uint32_t pos = (sm.ev_pos[g] & POS_MASK) + 1;
-    const uint32_t c = sm.ev_match[g];
+    uint32_t pos = (sm.ev_pos[EI(g)] & POS_MASK) + 1;
+    const uint32_t c = sm.ev_match[EI(g)];
     uint32_t e = g + 1;
     for (;;) {
-        const uint32_t stop = sm.ev_pos[e] & POS_MASK;
+        const uint32_t stop = sm.ev_pos[EI(e)] & POS_MASK;
         const uint32_t m = stop - pos;
         if (klen + m > 16) return false;
         if (m) { or_shifted(key, load_unaligned16(tp + pos, m), klen); klen += m; }
         if (e == c) return true;
-        const uint32_t ce = sm.ev_match[e];
-        const uint32_t vl = sm.ev_a[ce];
+        const uint32_t ce = sm.ev_match[EI(e)];
+        const uint32_t vl = sm.ev_a[EI(ce)];
         if (klen + vl > 16) return false;
         if (vl) {  // values of <= 16 bytes live zero-padded in their slot's 16-byte aligned inline area
-            or_shifted(key, e == carry_e ? carry_v : __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[e] * 16u)), klen);
+            or_shifted(key, e == carry_e ? carry_v : __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[EI(e)] * 16u)), klen);
             klen += vl;
         }
-        pos = (sm.ev_pos[ce] & POS_MASK) + 1;
+        pos = (sm.ev_pos[EI(ce)] & POS_MASK) + 1;
         e = ce + 1;
     }
 }
@@ -353,8 +368,8 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   uint32_t carry_e = NONE16;
   uint4 carry_v = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
   for (;;) {
-    const uint32_t c = sm.ev_match[g];
-    const bool simple = (sm.ev_pos[g] & EV_SIMPLE) != 0;
+    const uint32_t c = sm.ev_match[EI(g)];
+    const bool simple = (sm.ev_pos[EI(g)] & EV_SIMPLE) != 0;
     uint32_t err = 0, klen, val_off16 = 0, vl_tf = 0;
     const IeSlot* hit = nullptr;
     uint4 key;
@@ -414,16 +429,16 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
         else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
     }
     if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
-    sm.ev_a[g] = val_off16;
-    sm.ev_a[c] = IE_SLOT_VLEN(vl_tf);
-    const uint32_t parent = sm.ev_c[g];
+    sm.ev_a[EI(g)] = val_off16;
+    sm.ev_a[EI(c)] = IE_SLOT_VLEN(vl_tf);
+    const uint32_t parent = sm.ev_c[EI(g)];
     if (parent == NONE16) {
         if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
         return;
     }
     // one child of `parent` resolved; whoever resolves the last one carries on with the parent
     __threadfence_block();
-    if (atomicSub(&sm.ev_a[parent], 1u) != 1u) return;
+    if (atomicSub(&sm.ev_a[EI(parent)], 1u) != 1u) return;
     __threadfence_block();  // the siblings' results (written before their decrements) are visible from here on
     // short-key hits leave the slot's inline value in q3 (valid when the value is inline)
     carry_e = (klen <= 16 && IE_SLOT_VLEN(vl_tf) <= IE_INLINE_BYTES) ? g : NONE16;
@@ -495,81 +510,119 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     __syncthreads();
     PHASE_MARK(2);
 
-    // ---- P2: per-template structure -----------------------------------------------------------------
-    // One thread per template walks the set bits of its chunk masks in one flat loop (one event per
-    // iteration keeps the lanes of a warp together).  No explicit stack: the innermost open group is
-    // tracked through the parent links; ev_a[open] counts unresolved children until the group resolves.
-    if (!too_big && active) {
-        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
-        const uint32_t c_first = (lead + start) >> 4, c_end = (lead + end + 15) >> 4;  // chunks [c_first, c_end)
-        // the template's first byte is never escaped (a '\' ending the previous template does not reach across)
-        uint32_t first_fix = 0;
-        if (end > start && start > 0) {
-            const uint8_t b0 = __ldg(tp + start);
-            if ((b0 == '{' || b0 == '}') && __ldg(tp + start - 1) == '\\') first_fix = (b0 == '{' ? 1u : 2u) << (2 * ((lead + start) & 15));
+    // ---- P2a: flat event extraction ------------------------------------------------------------------------
+    // Every thread takes a contiguous run of chunk masks; one CTA scan of the per-run event counts gives each
+    // event its slot, so the tile's events end up in ONE array sorted by position (a template's events are a
+    // contiguous range of it).  cbase[c] = events before chunk c.
+    if (!too_big) {
+        const uint32_t per = (n_chunks + NT - 1) / NT;
+        const uint32_t c_lo = min(tid * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
+        uint32_t cnt = 0;
+        for (uint32_t c = c_lo; c < c_hi; ++c) {
+            const uint32_t m = sm.u.scan.cm[c];
+            cnt += __popc((m | (m >> 1)) & 0x55555555u);
         }
-        const uint32_t smask = 0xFFFFFFFFu << (2 * ((lead + start) & 15));
-        const uint32_t ekeep = (lead + end) & 15;
-        const uint32_t emask = ekeep ? ((1u << (2 * ekeep)) - 1u) : 0xFFFFFFFFu;
-        auto bits_at = [&](uint32_t cc) -> uint32_t {
-            uint32_t m = sm.u.scan.cm[cc];
-            if (cc == c_first) m = (m | first_fix) & smask;
-            if (cc + 1 == c_end) m &= emask;
-            return m;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += y;
+        }
+        if (lane == 31) sm.warp_scan[warp] = incl;
+        __syncthreads();
+        uint32_t wi = incl - cnt, total_ev = 0;
+#pragma unroll
+        for (int wv = 0; wv < NW; ++wv) {
+            const uint32_t x = sm.warp_scan[wv];
+            if (wv < (int)warp) wi += x;
+            total_ev += x;
+        }
+        if (total_ev > (uint32_t)E_CAP) { if (tid == 0) sm.overflow = 1; }
+        else {
+            if (tid == 0) sm.ev_n = total_ev;
+            for (uint32_t c = c_lo; c < c_hi; ++c) {
+                sm.u.scan.cbase[c] = (uint16_t)wi;
+                const uint32_t m = sm.u.scan.cm[c];
+                wi += __popc((m | (m >> 1)) & 0x55555555u);
+            }
+        }
+        __syncthreads();
+        // extraction, one chunk per thread and round (consecutive lanes take consecutive chunks: balanced); the
+        // first two events of a chunk are written without a loop, the loop takes the rest (dense chunks are rare)
+        if (!sm.overflow) {
+            for (uint32_t c = tid; c < n_chunks; c += NT) {
+                uint32_t m = sm.u.scan.cm[c];
+                if (m == 0) continue;
+                uint32_t w = sm.u.scan.cbase[c];
+                const uint32_t p0 = c * 16 - lead;
+                do {
+                    const int bit = (__ffs(m) - 1) & ~1;
+                    const uint32_t pair = (m >> bit) & 3u;
+                    m &= ~(3u << bit);
+                    sm.ev_pos[EI(w++)] = (p0 + (bit >> 1)) | (pair == 1u ? 0u : pair == 2u ? EV_CLOSE : EV_PUNT);
+                } while (m);
+            }
+        }
+    }
+    PHASE_MARK(2);
+    __syncthreads();
+
+    // ---- P2b: per-template structure -------------------------------------------------------------------------
+    // One thread per template walks its events: stack-free bracket matching through parent links; ev_a[open]
+    // counts unresolved children until the group resolves; a group that closes without children is a leaf and
+    // goes to the lookup queue right away (P3 skips the queue entries of templates that end up punted).
+    if (!too_big && !sm.overflow && active) {
+        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
+        auto event_index = [&](uint32_t p) -> uint32_t {  // events of the tile before byte position p
+            const uint32_t c = (lead + p) >> 4;
+            if (c >= n_chunks) return sm.ev_n;
+            const uint32_t m = sm.u.scan.cm[c] & ((1u << (2 * ((lead + p) & 15))) - 1u);
+            return sm.u.scan.cbase[c] + __popc((m | (m >> 1)) & 0x55555555u);
         };
-        uint32_t cnt = first_fix ? 1u : 0u;  // upper bound: boundary chunks may include the neighbours' bits
-        for (uint32_t c = c_first; c < c_end; ++c) cnt += __popc(sm.u.scan.cm[c]);
-        uint32_t eb = cnt ? atomicAdd(&sm.ev_n, cnt) : 0u;
-        uint32_t flags = 0, ne = 0;
-        if (eb + cnt > (uint32_t)E_CAP) { sm.overflow = 1; flags = TF_PUNT; eb = 0; }
-        else if (cnt) {
-            uint32_t wi = eb, n_open = 0, cur_open = NONE16;
+        const uint32_t eb = event_index(start), ee = event_index(end);
+        const uint32_t ne = ee - eb;
+        uint32_t flags = 0;
+        // The flat scan took "the previous byte is a backslash" across template boundaries: a template that
+        // starts with a brace right after a template ending in '\' lost that event -> the general path redoes it.
+        if (end > start && start > 0 && __ldg(tp + start - 1) == '\\') {
+            const uint8_t b0 = __ldg(tp + start);
+            if (b0 == '{' || b0 == '}') flags = TF_PUNT;
+        }
+        if (flags == 0) {
+            uint32_t n_open = 0, cur_open = NONE16;
             bool punt = false, stray = false;
-            uint32_t c = c_first;
-            uint32_t m = c < c_end ? bits_at(c) : 0u;
-            for (;;) {
-                while (m == 0 && ++c < c_end) m = bits_at(c);
-                if (m == 0) break;
-                const int bit = (__ffs(m) - 1) & ~1;
-                const uint32_t pair = (m >> bit) & 3u;
-                m &= ~(3u << bit);
-                const uint32_t pos = c * 16 - lead + (bit >> 1);
-                if (pair == 3u) { punt = true; break; }
-                if (pair == 1u) {
+            for (uint32_t e = eb; e < ee; ++e) {
+                const uint32_t v = sm.ev_pos[EI(e)];
+                if (v & EV_PUNT) { punt = true; break; }
+                if (!(v & EV_CLOSE)) {
                     ++n_open;
-                    sm.ev_pos[wi] = pos;
-                    sm.ev_c[wi] = (uint16_t)cur_open;
-                    sm.ev_a[wi] = 0;
-                    if (cur_open != NONE16) sm.ev_a[cur_open] += 1;
-                    cur_open = wi++;
+                    sm.ev_c[EI(e)] = (uint16_t)cur_open;
+                    sm.ev_a[EI(e)] = 0;
+                    if (cur_open != NONE16) sm.ev_a[EI(cur_open)] += 1;
+                    cur_open = e;
                 } else if (cur_open == NONE16) stray = true;
                 else {
                     const uint32_t o = cur_open;
-                    sm.ev_pos[wi] = pos | EV_CLOSE;
-                    sm.ev_match[o] = (uint16_t)wi; sm.ev_match[wi] = (uint16_t)o;
-                    cur_open = sm.ev_c[o];
-                    ++wi;
+                    sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
+                    cur_open = sm.ev_c[EI(o)];
+                    if (sm.ev_a[EI(o)] == 0) sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | o;
                 }
             }
-            ne = wi - eb;
             if (punt) flags = TF_PUNT;
-            else if (n_open == 0) flags = TF_VERBATIM;                // the loop at interp.rs:54 is never entered (stray '}' stay)
+            else if (n_open == 0) flags = TF_VERBATIM;              // the loop at interp.rs:54 is never entered (stray '}' stay)
             else if (stray || cur_open != NONE16) flags = TF_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
             if (flags == 0) {
                 // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
                 uint32_t ld = 0, tr = 0;
-                while (ld < ne && sm.ev_pos[eb + ld] == start + ld) ++ld;
-                while (tr < ne && sm.ev_pos[eb + ne - 1 - tr] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
+                while (ld < ne && sm.ev_pos[EI(eb + ld)] == start + ld) ++ld;
+                while (tr < ne && sm.ev_pos[EI(eb + ne - 1 - tr)] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
                 const uint32_t m0 = min(ld, tr);
                 for (uint32_t j = 0; j < m0; ++j) {
-                    if (sm.ev_match[eb + j] != eb + ne - 1 - j) break;
-                    sm.ev_pos[eb + j] |= EV_SIMPLE;
+                    if (sm.ev_match[EI(eb + j)] != eb + ne - 1 - j) break;
+                    sm.ev_pos[EI(eb + j)] |= EV_SIMPLE;
                 }
-                // leaf groups are ready (only now: a punted template may hold unmatched groups)
-                for (uint32_t e = eb; e < eb + ne; ++e)
-                    if (!(sm.ev_pos[e] & EV_CLOSE) && sm.ev_a[e] == 0) sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | e;
             }
-        } else flags = TF_VERBATIM;
+        }
         sm.t_eb[tid] = (uint16_t)eb;
         sm.t_ne[tid] = (uint16_t)ne;
         sm.t_flags[tid] = flags;
@@ -614,6 +667,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
         const uint32_t nq = sm.q_n[0];
         for (uint32_t k = tid; k < nq; k += NT) {
             const uint32_t item = sm.u.scan.q[k];
+            if (sm.t_flags[item >> 16]) continue;  // punted after some of its leaves were queued
             resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
     }
@@ -646,7 +700,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             walk_output_pieces(sm, tv, tp, tid, pc);
             olen = pc.bytes; nseg = pc.n;
             mode = 3;
-            if (sm.ev_pos[sm.t_eb[tid]] & EV_SIMPLE) {  // the whole template is one group: typed result
+            if (sm.ev_pos[EI(sm.t_eb[tid])] & EV_SIMPLE) {  // the whole template is one group: typed result
                 status = IE_RES_TYPED | ((uint32_t)sm.t_tag[tid] << 8);
                 aux = sm.t_aux[tid];
             }
@@ -737,13 +791,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             sidx = lo;
         }
         if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
-        const uintptr_t src = (uintptr_t)sm.u.seg.src[sidx] + (xb - sm.u.seg.out[sidx]);
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(src & ~(uintptr_t)3);
-        const uint32_t sh = (uint32_t)(src & 3) * 8;
-        const uint32_t w0 = __ldg(aw), w1 = __ldg(aw + 1), w2 = __ldg(aw + 2), w3 = __ldg(aw + 3);
-        const uint32_t w4 = sh ? __ldg(aw + 4) : 0u;  // only touched when it holds requested bytes
-        *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) =
-            make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (xb - sm.u.seg.out[sidx]);
+        *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
     }
     PHASE_MARK(10);
     // pass B: item 0 = the tile's first chunk, item j >= 1 = the chunk holding the start of segment j when
