@@ -110,7 +110,10 @@ __device__ __forceinline__ uint32_t pack2(uint32_t o, uint32_t c) {
     return (t * 0x01041040u) >> 24;
 }
 
-constexpr int P1_BATCH = 3;
+#ifndef IE_P1_BATCH
+#define IE_P1_BATCH 3
+#endif
+constexpr int P1_BATCH = IE_P1_BATCH;
 
 // One 16-byte chunk of template text -> 32 bits, 2 per byte: bit 2j = unescaped '{' at byte j,
 // bit 2j+1 = unescaped '}', both = punt marker.  `prev` is the byte before the chunk ("previous byte is
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
                     const int bit = (__ffs(m) - 1) & ~1;
                     const uint32_t pair = (m >> bit) & 3u;
                     m &= ~(3u << bit);
-                    sm.ev_pos[EI(w++)] = (p0 + (bit >> 1)) | (pair == 1u ? 0u : pair == 2u ? EV_CLOSE : EV_PUNT);
+                    sm.ev_pos[EI(w++)] = (p0 + (bit >> 1)) | ((pair - 1u) << 24);  // 1 open, 2 EV_CLOSE, 3 EV_PUNT
                 } while (m);
             }
         }
