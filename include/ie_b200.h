@@ -155,6 +155,11 @@ ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint
                                  const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, int invert,
                                  uint32_t* d_mask, uint64_t* d_n_deleted, void* stream);
 
+/* First-match form for goto_map / replace_map (runtime.rs:1085-1133, 1649-1692: the FIRST wildcard of an
+ * ordered list that matches wins): first[k] = index of the first pattern matching key k, 0xFFFFFFFF if none. */
+ie_status_t ie_glob_first_match(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
+                                const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, uint32_t* first);
+
 /* ---- device memory helpers for hosts without a CUDA binding (tests, bench, FFI callers) ----- */
 ie_status_t ie_device_alloc(ie_engine* e, uint64_t bytes, void** d_ptr);
 void ie_device_free(ie_engine* e, void* d_ptr);
@@ -168,7 +173,9 @@ void ie_host_free(void* h_ptr);
  * with fn one of interpolate_inserts (:31), get_simple_insertkey (:11), get_interpdata (:91),
  * recursive_interpolate (:179), recursive_escape (:163), recursive_unescape (:147),
  * extract_insert_keys (:248), value_to_string (:314), wildcard_match (runtime.rs:1633),
- * delete / delete_except (runtime.rs:1198 / 1219).  Returns malloc'ed UTF-8 JSON
+ * wildcard_captures (runtime.rs:1754), delete / delete_except (runtime.rs:1198 / 1219),
+ * replace_map (runtime.rs:1649; args item, wildcard_maps, repeat_until_done) and goto_map (runtime.rs:1085-1133;
+ * args text, target_maps -> {"value", "target", "interpolation_error"}).  Returns malloc'ed UTF-8 JSON
  * {"ok": value} | {"err": {"code", "message", "payload"}}; free with ie_free. */
 ie_status_t ie_call_json(ie_engine* e, const char* args_json, size_t len, char** out_json, size_t* out_len);
 void ie_free(void* p);

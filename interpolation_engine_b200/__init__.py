@@ -66,6 +66,7 @@ ABI = {
     "ie_escape_batch_device": (_i, [_vp, _i, _vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
     "ie_glob_sweep": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _i, _vp, ctypes.POINTER(_u64)]),
     "ie_glob_sweep_device": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _i, _vp, _vp, _vp]),
+    "ie_glob_first_match": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "ie_device_alloc": (_i, [_vp, _u64, ctypes.POINTER(_vp)]),
     "ie_device_free": (None, [_vp, _vp]),
     "ie_copy_to_device": (_i, [_vp, _vp, _vp, _u64]),
@@ -358,6 +359,14 @@ class Engine:
         self._check(self.lib.ie_glob_sweep(self.handle, _ptr(ka.bytes), _ptr(ka.offs), ka.n, _ptr(pa.bytes), _ptr(pa.offs), pa.n,
                                            int(bool(invert)), _ptr(mask), ctypes.byref(nd)))
         return mask[:(ka.n + 31) // 32], int(nd.value)
+
+    def glob_first_match(self, keys, patterns):
+        """Index of the first pattern matching each key (-1 = none): goto_map / replace_map selection."""
+        ka = keys if isinstance(keys, Arena) else Arena.from_strings(keys)
+        pa = patterns if isinstance(patterns, Arena) else Arena.from_strings(patterns)
+        first = np.zeros(max(ka.n, 1), dtype=np.uint32)
+        self._check(self.lib.ie_glob_first_match(self.handle, _ptr(ka.bytes), _ptr(ka.offs), ka.n, _ptr(pa.bytes), _ptr(pa.offs), pa.n, _ptr(first)))
+        return first[:ka.n].view(np.int32).copy() if ka.n else np.zeros(0, np.int32)
 
     def glob_sweep_device(self, d_keys, d_key_offs, n, patterns, invert, d_mask, d_n_deleted, stream=None):
         pa = patterns if isinstance(patterns, Arena) else Arena.from_strings(patterns)

@@ -563,7 +563,30 @@ ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint
     if (st != IE_OK) return st;
     CU(cudaSetDevice(e->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    CU(ie_launch_glob(d_keys, d_key_offs, n, gp, d_mask, d_n_deleted, s));
+    CU(ie_launch_glob(d_keys, d_key_offs, n, gp, d_mask, d_n_deleted, nullptr, s));
+    return IE_OK;
+}
+
+ie_status_t ie_glob_first_match(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n, const uint8_t* pats,
+                                const uint64_t* pat_offs, uint32_t n_pat, uint32_t* first) {
+    if (!e || (n && (!key_offs || !first))) return fail(IE_E_INVALID, "ie_glob_first_match: NULL argument");
+    IeGlobPatterns gp;
+    ie_status_t st = pack_patterns(pats, pat_offs, n_pat, 0, &gp);
+    if (st != IE_OK) return st;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint64_t bytes = n ? key_offs[n] : 0;
+    CU(e->d_in.ensure(bytes + 16, s));
+    CU(e->d_in_offs.ensure((n + 1) * 8, s));
+    CU(e->d_mask.ensure((n + 31) / 32 * 4 + 4, s));
+    CU(e->d_aux.ensure(n * 4 + 4, s));
+    CU(e->d_misc.ensure(64, s));
+    if (bytes) CU(cudaMemcpyAsync(e->d_in.p, keys, bytes, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, key_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CU(ie_launch_glob((const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, gp, (uint32_t*)e->d_mask.p, (uint64_t*)e->d_misc.p,
+                      (uint32_t*)e->d_aux.p, s));
+    if (n) CU(cudaMemcpyAsync(first, e->d_aux.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return IE_OK;
 }
 

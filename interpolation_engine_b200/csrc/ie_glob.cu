@@ -50,7 +50,8 @@ __device__ __forceinline__ void load_window(const uint8_t* p, uint32_t (&w)[8]) 
     for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
 
-__device__ __forceinline__ bool match_key(const IeGlobPatterns& pats, const uint8_t* s, uint32_t len, bool staged) {
+// Returns 1 + the index of the first pattern that matches the key, 0 when none does.
+__device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const uint8_t* s, uint32_t len, bool staged) {
     // Per pattern, a PROBE first: the last word of the prefix image and the last word of the key against
     // the last word of the suffix image (the most discriminating ones: "persona-123/" differs from most
     // keys in "123/", "/field-42" in "d-42").  Only keys that pass the probe of a pattern with longer pieces
@@ -64,7 +65,8 @@ __device__ __forceinline__ bool match_key(const IeGlobPatterns& pats, const uint
         t7 = __funnelshift_r(ew[0], ew[1], (uint32_t)((uintptr_t)e4 & 3) * 8);
     }
     bool any = false;
-    for (uint32_t q = 0; q < pats.n_pat && !any; ++q) {
+    uint32_t q = 0;
+    for (; q < pats.n_pat && !any; ++q) {
         const IeGlobFast& f = pats.fast[q];
         if (staged && f.kind != IE_GLOB_GENERIC) {
             const uint32_t pi = f.probe;
@@ -105,7 +107,7 @@ __device__ __forceinline__ bool match_key(const IeGlobPatterns& pats, const uint
             any = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
         }
     }
-    return any;
+    return any ? q : 0u;  // q was incremented past the matching pattern
 }
 
 // Persistent CTAs, grid-stride over tiles of 256 * kpt consecutive keys.  The text of a tile is contiguous in
@@ -114,7 +116,8 @@ __device__ __forceinline__ bool match_key(const IeGlobPatterns& pats, const uint
 // memory.  Tiles whose text exceeds the stage are matched from global memory by the generic matcher.
 __global__ void __launch_bounds__(GLOB_CTA, GLOB_CTAS_PER_SM) ie_glob_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ offs,
                                                                              uint64_t n, const __grid_constant__ IeGlobPatterns pats,
-                                                                             uint32_t* __restrict__ mask, unsigned long long* __restrict__ n_deleted) {
+                                                                             uint32_t* __restrict__ mask, unsigned long long* __restrict__ n_deleted,
+                                                                             uint32_t* __restrict__ first) {
     extern __shared__ __align__(16) uint8_t stage_raw[];  // [2][BUF_BYTES]
     __shared__ unsigned int s_deleted;
     const uint32_t tid = threadIdx.x;
@@ -177,7 +180,9 @@ __global__ void __launch_bounds__(GLOB_CTA, GLOB_CTAS_PER_SM) ie_glob_kernel(con
             if (k < n) {
                 const uint32_t len = (uint32_t)(a_next[j] - a[j]);
                 const uint8_t* s = staged ? text + (uint32_t)(a[j] - cur.b0) : keys + a[j];
-                del = match_key(pats, s, len, staged) != (pats.invert != 0);
+                const uint32_t hit = match_key(pats, s, len, staged);
+                if (first) first[k] = hit - 1u;  // 0xFFFFFFFF = no pattern matches (goto_map / replace_map pick the FIRST match)
+                del = (hit != 0) != (pats.invert != 0);
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, del);
             if ((tid & 31) == 0 && k < n) { mask[k >> 5] = word; my_deleted += __popc(word); }
@@ -242,7 +247,7 @@ void ie_glob_compile(IeGlobPatterns* pats) {
 }
 
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
-                           uint32_t* d_mask, uint64_t* d_n_deleted, cudaStream_t stream) {
+                           uint32_t* d_mask, uint64_t* d_n_deleted, uint32_t* d_first, cudaStream_t stream) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(d_n_deleted, 0, sizeof(uint64_t), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
@@ -254,6 +259,6 @@ cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, ui
     const uint64_t resident = (uint64_t)sms * GLOB_CTAS_PER_SM;
     const uint64_t blocks = min_tiles < resident ? min_tiles : resident;
     ie_glob_kernel<<<(unsigned)blocks, GLOB_CTA, 2 * BUF_BYTES, stream>>>(d_keys, d_key_offs, n, pats, d_mask,
-                                                                          reinterpret_cast<unsigned long long*>(d_n_deleted));
+                                                                          reinterpret_cast<unsigned long long*>(d_n_deleted), d_first);
     return cudaGetLastError();
 }

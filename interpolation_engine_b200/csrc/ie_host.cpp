@@ -573,6 +573,203 @@ const std::string& sarg(const JVal& args, const char* name) {
     return v.s;
 }
 
+// ---- the two callers that loop over the resolver (SURVEY.md §8 f): replace_map, goto_map ----------------------
+// Every resolve and every wildcard test goes through the GPU batch entry points; what stays on the host is the
+// sequencing (the reference evaluates map entries in order and stops at the first match or error) and the
+// capture extraction of the one pattern that matched.
+
+ApiError task_error(const std::string& msg) { return ApiError{-2, msg, ""}; }
+
+// runtime.rs:1754-1775: what each '*' swallows under the greedy, leftmost semantics of "^lit(.*)lit...$".
+// `ok[j][pos]`: literal j can start at pos and the rest of the pattern still reaches the end of the text.
+std::vector<std::string> wildcard_captures(const std::string& p, const std::string& s) {
+    std::vector<std::string> lits(1);
+    for (char c : p) { if (c == '*') lits.emplace_back(); else lits.back().push_back(c); }
+    const size_t m = lits.size() - 1, n = s.size();
+    std::vector<std::vector<uint8_t>> ok(m + 1, std::vector<uint8_t>(n + 2, 0)), later(m + 1, std::vector<uint8_t>(n + 2, 0));
+    for (size_t j = m + 1; j-- > 0;) {
+        const std::string& L = lits[j];
+        for (size_t pos = n + 1; pos-- > 0;) {
+            bool fits = pos + L.size() <= n && s.compare(pos, L.size(), L) == 0;
+            if (fits) fits = j == m ? pos + L.size() == n : later[j + 1][pos + L.size()] != 0;
+            ok[j][pos] = fits;
+            later[j][pos] = fits || later[j][pos + 1];  // some start >= pos works
+        }
+    }
+    std::vector<std::string> caps;
+    if (!ok[0][0] || m == 0) return caps;
+    size_t pos = lits[0].size();
+    for (size_t j = 1; j <= m; ++j) {
+        size_t e = n;
+        while (!ok[j][e]) --e;  // the largest start of literal j that still lets the rest match (exists: ok[0][0])
+        caps.push_back(s.substr(pos, e - pos));
+        pos = e + lits[j].size();
+    }
+    return caps;
+}
+
+// index of the first pattern that matches `text`, -1 if none: one launch of the glob kernel
+int first_match(ie_engine* e, const std::string& text, const std::vector<std::string>& patterns) {
+    for (size_t p0 = 0; p0 < patterns.size(); p0 += IE_MAX_PATTERNS) {
+        Arena keys, pats;
+        keys.push(text);
+        const size_t np = std::min<size_t>(IE_MAX_PATTERNS, patterns.size() - p0);
+        for (size_t i = 0; i < np; ++i) pats.push(patterns[p0 + i]);
+        uint32_t first = 0xFFFFFFFFu;
+        if (pats.offs[np] > 3584) {  // longer than the kernel's pattern block: one pattern per launch
+            for (size_t i = 0; i < np; ++i) {
+                Arena one;
+                one.push(patterns[p0 + i]);
+                check(ie_glob_first_match(e, keys.data(), keys.offs.data(), 1, one.data(), one.offs.data(), 1, &first));
+                if (first != 0xFFFFFFFFu) return (int)(p0 + i);
+            }
+            continue;
+        }
+        check(ie_glob_first_match(e, keys.data(), keys.offs.data(), 1, pats.data(), pats.offs.data(), (uint32_t)np, &first));
+        if (first != 0xFFFFFFFFu) return (int)(p0 + first);
+    }
+    return -1;
+}
+
+struct MapEntry { bool is_obj = false, empty = true; std::string key, val; };
+std::vector<MapEntry> map_entries(const JVal& maps) {
+    std::vector<MapEntry> out;
+    for (auto& m : *maps.a) {
+        MapEntry en;
+        en.is_obj = m.t == JVal::Obj;
+        if (en.is_obj && !m.o->empty()) {
+            en.empty = false;
+            en.key = m.o->begin()->first;  // obj.iter().next(): first key in sorted order
+            const JVal& v = m.o->begin()->second;
+            en.val = v.t == JVal::Str ? v.s : std::string();  // v.as_str().unwrap_or("")
+        }
+        out.push_back(en);
+    }
+    return out;
+}
+
+// runtime.rs:1658-1692.  Per iteration: ONE resolve batch (the text and every map key), one first-match sweep,
+// and — for the entry that matched — one resolve of its value against inserts + captures.
+std::string replace_str(ie_engine* e, const JVal& args, Session& s, std::string text, const std::vector<MapEntry>& maps, bool repeat) {
+    for (int guard = 0;; ++guard) {
+        if (guard > 10000) throw ApiError{IE_RES_LIMIT, message_for(IE_RES_LIMIT, ""), ""};  // the reference would not terminate
+        std::vector<std::string> batch{text};
+        for (auto& m : maps) if (m.is_obj && !m.empty) batch.push_back(m.key);
+        const std::vector<Outcome> res = s.resolve(batch);
+        const std::string current = value_to_string(outcome_value(res[0]));
+        // entries in order up to the first one the reference would fail on
+        std::vector<std::string> keys;
+        std::vector<size_t> which;
+        const ApiError* pending = nullptr;
+        ApiError pending_store{0, "", ""};
+        size_t bi = 1;
+        for (size_t j = 0; j < maps.size() && !pending; ++j) {
+            if (!maps[j].is_obj) { pending_store = task_error("replace_map expects object"); pending = &pending_store; break; }
+            if (maps[j].empty) { pending_store = task_error("replace_map entry empty"); pending = &pending_store; break; }
+            try { keys.push_back(value_to_string(outcome_value(res[bi++]))); which.push_back(j); }
+            catch (const ApiError& er) { pending_store = er; pending = &pending_store; }
+        }
+        const int f = first_match(e, current, keys);
+        if (f < 0 && pending) throw *pending;
+        std::string new_text = current;
+        if (f >= 0) {
+            const std::vector<std::string> caps = wildcard_captures(keys[f], current);
+            JVal args2 = args;
+            args2.o = std::make_shared<JObj>(*args.o);
+            JObj extra = s.inserts;
+            for (size_t i = 0; i < caps.size(); ++i) extra[std::to_string(i + 1)] = JVal::str(caps[i]);
+            (*args2.o)["inserts"] = JVal::obj(std::move(extra));
+            (*args2.o)["clock"] = JVal::obj({{"hhmm", JVal::str(s.hhmm)}, {"hhmmss", JVal::str(s.hhmmss)}});
+            Session s2(e, args2);
+            new_text = value_to_string(outcome_value(s2.resolve({maps[which[f]].val})[0]));
+        }
+        if (!repeat || new_text == text) return new_text;
+        text = new_text;
+    }
+}
+
+// runtime.rs:1733-1752
+bool find_null_map_value(Session& s, const JVal& maps, JVal* out) {
+    for (auto& m : *maps.a) {
+        if (m.t != JVal::Obj) continue;
+        for (auto& kv : *m.o) {
+            if (kv.first == "NULL") { *out = kv.second; return true; }
+            if (kv.first.find('{') != std::string::npos) {
+                const Outcome oc = s.resolve({kv.first})[0];
+                if (oc.code == IE_RES_PANIC) throw ApiError{oc.code, message_for(oc.code, oc.bytes), oc.bytes};
+                if ((oc.code == IE_RES_STRING || oc.code == IE_RES_TYPED) && value_to_string(outcome_value(oc)) == "NULL") { *out = kv.second; return true; }
+            }
+        }
+    }
+    return false;
+}
+
+// runtime.rs:1649-1731 (every `?` in the match arms leaves the function: errors propagate, the trailing NULL
+// handler only ever sees Ok)
+JVal replace_map(ie_engine* e, const JVal& args, Session& s, const JVal& item, const std::vector<MapEntry>& maps, bool has_null,
+                 const JVal& null_value, bool repeat) {
+    if (item.t == JVal::Str) {
+        if (has_null && simple_insertkey(item.s, nullptr)) {
+            const Outcome oc = s.resolve({item.s})[0];
+            if (oc.code == IE_RES_PANIC) throw ApiError{oc.code, message_for(oc.code, oc.bytes), oc.bytes};
+            if (oc.code != IE_RES_STRING && oc.code != IE_RES_TYPED) return null_value;
+        }
+        return JVal::str(replace_str(e, args, s, item.s, maps, repeat));
+    }
+    if (item.t == JVal::Arr) {
+        JArr out;
+        for (auto& v : *item.a) out.push_back(replace_map(e, args, s, v, maps, has_null, null_value, repeat));
+        return JVal::arr(std::move(out));
+    }
+    if (item.t == JVal::Obj) {
+        JObj out;
+        for (auto& kv : *item.o) {
+            const std::string nk = replace_str(e, args, s, kv.first, maps, repeat);
+            out[nk] = replace_map(e, args, s, kv.second, maps, has_null, null_value, repeat);
+        }
+        return JVal::obj(std::move(out));
+    }
+    return item;
+}
+
+// runtime.rs:1085-1133: one resolve batch (text, every key, every value), one first-match sweep.
+JVal goto_map(ie_engine* e, Session& s, const std::string& text, const JVal& target_maps) {
+    const std::vector<MapEntry> maps = map_entries(target_maps);
+    std::vector<std::string> batch{text};
+    for (auto& m : maps) if (m.is_obj && !m.empty) { batch.push_back(m.key); batch.push_back(m.val); }
+    const std::vector<Outcome> res = s.resolve(batch);
+    bool interp_error = false;
+    std::string value_text;
+    if (res[0].code == IE_RES_PANIC) throw ApiError{res[0].code, message_for(res[0].code, res[0].bytes), res[0].bytes};
+    try { value_text = value_to_string(outcome_value(res[0])); } catch (const ApiError&) { interp_error = true; value_text = "NULL"; }
+    std::vector<std::string> keys, vals;
+    std::vector<const Outcome*> val_oc;
+    ApiError pending{0, "", ""};
+    bool has_pending = false;
+    size_t bi = 1;
+    for (size_t j = 0; j < maps.size(); ++j) {
+        if (!maps[j].is_obj) { pending = task_error("target_maps entry must be object"); has_pending = true; break; }
+        if (maps[j].empty) { pending = task_error("target_maps entry empty"); has_pending = true; break; }
+        const Outcome& ko = res[bi++];
+        const Outcome& vo = res[bi++];
+        try { keys.push_back(value_to_string(outcome_value(ko))); } catch (const ApiError& er) { pending = er; has_pending = true; break; }
+        if (!interp_error) {  // the value is resolved before the key is tested (:1124-1125)
+            try { value_to_string(outcome_value(vo)); } catch (const ApiError& er) { keys.pop_back(); pending = er; has_pending = true; break; }
+        }
+        val_oc.push_back(&vo);
+    }
+    int f = -1;
+    if (interp_error) { for (size_t j = 0; j < keys.size() && f < 0; ++j) if (keys[j] == "NULL") f = (int)j; }
+    else f = first_match(e, value_text, keys);
+    if (f < 0) {
+        if (has_pending) throw pending;
+        if (interp_error) throw task_error("goto_map value could not be resolved but 'NULL' is not a key in target_maps");
+        throw task_error("goto_map has no matches for '" + value_text + "'");
+    }
+    const std::string target = value_to_string(outcome_value(*val_oc[f]));  // interp_error: resolved only now (:1110), errors propagate
+    return JVal::obj({{"value", JVal::str(value_text)}, {"target", JVal::str(target)}, {"interpolation_error", JVal::boolean(interp_error)}});
+}
+
 JVal dispatch(ie_engine* e, const JVal& args) {
     const std::string& fn = sarg(args, "fn");
     if (fn == "interpolate_inserts") {  // interp.rs:31
@@ -646,6 +843,27 @@ JVal dispatch(ie_engine* e, const JVal& args) {
         for (auto& kv : ins) { const bool m = (any[k >> 5] >> (k & 31)) & 1u; if (m != except) doomed.push_back(kv.first); ++k; }
         for (auto& d : doomed) { ins.erase(d); deleted.push_back(JVal::str(d)); }
         return JVal::obj({{"deleted", JVal::arr(std::move(deleted))}, {"inserts", JVal::obj(std::move(ins))}});
+    }
+    if (fn == "wildcard_captures") {  // runtime.rs:1754
+        const std::string &p = sarg(args, "pattern"), &t = sarg(args, "text");
+        JArr out;
+        if (first_match(e, t, {p}) == 0) for (auto& c : wildcard_captures(p, t)) out.push_back(JVal::str(c));
+        return JVal::arr(std::move(out));
+    }
+    if (fn == "replace_map") {  // runtime.rs:1146-1169, 1649
+        const JVal& maps = arg(args, "wildcard_maps");
+        if (maps.t != JVal::Arr) throw task_error("replace_map.wildcard_maps must be array");
+        Session s(e, args);
+        JVal null_value;
+        const bool has_null = find_null_map_value(s, maps, &null_value);
+        const JVal& rep = arg(args, "repeat_until_done");
+        return replace_map(e, args, s, arg(args, "item"), map_entries(maps), has_null, null_value, rep.t == JVal::Bool && rep.b);
+    }
+    if (fn == "goto_map") {  // runtime.rs:1085-1133
+        const JVal& maps = arg(args, "target_maps");
+        if (maps.t != JVal::Arr) throw task_error("goto_map.target_maps must be array");
+        Session s(e, args);
+        return goto_map(e, s, sarg(args, "text"), maps);
     }
     throw std::runtime_error("unknown fn '" + fn + "'");
 }

@@ -81,5 +81,6 @@ struct IeGlobPatterns {  // passed by value as a kernel parameter (about 12 KiB;
     IeGlobFast fast[IE_MAX_PATTERNS];
 };
 void ie_glob_compile(IeGlobPatterns* pats);  // host: fills fast[] / any_pre / any_suf from bytes / off
+// d_first (may be NULL): [n] index of the first matching pattern, 0xFFFFFFFF when none
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
-                           uint32_t* d_mask, uint64_t* d_n_deleted, cudaStream_t stream);
+                           uint32_t* d_mask, uint64_t* d_n_deleted, uint32_t* d_first, cudaStream_t stream);

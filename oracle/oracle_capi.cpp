@@ -82,6 +82,23 @@ Value dispatch(const Value& args) {
         out["inserts"] = Value::object(std::move(ins));
         return Value::object(std::move(out));
     }
+    if (fn == "replace_map") {  // runtime.rs:1649
+        const Value* maps = field(args, "wildcard_maps");
+        if (!maps || maps->kind != Value::Arr) throw task_error("replace_map.wildcard_maps must be array");
+        const Value* item = field(args, "item");
+        const Value* rep = field(args, "repeat_until_done");
+        return replace_map(item ? *item : Value::null(), *maps->a, inserts, ctx, rep && rep->kind == Value::Bool && rep->b);
+    }
+    if (fn == "goto_map") {  // runtime.rs:1085
+        const Value* maps = field(args, "target_maps");
+        if (!maps || maps->kind != Value::Arr) throw task_error("goto_map.target_maps must be array");
+        const GotoChoice g = goto_map(str_field(args, "text"), *maps->a, inserts, ctx);
+        Object out;
+        out["value"] = Value::string(g.value_text);
+        out["target"] = Value::string(g.target);
+        out["interpolation_error"] = Value::boolean(g.interp_error);
+        return Value::object(std::move(out));
+    }
     throw std::runtime_error("unknown fn " + fn);
 }
 

@@ -4,7 +4,8 @@
 //
 // CPU restatement of the reference resolver, rust-project/src/interp.rs (all 322 lines),
 // and of wildcard_match / wildcard_captures / delete / delete_except from
-// rust-project/src/runtime.rs:1633-1647, 1754-1775, 1198-1239.  The pass structure of
+// rust-project/src/runtime.rs:1633-1647, 1754-1775, 1198-1239, and of the two callers that loop over the
+// resolver, replace_map (runtime.rs:1649-1752) and goto_map's target selection (:1085-1133).  The pass structure of
 // interpolate_inserts is kept on purpose (sentinel replace passes, per-iteration brace counts,
 // rfind/find, whole-string rebuild per insertion, ordered-map lookup plus a deep value clone
 // per hit) because this code is also the "reference-shaped" CPU baseline that bench.py times.
@@ -387,6 +388,108 @@ inline std::vector<std::string> delete_matching(Object& inserts, const std::vect
         if (any != except) { inserts.erase(k); deleted.push_back(k); }
     }
     return deleted;
+}
+
+// ---- "next" rows of SURVEY.md §8(f): the two callers that run the resolver in a loop --------------------------
+
+// anyhow errors of runtime.rs that are not resolver errors (code -2: the message is the whole contract)
+inline InterpError task_error(const std::string& msg) { return InterpError{-2, "", msg}; }
+
+// runtime.rs:1733-1752
+inline std::optional<Value> find_null_map_value(const Array& maps, const Object& inserts, const Ctx& ctx) {
+    for (auto& map : maps) {
+        if (map.kind != Value::Obj) continue;
+        for (auto& kv : *map.o) {
+            if (kv.first == "NULL") return kv.second.deep_clone();
+            if (kv.first.find('{') != std::string::npos) {
+                try {
+                    if (value_to_string(interpolate_inserts(inserts, kv.first, ctx)) == "NULL") return kv.second.deep_clone();
+                } catch (const InterpError&) {}
+            }
+        }
+    }
+    return std::nullopt;
+}
+
+// runtime.rs:1658-1692 (the nested fn replace_str)
+inline std::string replace_str(std::string text, const Array& maps, const Object& inserts, const Ctx& ctx, bool repeat_until_done) {
+    for (long guard = 0;; ++guard) {
+        if (guard > 10000) throw InterpError{ERR_LIMIT, "", "expansion limit exceeded"};  // the reference would spin forever
+        const std::string current = value_to_string(interpolate_inserts(inserts, text, ctx));
+        std::optional<std::string> replaced;
+        for (auto& map : maps) {
+            if (map.kind != Value::Obj) throw task_error("replace_map expects object");
+            if (map.o->empty()) throw task_error("replace_map entry empty");
+            const auto& kv = *map.o->begin();  // obj.iter().next(): first key in sorted order
+            const std::string key = value_to_string(interpolate_inserts(inserts, kv.first, ctx));
+            if (wildcard_match(key, current)) {
+                const std::vector<std::string> caps = wildcard_captures(key, current);
+                Object extra = inserts;
+                for (size_t i = 0; i < caps.size(); ++i) extra[std::to_string(i + 1)] = Value::string(caps[i]);
+                replaced = value_to_string(interpolate_inserts(extra, kv.second.is_string() ? kv.second.s : std::string(), ctx));
+                break;
+            }
+        }
+        const std::string new_text = replaced ? *replaced : current;
+        if (!repeat_until_done || new_text == text) return new_text;
+        text = new_text;
+    }
+}
+
+// runtime.rs:1649-1731.  Every `?` inside the match arms returns from the function, so the trailing
+// "NULL handler" match only ever sees Ok: errors propagate, except for the simple-key shortcut at :1696-1702.
+inline Value replace_map(const Value& item, const Array& maps, const Object& inserts, const Ctx& ctx, bool repeat_until_done) {
+    const std::optional<Value> null_value = find_null_map_value(maps, inserts, ctx);
+    if (item.kind == Value::String) {
+        if (get_simple_insertkey(item.s) && null_value) {
+            bool failed = false;
+            try { interpolate_inserts(inserts, item.s, ctx); } catch (const InterpError& e) { if (e.code == ERR_PANIC) throw; failed = true; }
+            if (failed) return *null_value;
+        }
+        return Value::string(replace_str(item.s, maps, inserts, ctx, repeat_until_done));
+    }
+    if (item.kind == Value::Arr) {
+        Array out;
+        for (auto& v : *item.a) out.push_back(replace_map(v, maps, inserts, ctx, repeat_until_done));
+        return Value::array(std::move(out));
+    }
+    if (item.kind == Value::Obj) {
+        Object out;
+        for (auto& kv : *item.o) {
+            std::string nk = replace_str(kv.first, maps, inserts, ctx, repeat_until_done);
+            out[nk] = replace_map(kv.second, maps, inserts, ctx, repeat_until_done);  // Map::insert: a later duplicate wins
+        }
+        return Value::object(std::move(out));
+    }
+    return item.deep_clone();
+}
+
+// runtime.rs:1085-1133: the target a goto_map task jumps to ("CONTINUE" = fall through); plus what it logs.
+struct GotoChoice { std::string value_text, target; bool interp_error; };
+inline GotoChoice goto_map(const std::string& text, const Array& target_maps, const Object& inserts, const Ctx& ctx) {
+    GotoChoice g{"", "", false};
+    try { g.value_text = value_to_string(interpolate_inserts(inserts, text, ctx)); }
+    catch (const InterpError& e) { if (e.code == ERR_PANIC) throw; g.interp_error = true; g.value_text = "NULL"; }
+    std::optional<std::string> target;
+    for (auto& entry : target_maps) {
+        if (entry.kind != Value::Obj) throw task_error("target_maps entry must be object");
+        if (entry.o->empty()) throw task_error("target_maps entry empty");
+        const auto& kv = *entry.o->begin();
+        const std::string key = value_to_string(interpolate_inserts(inserts, kv.first, ctx));
+        const std::string vtxt = kv.second.is_string() ? kv.second.s : std::string();
+        if (g.interp_error) {
+            if (key == "NULL") { target = value_to_string(interpolate_inserts(inserts, vtxt, ctx)); break; }
+        } else {
+            const std::string val = value_to_string(interpolate_inserts(inserts, vtxt, ctx));
+            if (wildcard_match(key, g.value_text)) { target = val; break; }
+        }
+    }
+    if (!target) {
+        if (g.interp_error) throw task_error("goto_map value could not be resolved but 'NULL' is not a key in target_maps");
+        throw task_error("goto_map has no matches for '" + g.value_text + "'");
+    }
+    g.target = *target;
+    return g;
 }
 
 }  // namespace orc

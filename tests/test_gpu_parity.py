@@ -282,6 +282,37 @@ def test_c3_many_states_one_launch(eng, oracle):
         assert np.array_equal(one.aux[typed], got.aux[s * n:(s + 1) * n][typed])  # entry index within the state's own inserts
 
 
+# ---- replace_map / goto_map (SURVEY.md §8 f: the callers that loop over the resolver) ------------------------
+def test_replace_map_goto_map_on_gpu(eng, oracle):
+    from tests.test_oracle_golden import REPLACE_GOTO_VECTORS, TA_PRINTED_MAPS, _norm
+    for fn, kw, expected in REPLACE_GOTO_VECTORS:
+        got, want = both(eng, oracle, fn, **kw)
+        assert got == want, (fn, kw, got, want)
+        assert _norm(got) == expected
+    rng = random.Random(77)
+    pieces = ["a", "b", " ", "  ", "-", "<t>", "</t>", "\n", "{x}", "{y}", "{n}", "*"]
+    for _ in range(150):
+        ins = {"x": rng.choice(["a b", "  a", "<t>q</t>", ""]), "y": rng.choice(["*", "b-a", "{x}"]), "n": rng.randint(0, 9)}
+        maps = []
+        for _ in range(rng.randint(0, 4)):
+            k = "".join(rng.choice(["a", "b", " ", "-", "*", "<t>", "{n}"]) for _ in range(rng.randint(0, 4)))
+            v = "".join(rng.choice(["{1}", "{2}", "z", " ", "{x}", "{3}"]) for _ in range(rng.randint(0, 3)))
+            maps.append({k: v})
+        if rng.random() < 0.3:
+            maps.append({"NULL": "nil"})
+        item = "".join(rng.choice(pieces) for _ in range(rng.randint(0, 5)))
+        for rep in (False, True):
+            got, want = both(eng, oracle, "replace_map", inserts=ins, item=item, wildcard_maps=maps, repeat_until_done=rep)
+            assert_same(got, want, (item, maps, rep))
+        got, want = both(eng, oracle, "goto_map", inserts=ins, text=item, target_maps=[{k: "T" + v} for m in maps for k, v in m.items()])
+        assert_same(got, want, (item, maps))
+    for pat, text in [("*-*", "a-b-c"), ("a*", "b"), ("*", ""), ("**", "xy"), ("*a*a*", "banana"), ("x", "x"), ("*<q>*</q>*", "1<q>2</q>3<q>4</q>5")]:
+        got, want = both(eng, oracle, "wildcard_captures", pattern=pat, text=text)
+        assert got == want, (pat, text, got, want)
+    first = eng.glob_first_match(["persona-1/a", "zzz", "", "b"], ["b", "persona-*", "*"])
+    assert list(first) == [1, 2, 2, 0]
+
+
 # ---- wildcard sweeps -------------------------------------------------------------------------------
 def test_wildcard_match_and_delete(eng, oracle):
     with open(GOLDEN) as f:
