@@ -67,39 +67,52 @@ __device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const 
     bool any = false;
     uint32_t q = 0;
     for (; q < pats.n_pat && !any; ++q) {
-        const IeGlobFast& f = pats.fast[q];
-        if (staged && f.kind != IE_GLOB_GENERIC) {
-            const uint32_t pi = f.probe;
-            const uint32_t hw = __funnelshift_r(aw[pi], aw[pi + 1], sh);
-            bool cand = (((hw ^ f.pre[pi]) & f.pre_mask[pi]) | ((t7 ^ f.suf[7]) & f.suf_mask[7])) == 0 &&
-                        (f.exact ? len == f.min_len : len >= f.min_len);
-            if (cand && (!f.complete || f.kind == IE_GLOB_MID)) {
+        const uint4 pa = *reinterpret_cast<const uint4*>(&pats.probe[q]);       // pre_word, pre_mask, suf_word, suf_mask
+        const uint4 pb = *(reinterpret_cast<const uint4*>(&pats.probe[q]) + 1);  // min_len, max_len, probe_off, kind
+        const uint32_t kind = pb.w & 0xFFu;
+        if (staged && kind != IE_GLOB_GENERIC) {
+            const uint32_t* pw = aw + (pb.z >> 2);
+            const uint32_t hw = __funnelshift_r(pw[0], pw[1], sh);
+            bool cand = (((hw ^ pa.x) & pa.y) | ((t7 ^ pa.z) & pa.w)) == 0 && len >= pb.x && len <= pb.y;
+            if (cand && (pb.w >> 8) == 0) {  // pieces longer than the probe words: the full 32-byte windows
+                const IeGlobFast& f = pats.fast[q];
                 uint32_t H[8], T[8];  // the key's first / last 32 bytes (bytes outside the key are masked out)
                 load_window(s, H);
-                if (!f.complete) {
-                    load_window(s + len - 32, T);
-                    uint32_t diff = 0;
+                load_window(s + len - 32, T);
+                uint32_t diff = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) diff |= ((H[w] ^ f.pre[w]) & f.pre_mask[w]) | ((T[w] ^ f.suf[w]) & f.suf_mask[w]);
-                    cand = diff == 0;
-                }
-                if (cand && f.kind == IE_GLOB_MID) {
-                    if (len > 32) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
-                    else {
-                        // positions of the window where the middle piece's first bytes occur, between prefix and suffix
-                        uint32_t hits = 0;
+                for (int w = 0; w < 8; ++w) diff |= ((H[w] ^ f.pre[w]) & f.pre_mask[w]) | ((T[w] ^ f.suf[w]) & f.suf_mask[w]);
+                cand = diff == 0;
+            }
+            if (cand && kind == IE_GLOB_MID) {
+                const IeGlobFast& f = pats.fast[q];
+                if (len > 32) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
+                else {
+                    // Start positions of the middle piece: bytes of the key's first 32 equal to its FIRST byte (SIMD
+                    // zero-byte test per word), limited to [mid_lo, len - mid_hi]; each candidate (a handful at most)
+                    // then compares the piece's first word.
+                    uint32_t H[8];
+                    load_window(s, H);
+                    const uint32_t b0 = (f.mid & 0xFFu) * 0x01010101u;
+                    uint32_t hits = 0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t lo = H[i >> 2], hi = (i >> 2) < 7 ? H[(i >> 2) + 1] : 0u;
-                            const uint32_t wv = (i & 3) ? __funnelshift_r(lo, hi, 8 * (i & 3)) : lo;
-                            hits |= (((wv ^ f.mid) & f.mid_mask) == 0 ? 1u : 0u) << i;
-                        }
-                        const uint32_t first = f.mid_lo, last = len - f.mid_hi;  // allowed start positions [first, last]
-                        const uint32_t range = (last >= 31 ? 0xFFFFFFFFu : (2u << last) - 1u) & ~((1u << first) - 1u);
-                        hits &= range;
-                        cand = hits != 0;
-                        if (cand && f.mid_len > 4) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
+                    for (int w = 0; w < 8; ++w) {
+                        const uint32_t x = H[w] ^ b0;
+                        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+                        hits |= (((z >> 7) * 0x00204081u >> 21) & 0xFu) << (4 * w);
                     }
+                    const uint32_t first = f.mid_lo, last = len - f.mid_hi;  // allowed start positions [first, last]
+                    hits &= (last >= 31 ? 0xFFFFFFFFu : (2u << last) - 1u) & ~((1u << first) - 1u);
+                    cand = false;
+                    while (hits && !cand) {
+                        const uint32_t i = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const uint8_t* pm = s + i;
+                        const uint32_t* mw = reinterpret_cast<const uint32_t*>((uintptr_t)pm & ~(uintptr_t)3);
+                        const uint32_t wv = __funnelshift_r(mw[0], mw[1], (uint32_t)((uintptr_t)pm & 3) * 8);
+                        cand = ((wv ^ f.mid) & f.mid_mask) == 0;
+                    }
+                    if (cand && f.mid_len > 4) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
                 }
             }
             any = cand;
@@ -203,6 +216,8 @@ void ie_glob_compile(IeGlobPatterns* pats) {
     for (uint32_t q = 0; q < pats->n_pat; ++q) {
         IeGlobFast& f = pats->fast[q];
         std::memset(&f, 0, sizeof f);
+        std::memset(&pats->probe[q], 0, sizeof pats->probe[q]);
+        pats->probe[q].kind = IE_GLOB_GENERIC;
         f.kind = IE_GLOB_GENERIC;
         f.suf_first = 8;
         const uint8_t* p = pats->bytes + pats->off[q];
@@ -241,6 +256,12 @@ void ie_glob_compile(IeGlobPatterns* pats) {
             f.mid_lo = (uint8_t)pre_len;               // the middle piece may start at pre_len ...
             f.mid_hi = (uint8_t)(suf_len + mid_len);   // ... up to len - suf_len - mid_len
         }
+        IeGlobProbe& pr = pats->probe[q];
+        pr.pre_word = f.pre[f.probe]; pr.pre_mask = f.pre_mask[f.probe];
+        pr.suf_word = f.suf[7]; pr.suf_mask = f.suf_mask[7];
+        pr.min_len = f.min_len; pr.max_len = f.exact ? f.min_len : 0xFFFFFFFFu;
+        pr.probe_off = 4u * f.probe;
+        pr.kind = f.kind | ((uint32_t)f.complete << 8);
         if (pre_len) pats->any_pre = 1;
         if (suf_len) pats->any_suf = 1;
     }

@@ -2,12 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ie_common.cuh"
 
 #ifndef IE_RESOLVE_TILE
 #define IE_RESOLVE_TILE 128   // templates per CTA tile of the resolve kernel at most
 #endif
-#define IE_TILE_TEXT_BYTES 36000u  // template text one tile can hold (chunk-mask table); longer tiles take the per-thread path
+#ifndef IE_M_PER
+#define IE_M_PER 18              // 16-byte chunks of template text per template a tile can hold (chunk-mask table)
+#endif
+#define IE_TILE_TEXT_BYTES (IE_M_PER * IE_RESOLVE_TILE * 16u - 864u)  // longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
 #define IE_GENERAL_WORKERS 2048u
 
@@ -41,6 +46,7 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
 // Templates per tile for a batch whose templates average `avg_bytes` (0 = unknown, assume short): the
 // largest power of two <= IE_RESOLVE_TILE whose expected text fits a tile with 25 % headroom.
 inline uint32_t ie_pick_tile(uint64_t avg_bytes) {
+    if (const char* dbg = getenv("IE_DEBUG_TILE")) { const int v = atoi(dbg); if (v >= 4 && v <= IE_RESOLVE_TILE) return (uint32_t)v; }  // experiments only
     uint32_t tt = IE_RESOLVE_TILE;
     while (tt > 4 && (uint64_t)tt * avg_bytes * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
     return tt;
@@ -72,12 +78,21 @@ struct IeGlobFast {  // a pattern with at most two '*' runs and literal pieces o
     uint16_t mid_len;
     uint8_t mid_lo, mid_hi;        // allowed start positions of the middle piece: [mid_lo, len - mid_hi]
 };
+struct __align__(16) IeGlobProbe {  // what the per-pattern probe needs, in two 16-byte constant loads
+    uint32_t pre_word, pre_mask;   // the probe word of the prefix image (word `probe` of pre / pre_mask)
+    uint32_t suf_word, suf_mask;   // the last word of the suffix image
+    uint32_t min_len, max_len;     // len must lie in [min_len, max_len] (max_len = min_len: no star)
+    uint32_t probe_off;            // byte offset of the prefix probe word in the key
+    uint32_t kind;                 // IE_GLOB_* | complete << 8
+};
 struct IeGlobPatterns {  // passed by value as a kernel parameter (about 12 KiB; CUDA >= 12.1 allows 32 KiB)
     uint32_t n_pat;
     uint32_t invert;
     uint32_t any_pre, any_suf;
     uint16_t off[IE_MAX_PATTERNS + 1];
     uint8_t bytes[3584];
+    uint8_t pad_[14];  // probe[] is 16-byte aligned
+    IeGlobProbe probe[IE_MAX_PATTERNS];
     IeGlobFast fast[IE_MAX_PATTERNS];
 };
 void ie_glob_compile(IeGlobPatterns* pats);  // host: fills fast[] / any_pre / any_suf from bytes / off

@@ -51,11 +51,17 @@ constexpr int TT = IE_RESOLVE_TILE;  // templates per tile at most (the launch p
 constexpr int NT = IE_TILE_NT;       // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int CTAS_PER_SM = IE_TILE_CTAS;  // resident CTAs the register budget is tuned for (48 registers)
-constexpr int E_CAP = 12 * TT;       // brace events per tile
+#ifndef IE_E_PER
+#define IE_E_PER 12
+#endif
+#ifndef IE_S_PER
+#define IE_S_PER 8
+#endif
+constexpr int E_CAP = IE_E_PER * TT;  // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
 constexpr int E_PAD = E_CAP + E_CAP / 32 + 2;
-constexpr int M_CAP = 18 * TT;       // 16-byte chunks per tile (288 bytes of template text per template)
-constexpr int S_CAP = 8 * TT;        // copy segments per tile
+constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks per tile (288 bytes of template text per template)
+constexpr int S_CAP = IE_S_PER * TT;  // copy segments per tile
 constexpr int C_CAP = 16 * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
