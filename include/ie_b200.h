@@ -175,7 +175,8 @@ void ie_host_free(void* h_ptr);
  * extract_insert_keys (:248), value_to_string (:314), wildcard_match (runtime.rs:1633),
  * wildcard_captures (runtime.rs:1754), delete / delete_except (runtime.rs:1198 / 1219),
  * replace_map (runtime.rs:1649; args item, wildcard_maps, repeat_until_done) and goto_map (runtime.rs:1085-1133;
- * args text, target_maps -> {"value", "target", "interpolation_error"}).  Returns malloc'ed UTF-8 JSON
+ * args text, target_maps -> {"value", "target", "interpolation_error"}), add_line_numbers / load_program
+ * (parser.rs:74 / :8; arg text; host only).  Returns malloc'ed UTF-8 JSON
  * {"ok": value} | {"err": {"code", "message", "payload"}}; free with ie_free. */
 ie_status_t ie_call_json(ie_engine* e, const char* args_json, size_t len, char** out_json, size_t* out_len);
 void ie_free(void* p);

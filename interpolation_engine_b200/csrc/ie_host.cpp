@@ -770,6 +770,98 @@ JVal goto_map(ie_engine* e, Session& s, const std::string& text, const JVal& tar
     return JVal::obj({{"value", JVal::str(value_text)}, {"target", JVal::str(target)}, {"interpolation_error", JVal::boolean(interp_error)}});
 }
 
+// ---- program loader: parser.rs:8-93 -------------------------------------------------------
+// Host-only: the on-disk format in front of the path.  `line:N` is spliced behind every `cmd: '<name>'` pair the
+// reference's per-line regex (parser.rs:75-77) would match, then the text goes through the JSON5-subset reader.
+struct LineScanner {
+    const std::string& ln;
+    static bool word(unsigned char c) { return std::isalnum(c) || c == '_' || c >= 0x80; }  // \w, ASCII + opaque UTF-8
+    static bool space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }           // \s, ASCII
+    size_t skip_space(size_t i) const { while (i < ln.size() && space((unsigned char)ln[i])) ++i; return i; }
+    // end of the `cmd` key spelled at i (bare word with \b on both sides, or quoted), 0 if none
+    size_t key_end(size_t i) const {
+        if (ln.compare(i, 3, "cmd") == 0) {
+            const bool left = i == 0 || !word((unsigned char)ln[i - 1]);
+            const bool right = i + 3 >= ln.size() || !word((unsigned char)ln[i + 3]);
+            return left && right ? i + 3 : 0;
+        }
+        if (ln.compare(i, 5, "\"cmd\"") == 0 || ln.compare(i, 5, "'cmd'") == 0) return i + 5;
+        return 0;
+    }
+    // end (one past the closing quote) of the string literal that starts at i, 0 if it does not close on this line
+    size_t string_end(size_t i) const {
+        if (i >= ln.size() || (ln[i] != '"' && ln[i] != '\'')) return 0;
+        const char q = ln[i];
+        for (size_t v = i + 1; v < ln.size(); ++v) {
+            if (ln[v] == '\\') { if (++v >= ln.size()) return 0; continue; }
+            if (ln[v] == q) return v + 1;
+        }
+        return 0;
+    }
+};
+std::string add_line_numbers(const std::string& text) {
+    std::string out;
+    size_t begin = 0, number = 0;
+    while (begin < text.size()) {  // str::lines()
+        size_t end = text.find('\n', begin);
+        const bool had_nl = end != std::string::npos;
+        if (!had_nl) end = text.size();
+        std::string ln = text.substr(begin, end - begin);
+        begin = had_nl ? end + 1 : end;
+        if (had_nl && !ln.empty() && ln.back() == '\r') ln.pop_back();
+        ++number;
+        const LineScanner sc{ln};
+        size_t from = 0;
+        for (size_t i = 0; i < ln.size();) {
+            const size_t k = sc.key_end(i);
+            size_t c = k ? sc.skip_space(k) : 0;
+            if (k && c < ln.size() && ln[c] == ':') {
+                const size_t v0 = sc.skip_space(c + 1), v1 = sc.string_end(v0);
+                const size_t t = v1 ? sc.skip_space(v1) : 0;
+                if (v1 && t < ln.size() && (ln[t] == ',' || ln[t] == '}')) {
+                    out.append(ln, from, i - from).append(ln, i, k - i).append(":").append(ln, v0, v1 - v0);
+                    out.append(", line:").append(std::to_string(number)).append(ln, v1, t + 1 - v1);
+                    i = from = t + 1;
+                    continue;
+                }
+            }
+            ++i;
+        }
+        out.append(ln, from, std::string::npos).push_back('\n');
+    }
+    return out;
+}
+JVal load_program(const std::string& raw) {
+    JVal root = parse(add_line_numbers(raw));
+    if (root.t != JVal::Obj) throw task_error("Program root must be an object");
+    JObj& obj = *root.o;
+    if (!obj.count("named_tasks") && obj.count("tasks")) { obj["named_tasks"] = obj["tasks"]; obj.erase("tasks"); }  // parser.rs:17-20
+    auto object_field = [&](const char* k) -> JVal {
+        auto it = obj.find(k);
+        if (it == obj.end() || it->second.t != JVal::Obj) throw task_error(std::string("Program missing '") + k + "' object");
+        return it->second;
+    };
+    auto check_task = [](const JVal& v) {
+        if (v.t == JVal::Obj) return;
+        std::string j;
+        dump(v, j);  // the reference formats the value with {:?}; compact JSON here (documented deviation)
+        throw task_error("Task must be an object, got " + j);
+    };
+    JObj out;
+    out["default_state"] = object_field("default_state");
+    auto ord = obj.find("order");
+    if (ord == obj.end() || ord->second.t != JVal::Arr) throw task_error("Program missing 'order' array");
+    for (auto& t : *ord->second.a) check_task(t);
+    out["order"] = ord->second;
+    const JVal named = object_field("named_tasks");
+    for (auto& kv : *named.o) check_task(kv.second);
+    out["named_tasks"] = named;
+    out["save_states"] = object_field("save_states");
+    auto ca = obj.find("completion_args");
+    out["completion_args"] = (ca != obj.end() && ca->second.t == JVal::Obj) ? ca->second : JVal::obj();
+    return JVal::obj(std::move(out));
+}
+
 JVal dispatch(ie_engine* e, const JVal& args) {
     const std::string& fn = sarg(args, "fn");
     if (fn == "interpolate_inserts") {  // interp.rs:31
@@ -844,6 +936,8 @@ JVal dispatch(ie_engine* e, const JVal& args) {
         for (auto& d : doomed) { ins.erase(d); deleted.push_back(JVal::str(d)); }
         return JVal::obj({{"deleted", JVal::arr(std::move(deleted))}, {"inserts", JVal::obj(std::move(ins))}});
     }
+    if (fn == "add_line_numbers") return JVal::str(add_line_numbers(sarg(args, "text")));  // parser.rs:74
+    if (fn == "load_program") return load_program(sarg(args, "text"));                      // parser.rs:8
     if (fn == "wildcard_captures") {  // runtime.rs:1754
         const std::string &p = sarg(args, "pattern"), &t = sarg(args, "text");
         JArr out;

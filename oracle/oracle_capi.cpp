@@ -82,6 +82,8 @@ Value dispatch(const Value& args) {
         out["inserts"] = Value::object(std::move(ins));
         return Value::object(std::move(out));
     }
+    if (fn == "add_line_numbers") return Value::string(add_line_numbers(str_field(args, "text")));  // parser.rs:74
+    if (fn == "load_program") return load_program(str_field(args, "text"));                          // parser.rs:8
     if (fn == "replace_map") {  // runtime.rs:1649
         const Value* maps = field(args, "wildcard_maps");
         if (!maps || maps->kind != Value::Arr) throw task_error("replace_map.wildcard_maps must be array");

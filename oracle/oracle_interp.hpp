@@ -492,4 +492,98 @@ inline GotoChoice goto_map(const std::string& text, const Array& target_maps, co
     return g;
 }
 
+// ---- program loader: rust-project/src/parser.rs:8-93 -----------------------------------------
+// add_line_numbers (parser.rs:74-93): per line, every non-overlapping leftmost match of
+//   (\bcmd\b|"cmd"|'cmd')\s*:\s*("([^"\\]|\\.)*"|'([^'\\]|\\.)*')(\s*(?:,|\}))
+// becomes  key:val, line:N trail .  \b and \s are taken over ASCII (bytes >= 0x80 count as word characters);
+// the regex crate's Unicode classes are PARITY UNPINNED.
+inline bool lp_word(unsigned char c) { return std::isalnum(c) || c == '_' || c >= 0x80; }
+inline bool lp_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+inline std::string add_line_numbers(const std::string& input) {
+    std::string out;
+    size_t line_no = 0, at = 0;
+    while (at < input.size()) {  // str::lines(): split on \n, a trailing \r is dropped, no empty last line
+        size_t nl = input.find('\n', at);
+        std::string line = input.substr(at, nl == std::string::npos ? std::string::npos : nl - at);
+        at = nl == std::string::npos ? input.size() : nl + 1;
+        if (nl != std::string::npos && !line.empty() && line.back() == '\r') line.pop_back();
+        ++line_no;
+        size_t i = 0, copied = 0;
+        std::string res;
+        const size_t n = line.size();
+        while (i < n) {
+            size_t k = std::string::npos;  // end of the key alternative matched at i
+            if (line.compare(i, 3, "cmd") == 0 && (i == 0 || !lp_word((unsigned char)line[i - 1])) &&
+                (i + 3 == n || !lp_word((unsigned char)line[i + 3]))) k = i + 3;
+            else if (line.compare(i, 5, "\"cmd\"") == 0 || line.compare(i, 5, "'cmd'") == 0) k = i + 5;
+            if (k != std::string::npos) {
+                size_t j = k;
+                while (j < n && lp_space((unsigned char)line[j])) ++j;
+                if (j < n && line[j] == ':') {
+                    ++j;
+                    while (j < n && lp_space((unsigned char)line[j])) ++j;
+                    if (j < n && (line[j] == '"' || line[j] == '\'')) {
+                        const char q = line[j];
+                        size_t v = j + 1;
+                        bool closed = false;
+                        while (v < n) {
+                            if (line[v] == '\\') { if (v + 1 >= n) break; v += 2; continue; }
+                            if (line[v] == q) { closed = true; break; }
+                            ++v;
+                        }
+                        if (closed) {
+                            size_t t = v + 1;
+                            while (t < n && lp_space((unsigned char)line[t])) ++t;
+                            if (t < n && (line[t] == ',' || line[t] == '}')) {
+                                res.append(line, copied, i - copied);
+                                res.append(line, i, k - i).append(":").append(line, j, v + 1 - j);
+                                res.append(", line:").append(std::to_string(line_no)).append(line, v + 1, t + 1 - (v + 1));
+                                i = copied = t + 1;
+                                continue;
+                            }
+                        }
+                    }
+                }
+            }
+            ++i;
+        }
+        res.append(line, copied, std::string::npos);
+        out += res;
+        out += '\n';
+    }
+    return out;
+}
+
+// parser.rs:8-64: the Program as an object {default_state, order, named_tasks, save_states, completion_args}
+inline Value load_program(const std::string& raw) {
+    Value root = parse_json(add_line_numbers(raw));  // json5::from_str: the JSON5 subset of oracle_value.hpp
+    if (root.kind != Value::Obj) throw task_error("Program root must be an object");
+    Object& obj = *root.o;
+    if (!obj.count("named_tasks") && obj.count("tasks")) { obj["named_tasks"] = obj["tasks"]; obj.erase("tasks"); }
+    auto need_obj = [&](const char* k) -> const Object& {
+        auto it = obj.find(k);
+        if (it == obj.end() || it->second.kind != Value::Obj) throw task_error(std::string("Program missing '") + k + "' object");
+        return *it->second.o;
+    };
+    auto as_task = [](const Value& v) {
+        if (v.kind == Value::Obj) return;
+        std::string j;
+        to_json(v, j);  // the reference prints the Value's Debug form ({value:?}): compact JSON here, PARITY UNPINNED
+        throw task_error("Task must be an object, got " + j);
+    };
+    Object out;
+    out["default_state"] = Value::object(need_obj("default_state"));
+    auto ord = obj.find("order");
+    if (ord == obj.end() || ord->second.kind != Value::Arr) throw task_error("Program missing 'order' array");
+    for (auto& t : *ord->second.a) as_task(t);
+    out["order"] = ord->second;
+    const Object& named = need_obj("named_tasks");
+    for (auto& kv : named) as_task(kv.second);
+    out["named_tasks"] = Value::object(named);
+    out["save_states"] = Value::object(need_obj("save_states"));
+    auto ca = obj.find("completion_args");
+    out["completion_args"] = (ca != obj.end() && ca->second.kind == Value::Obj) ? ca->second : Value::object();
+    return Value::object(std::move(out));
+}
+
 }  // namespace orc

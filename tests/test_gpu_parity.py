@@ -313,6 +313,22 @@ def test_replace_map_goto_map_on_gpu(eng, oracle):
     assert list(first) == [1, 2, 2, 0]
 
 
+def test_program_loader_host_vs_oracle(eng, oracle):
+    """parser.rs:8-93 (line injection + JSON5 subset + structure checks): host layer == oracle, incl. fuzzed lines."""
+    from tests.test_oracle_golden import LOADER_VECTORS, TINY_PROGRAM
+    for fn, text, expected in LOADER_VECTORS:
+        assert eng.call(fn, text=text) == ("ok", expected)
+    assert eng.call("load_program", text=TINY_PROGRAM) == oracle.call("load_program", text=TINY_PROGRAM)
+    rng = random.Random(3)
+    toks = ["cmd", "'cmd'", '"cmd"', ":", " ", "\t", "'a'", '"b\\"c"', ",", "}", "{", "x", "_", "'", '"', "\\", "\n", "\r\n", "7"]
+    for _ in range(400):
+        text = "".join(rng.choice(toks) for _ in range(rng.randint(0, 14)))
+        assert eng.call("add_line_numbers", text=text) == oracle.call("add_line_numbers", text=text), text
+    for text in ("[1]", "{order:[], tasks:{}, save_states:{}}", "{default_state:{}, order:[3], tasks:{}, save_states:{}}", "{"):
+        got, want = eng.call("load_program", text=text), oracle.call("load_program", text=text)
+        assert got[0] == want[0] == "err" and (got[1]["message"] == want[1]["message"] or text == "{"), (text, got, want)
+
+
 # ---- wildcard sweeps -------------------------------------------------------------------------------
 def test_wildcard_match_and_delete(eng, oracle):
     with open(GOLDEN) as f:
