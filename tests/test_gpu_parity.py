@@ -329,6 +329,44 @@ def test_program_loader_host_vs_oracle(eng, oracle):
         assert got[0] == want[0] == "err" and (got[1]["message"] == want[1]["message"] or text == "{"), (text, got, want)
 
 
+def test_device_api_with_misaligned_arenas(eng, oracle):
+    """The device-buffer entry points take arenas at ANY byte alignment (a sub-range of a caller's buffer): every
+    kernel streams aligned 16-byte chunks around them.  Same inputs at offsets 0..15 must give the same strings."""
+    state = workloads.c4_state()
+    table = eng.pack(state)
+    tmpl = workloads.c4_templates(3000)
+    want = eng.resolve_batch(table, tmpl)
+    n, nb = tmpl.n, tmpl.bytes.nbytes
+    keys = ie.Arena.from_strings([f"persona-{k % 37}/field-{k % 11}" for k in range(2500)])
+    pats = ["persona-3/*", "*/field-7", "*-1*/*"]
+    want_mask, want_nd = eng.glob_sweep(keys, pats)
+    want_esc = eng.escape_batch(tmpl, 1)
+    for shift in (1, 3, 8, 15):
+        d_t = eng.alloc(nb + 64).upload(np.concatenate([np.zeros(shift, np.uint8), tmpl.bytes]))
+        d_o = eng.alloc((n + 1) * 8).upload(tmpl.offs)
+        cap = nb * 3 + 4096
+        d_out, d_oo, d_ol, d_st, d_ax, d_info = (eng.alloc(cap + 16), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
+        eng.resolve_batch_device(table, d_t.ptr + shift, d_o.ptr, n, d_out.ptr + shift, cap, d_oo.ptr, d_ol.ptr, d_st.ptr, d_ax.ptr, d_info.ptr)
+        eng.sync()
+        out, offs, lens = d_out.download(np.uint8, cap + 16)[shift:], d_oo.download(np.uint64, n), d_ol.download(np.uint32, n)
+        assert np.array_equal(d_st.download(np.int32, n), want.status_raw) and np.array_equal(lens, want.lens)
+        assert oracle.first_mismatch(out, offs, want.out, want.offs, lens) is None, shift
+        # escape
+        d_eo, d_eoffs = eng.alloc(2 * nb + 64), eng.alloc((n + 1) * 8)
+        eng._check(eng.lib.ie_escape_batch_device(eng.handle, 1, d_t.ptr + shift, d_o.ptr, n, nb, d_eo.ptr + shift, 2 * nb + 16, d_eoffs.ptr, None))
+        eng.sync()
+        eoffs = d_eoffs.download(np.uint64, n + 1)
+        assert np.array_equal(eoffs, want_esc.offs)
+        assert np.array_equal(d_eo.download(np.uint8, 2 * nb + 64)[shift:shift + int(eoffs[-1])], want_esc.bytes)
+        # glob
+        d_k = eng.alloc(keys.bytes.nbytes + 64).upload(np.concatenate([np.zeros(shift, np.uint8), keys.bytes]))
+        d_ko = eng.alloc((keys.n + 1) * 8).upload(keys.offs)
+        d_m, d_n = eng.alloc((keys.n + 31) // 32 * 4 + 8), eng.alloc(8)
+        eng.glob_sweep_device(d_k.ptr + shift, d_ko.ptr, keys.n, pats, False, d_m.ptr, d_n.ptr)
+        eng.sync()
+        assert np.array_equal(d_m.download(np.uint32, (keys.n + 31) // 32), want_mask) and int(d_n.download(np.uint64, 1)[0]) == want_nd
+
+
 # ---- wildcard sweeps -------------------------------------------------------------------------------
 def test_wildcard_match_and_delete(eng, oracle):
     with open(GOLDEN) as f:
