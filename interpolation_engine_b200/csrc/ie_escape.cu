@@ -151,7 +151,18 @@ __global__ void __launch_bounds__(NT, ESC_CTAS) ie_escape_kernel(int mode, const
     uint32_t valid[CPT], special[CPT], cnt[CPT];
 
     // chunk c = 64 * warp + 32 * u + lane of the tile that starts at t0, coalesced
+    // interior tile: every byte of it and the byte after it belong to the arena (no range checks per chunk)
+    auto is_interior = [&](int64_t t0) { return t0 >= (int64_t)base0 && t0 + TILE_BYTES < (int64_t)end0; };
     auto load_tile = [&](int64_t t0) {
+        const uint8_t* tp = in + t0 + (64 * warp + lane) * 16;
+        if (is_interior(t0)) {
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) {
+                v[u] = __ldg(reinterpret_cast<const uint4*>(tp + u * 512));
+                nb[u] = mode == 0 ? __ldg(tp + u * 512 + 16) : 0u;
+            }
+            return;
+        }
 #pragma unroll
         for (int u = 0; u < CPT; ++u) {
             const int64_t p = t0 + (int64_t)(64 * warp + 32 * u + lane) * 16;
@@ -200,14 +211,20 @@ __global__ void __launch_bounds__(NT, ESC_CTAS) ie_escape_kernel(int mode, const
     };
     // masks and output sizes of the loaded chunks
     auto classify = [&](int64_t t0, bool have_fix) {
+        const bool interior = is_interior(t0);
 #pragma unroll
         for (int u = 0; u < CPT; ++u) {
             const uint32_t c = 64 * warp + 32 * u + lane;
-            const int64_t p = t0 + (int64_t)c * 16;
-            const int64_t a = (int64_t)base0 - p, b = (int64_t)end0 - p;  // valid bytes are [a, b) of the chunk
-            const uint32_t va = a <= 0 ? 0xFFFFu : (a >= 16 ? 0u : (0xFFFFu << a) & 0xFFFFu);
-            const uint32_t vb = b >= 16 ? 0xFFFFu : (b <= 0 ? 0u : (1u << b) - 1u);
-            valid[u] = va & vb;
+            int64_t b = 17;  // bytes of the arena from the chunk's first byte on (> 16: the next byte exists)
+            valid[u] = 0xFFFFu;
+            if (!interior) {
+                const int64_t p = t0 + (int64_t)c * 16;
+                const int64_t a = (int64_t)base0 - p;  // valid bytes are [a, b) of the chunk
+                b = (int64_t)end0 - p;
+                const uint32_t va = a <= 0 ? 0xFFFFu : (a >= 16 ? 0u : (0xFFFFu << a) & 0xFFFFu);
+                const uint32_t vb = b >= 16 ? 0xFFFFu : (b <= 0 ? 0u : (1u << b) - 1u);
+                valid[u] = va & vb;
+            }
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             if (mode == 1) {
                 uint32_t brace = 0;
