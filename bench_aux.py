@@ -6,7 +6,8 @@ BASELINE.json on one B200, one JSON line each, same roofline / cpu_baseline conv
 
   c5      wildcard delete sweep over 10 M keys x 64 pattern sets (runtime.rs:1198-1239, 1633-1647)
   escape  recursive_escape / recursive_unescape over the 1 Mi C4 templates (interp.rs:147-177)
-  c3      text_adventure-derived templates over cloned states (one table per state, small batches)
+  c3      text_adventure-derived templates over 10 000 cloned states (one launch; and one launch per state)
+  c1c2    the hello_world / math task traces, one recursive_interpolate call per task (latency-bound)
 """
 import argparse
 import json
@@ -143,7 +144,8 @@ def bench_c3(eng, ie, workloads, torch, dev, orc):
     return {"metric": "C3 text_adventure-derived (state, template) pairs/sec, 10 000 cloned states in one launch", "value": n / (r.kernel_ms * 1e-3),
             "unit": "strings/s", "n_gpus": 1, "ms_per_step": r.kernel_ms, "higher_is_better": True, "dtype": "u8", "data": "synthetic", "vs_baseline": None,
             "config": {"workload": f"C3: {n_states} states x {arena.n} templates = {n} pairs, one packed table set ({table.device_bytes >> 20} MiB), one launch",
-                       "general_path_templates": int(r.n_general), "host_pack_ms": pack_s * 1e3},
+                       "general_path_templates": int(r.n_general), "host_pack_ms": pack_s * 1e3,
+                       "host_pack_c_call_ms": table.pack_call_s * 1e3},
             "roofline": {"bound": "hbm", "achieved": alg / (r.kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (r.kernel_ms * 1e-3) / 1e9 / peak,
                          "traffic": None, "kernel": "ie_resolve_tile_kernel", "algorithmic_bytes_per_launch": alg,
                          "note": "template text counted once per state although it is L2-resident after the first", "peak_source": src + ", of measured"},
@@ -153,9 +155,38 @@ def bench_c3(eng, ie, workloads, torch, dev, orc):
             "cpu_baseline": {"value": n / cpu_s, "unit": "strings/s", "cores": 1, "kind": "port", "sample": "256 states, 1 thread, table build included"}}
 
 
+def bench_c1c2(eng, ie, workloads, torch, dev, orc):
+    """C1 / C2 (BASELINE configs 0-1): the interactive shape — one task at a time, a handful of templates per call.
+    The reference's own CPU path is the right tool here; both sides are timed per recursive_interpolate call."""
+    c1 = {"cmd": "print", "text": "Hello, world!", "line": 8}                                   # hello_world: 5 templates, 0 lookups
+    c2a = {"cmd": "math", "input": "max(1,2,3)", "output_name": "result", "line": 8}             # math task 1: 7 templates
+    c2b = {"cmd": "print", "text": "The result is {result}!\n", "line": 9}                      # math task 2: 5 templates, 1 lookup
+    calls = [({}, c1), ({}, c2a), ({"result": 3}, c2b)]
+    for ins, task in calls:  # warm-up + parity
+        assert eng.call("recursive_interpolate", inserts=ins, value=task) == orc.call("recursive_interpolate", inserts=ins, value=task)
+    reps = 200
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for ins, task in calls:
+            eng.call("recursive_interpolate", inserts=ins, value=task)
+    gpu_us = (time.perf_counter() - t0) / (reps * len(calls)) * 1e6
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for ins, task in calls:
+            orc.call("recursive_interpolate", inserts=ins, value=task)
+    cpu_us = (time.perf_counter() - t0) / (reps * len(calls)) * 1e6
+    n_t = 17  # templates over the three calls
+    return {"metric": "C1/C2 recursive_interpolate calls/sec (hello_world + math traces, one task per call)", "value": 1e6 / gpu_us, "unit": "calls/s",
+            "n_gpus": 1, "ms_per_step": gpu_us * 1e-3, "higher_is_better": True, "dtype": "u8", "data": "the two example programs' task objects", "vs_baseline": None,
+            "config": {"workload": "C1 + C2: 3 tasks, 17 templates, 1 lookup; JSON in, pack, H2D, two kernels, D2H, JSON out per call",
+                       "templates_per_call": n_t / 3},
+            "cpu_baseline": {"value": 1e6 / cpu_us, "unit": "calls/s", "cores": 1, "kind": "port", "sample": f"{reps} x 3 calls through the oracle's JSON entry point"},
+            "note": "latency-bound: a GPU call costs %.0f us against %.0f us on one CPU thread; the CPU wins by %.1fx at this batch size, as expected" % (gpu_us, cpu_us, gpu_us / cpu_us)}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="c5,escape,c3")
+    ap.add_argument("--which", default="c5,escape,c3,c1c2")
     args = ap.parse_args()
     import torch
 
@@ -167,7 +198,7 @@ def main():
     eng = ie.Engine(0)
     orc = oracle_lib.load()
     for name in args.which.split(","):
-        fn = {"c5": bench_c5, "escape": bench_escape, "c3": bench_c3}[name]
+        fn = {"c5": bench_c5, "escape": bench_escape, "c3": bench_c3, "c1c2": bench_c1c2}[name]
         print(json.dumps(fn(eng, ie, workloads, torch, dev, orc)), flush=True)
 
 

@@ -10,6 +10,7 @@ Reference being replaced: rust-project/src/interp.rs and rust-project/src/runtim
 1633-1647 of tillfalko/interpolation-engine.
 """
 import ctypes
+import time
 import json
 import os
 
@@ -309,10 +310,12 @@ class Engine:
         ko, vo = cat_offs([pk.key_offs for pk in packs]), cat_offs([pk.val_offs for pk in packs])
         merged = PackedInserts(kb, ko, vb, vo, tags)
         h = ctypes.c_void_p()
+        t0 = time.perf_counter()
         self._check(self.lib.ie_table_pack_many(self.handle, len(packs), _ptr(state_offs), _ptr(kb), _ptr(ko), _ptr(vb), _ptr(vo), _ptr(tags),
                                                 hhmm.encode() if hhmm else None, hhmmss.encode() if hhmmss else None, ctypes.byref(h)))
         t = Table(self, h, merged)
         t.n_states = len(packs)
+        t.pack_call_s = time.perf_counter() - t0  # the C call alone: image build on host threads + one upload
         return t
 
     # ---- interpolate_inserts, batched (interp.rs:31-89) ----------------------------------------

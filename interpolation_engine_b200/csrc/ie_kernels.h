@@ -2,8 +2,6 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "ie_common.cuh"
 
 #ifndef IE_RESOLVE_TILE
@@ -46,7 +44,6 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
 // Templates per tile for a batch whose templates average `avg_bytes` (0 = unknown, assume short): the
 // largest power of two <= IE_RESOLVE_TILE whose expected text fits a tile with 25 % headroom.
 inline uint32_t ie_pick_tile(uint64_t avg_bytes) {
-    if (const char* dbg = getenv("IE_DEBUG_TILE")) { const int v = atoi(dbg); if (v >= 4 && v <= IE_RESOLVE_TILE) return (uint32_t)v; }  // experiments only
     uint32_t tt = IE_RESOLVE_TILE;
     while (tt > 4 && (uint64_t)tt * avg_bytes * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
     return tt;

@@ -15,8 +15,8 @@ lib = ctypes.CDLL(ie.LIB_PATH)
 lib.ie_debug_phase_cycles(buf, 1)
 r = eng.resolve_batch(table, tmpl)
 lib.ie_debug_phase_cycles(buf, 1)
-names = ['acquire','P0+P1','sync1','P2','sync2','P3','sync3','P4a','scan+lookback','P4b emit','P5 passA','P5 passB']
+names = ['-','P0+P1','sync1','P2b','sync2b','P3','sync3','P4 sizes','scan+emit','claim+offs','P5 passA','P5 passB','P2a','sync2a']
 tiles = (tmpl.n + 127)//128
-tot = sum(buf[k] for k in range(12))
+tot = sum(buf[k] for k in range(14))
 for k,nm in enumerate(names): print(f"{nm:14s} {buf[k]/tiles:10.0f} cyc/tile  {100*buf[k]/tot:5.1f}%")
 print("total per tile", tot/tiles, "kernel_ms", r.kernel_ms)
