@@ -93,6 +93,8 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     ws->general_count = ws->tile_counter + 1;
     ws->overflow = ws->tile_counter + 2;
     ws->fix_count = ws->tile_counter + 3;
+    ws->retry_count = ws->tile_counter + 4;
+    ws->retry_list = nullptr;
     ws->fix_list = nullptr;
     ws->tile_first = nullptr;
     ws->tile_state = (uint64_t*)((uint8_t*)e->ws_zero.p + 64);
@@ -100,10 +102,13 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     ws->scratch = nullptr;
     ws->general_workers = IE_GENERAL_WORKERS;
     if (need_general) {
-        CU(e->ws_list.ensure((size_t)std::max<uint64_t>(n, 1) * sizeof(uint32_t), e->stream));
+        CU(e->ws_list.ensure((size_t)std::max<uint64_t>(n, 1) * 2 * sizeof(uint32_t), e->stream));
         ws->general_list = (uint32_t*)e->ws_list.p;
+        ws->retry_list = ws->general_list + std::max<uint64_t>(n, 1);
         if (tcap > e->tcap || !e->ws_scratch.p) {
-            CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH), e->stream));
+            const size_t big = (size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH);
+            const size_t small = (size_t)IE_GENERAL_SMALL_WORKERS * ((size_t)IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY);
+            CU(e->ws_scratch.ensure(std::max(big, small), e->stream));
             e->tcap = tcap;
         }
         ws->scratch = (uint8_t*)e->ws_scratch.p;

@@ -12,7 +12,10 @@
 #endif
 #define IE_TILE_TEXT_BYTES (IE_M_PER * IE_RESOLVE_TILE * 16u - 864u)  // longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
-#define IE_GENERAL_WORKERS 2048u
+#define IE_GENERAL_WORKERS 2048u       // tier 2 of the general path: full-size scratch (tcap + IE_KEY_SCRATCH each)
+#define IE_GENERAL_SMALL_WORKERS 18944u  // tier 1: 148 SMs x 128 threads with a small scratch each
+#define IE_GENERAL_SMALL_TEXT 3072u
+#define IE_GENERAL_SMALL_KEY 512u
 
 // Per-engine device workspace.  [zero_base, zero_base + zero_bytes) is cleared before a batch.
 struct IeWorkspace {
@@ -26,6 +29,8 @@ struct IeWorkspace {
     uint64_t* tile_first;     // escape kernel: [tiles + 1] first string starting at or after each tile
     uint64_t* tile_state;     // [tiles] flag << 62 | bytes
     uint32_t* general_list;   // [n]
+    uint32_t* retry_list;     // [n] templates that outgrew the small scratch of the general path's first tier
+    uint32_t* retry_count;
     uint8_t* scratch;         // general_workers * (tcap + IE_KEY_SCRATCH)
     uint32_t general_workers;
 };

@@ -121,16 +121,21 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
                                                                 uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                                 uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
                                                                 uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info,
-                                                                uint32_t max_expansions, uint32_t tcap, uint64_t out_bias) {
+                                                                uint32_t max_expansions, uint32_t tcap, uint32_t kcap, uint64_t out_bias,
+                                                                const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
+                                                                uint32_t* __restrict__ retry_list, uint32_t* __restrict__ retry_count) {
+    // Two tiers share this kernel: many workers with a small scratch each take the punted templates first
+    // (retry_list != nullptr: a template that outgrows the small scratch is queued there, nothing is written for
+    // it), then a few workers with the full-size scratch take the queue.
     const uint32_t worker = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_workers = gridDim.x * blockDim.x;
-    const uint32_t count = *ws.general_count;
-    if (worker == 0 && count) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_general), (unsigned long long)count);
-    uint8_t* T = ws.scratch + (size_t)worker * ((size_t)tcap + KSCR);
+    const uint32_t count = *list_count;
+    if (worker == 0 && count && retry_list) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_general), (unsigned long long)count);
+    uint8_t* T = ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
     uint8_t* kscr = T + tcap;
 
     for (uint32_t q = worker; q < count; q += n_workers) {
-        const uint32_t r = ws.general_list[q];             // result index = state * per_state + template
+        const uint32_t r = list[q];                         // result index = state * per_state + template
         const uint32_t i = (uint32_t)(r % per_state);
         const IeTableView tv = views[r / per_state];
         const uint8_t* t = tmpl + offs[i];
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
         uint32_t status = IE_RES_STRING, aux = 0;
         const uint8_t* payload = nullptr;  // final bytes when not in T
         uint32_t payload_len = 0;
-        bool uneven = false;
+        bool uneven = false, scratch_full = false;
         if (hi > lo) {
             frames[nf++] = Frame{t + lo, hi - lo, hi - lo};
             count_braces(t + lo, hi - lo, in_open, in_close);
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
             const uint8_t c = f.ptr[f.pos - 1];
             if (c == '{' || c == '}') {
                 if (f.pos >= 2 && f.ptr[f.pos - 2] == '\\') {  // escaped: sentinel text
-                    if (ttop < 4) { status = IE_RES_LIMIT; break; }
+                    if (ttop < 4) { status = IE_RES_LIMIT; scratch_full = true; break; }
                     ttop -= 4;
                     if (c == '{') { T[ttop] = 0x2E; T[ttop + 1] = 0xE3; T[ttop + 2] = 0x80; T[ttop + 3] = 0xA0; }
                     else { T[ttop] = 0xE3; T[ttop + 1] = 0x80; T[ttop + 2] = 0xA0; T[ttop + 3] = 0x2E; }
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
                     continue;
                 }
                 if (c == '}') {
-                    if (ttop < 1) { status = IE_RES_LIMIT; break; }
+                    if (ttop < 1) { status = IE_RES_LIMIT; scratch_full = true; break; }
                     T[--ttop] = '}'; --in_close; ++t_close; --f.pos;
                     continue;
                 }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
                 uint32_t idx = ttop;
                 while (idx < tcap && T[idx] != '}') ++idx;
                 if (idx == tcap) { status = IE_RES_PANIC; break; }
-                if (unsentinelise<false>(T + ttop, idx - ttop, nullptr) > KSCR) { status = IE_RES_LIMIT; break; }
+                if (unsentinelise<false>(T + ttop, idx - ttop, nullptr) > kcap) { status = IE_RES_LIMIT; scratch_full = true; break; }
                 const uint32_t klen = unsentinelise<true>(T + ttop, idx - ttop, kscr);
                 payload = kscr; payload_len = klen;
                 if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }
@@ -197,16 +202,20 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
             }
             if (c == '\\' && f.pos == f.len && ttop < tcap && T[ttop] == '}') {
                 // a spliced value ending in '\' escapes the '}' that now follows it (interp.rs:82-83)
-                if (ttop < 3) { status = IE_RES_LIMIT; break; }
+                if (ttop < 3) { status = IE_RES_LIMIT; scratch_full = true; break; }
                 ttop += 1; ttop -= 4;
                 T[ttop] = 0xE3; T[ttop + 1] = 0x80; T[ttop + 2] = 0xA0; T[ttop + 3] = 0x2E;
                 --t_close; --f.pos;
                 continue;
             }
-            if (ttop < 1) { status = IE_RES_LIMIT; break; }
+            if (ttop < 1) { status = IE_RES_LIMIT; scratch_full = true; break; }
             T[--ttop] = c; --f.pos;
         }
 
+        if (scratch_full && retry_list) {  // outgrew the small scratch: the full-size tier redoes it
+            retry_list[atomicAdd(retry_count, 1u)] = r;
+            continue;
+        }
         uint64_t off = 0;
         uint32_t olen = 0;
         if (uneven) {
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
                 // rendering of the previous result, typed and without rescan (interp.rs:47-51)
                 uint32_t klen = unsentinelise<false>(T + ttop, tcap - ttop, nullptr);
                 const uint8_t* key = kscr;
-                if (klen > KSCR) status = IE_RES_LIMIT;
+                if (klen > kcap) { status = IE_RES_LIMIT; scratch_full = true; }
                 else {
                     unsentinelise<true>(T + ttop, tcap - ttop, kscr);
                     for (uint32_t layer = 0; layer < m; ++layer) {
@@ -297,7 +306,16 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if ((err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                                        out_bias, tt, stream)) != cudaSuccess)
         return err;
+    // tier 1: IE_GENERAL_SMALL_WORKERS workers with IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY bytes each (they fit
+    // the same scratch allocation as tier 2); tier 2: ws.general_workers workers with the caller's full limits
+    const uint32_t small_t = tcap < IE_GENERAL_SMALL_TEXT ? tcap : IE_GENERAL_SMALL_TEXT;
+    ie_resolve_general_kernel<<<IE_GENERAL_SMALL_WORKERS / 64, 64, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+                                                                                d_status, d_aux, ws, d_info, max_expansions, small_t,
+                                                                                IE_GENERAL_SMALL_KEY, out_bias, ws.general_list, ws.general_count,
+                                                                                ws.retry_list, ws.retry_count);
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
     ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
-                                                                         d_status, d_aux, ws, d_info, max_expansions, tcap, out_bias);
+                                                                         d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH,
+                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr);
     return cudaGetLastError();
 }
