@@ -106,9 +106,7 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
         ws->general_list = (uint32_t*)e->ws_list.p;
         ws->retry_list = ws->general_list + std::max<uint64_t>(n, 1);
         if (tcap > e->tcap || !e->ws_scratch.p) {
-            const size_t big = (size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH);
-            const size_t small = (size_t)IE_GENERAL_SMALL_WORKERS * ((size_t)IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY);
-            CU(e->ws_scratch.ensure(std::max(big, small), e->stream));
+            CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH), e->stream));
             e->tcap = tcap;
         }
         ws->scratch = (uint8_t*)e->ws_scratch.p;

@@ -13,9 +13,9 @@
 #define IE_TILE_TEXT_BYTES (IE_M_PER * IE_RESOLVE_TILE * 16u - 864u)  // longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
 #define IE_GENERAL_WORKERS 2048u       // tier 2 of the general path: full-size scratch (tcap + IE_KEY_SCRATCH each)
-#define IE_GENERAL_SMALL_WORKERS 18944u  // tier 1: 148 SMs x 128 threads with a small scratch each
-#define IE_GENERAL_SMALL_TEXT 3072u
-#define IE_GENERAL_SMALL_KEY 512u
+#define IE_GENERAL_SMALL_THREADS 512     // general path: 16 warps per block, one template per warp (tier 1: scratch in shared memory)
+#define IE_GENERAL_SMALL_TEXT 1792u
+#define IE_GENERAL_SMALL_KEY 256u
 
 // Per-engine device workspace.  [zero_base, zero_base + zero_bytes) is cleared before a batch.
 struct IeWorkspace {

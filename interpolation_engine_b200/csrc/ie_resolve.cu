@@ -115,7 +115,7 @@ __device__ uint8_t* reserve_out(uint8_t* out, uint64_t out_cap, ie_batch_info* i
     return out + off;
 }
 
-__global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableView* __restrict__ views, uint64_t per_state,
+__global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_kernel(const IeTableView* __restrict__ views, uint64_t per_state,
                                                                 const uint8_t* __restrict__ tmpl,
                                                                 const uint64_t* __restrict__ offs, uint8_t* __restrict__ out,
                                                                 uint64_t out_cap, uint64_t* __restrict__ out_offs,
@@ -123,15 +123,24 @@ __global__ void __launch_bounds__(64) ie_resolve_general_kernel(const IeTableVie
                                                                 uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info,
                                                                 uint32_t max_expansions, uint32_t tcap, uint32_t kcap, uint64_t out_bias,
                                                                 const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
-                                                                uint32_t* __restrict__ retry_list, uint32_t* __restrict__ retry_count) {
+                                                                uint32_t* __restrict__ retry_list, uint32_t* __restrict__ retry_count,
+                                                                uint32_t smem_stride) {
     // Two tiers share this kernel: many workers with a small scratch each take the punted templates first
     // (retry_list != nullptr: a template that outgrows the small scratch is queued there, nothing is written for
     // it), then a few workers with the full-size scratch take the queue.
-    const uint32_t worker = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_workers = gridDim.x * blockDim.x;
+    // ONE TEMPLATE PER WARP, worked by lane 0: the machine is a byte-serial automaton whose control flow differs
+    // per template, so 32 templates on the lanes of one warp run one after the other anyway (measured: 2.5 ms per
+    // template that way); one lane per warp lets the SM interleave dozens of independent automata instead.
+    if (threadIdx.x & 31) return;
+    const uint32_t worker = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_workers = (gridDim.x * blockDim.x) >> 5;
     const uint32_t count = *list_count;
     if (worker == 0 && count && retry_list) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_general), (unsigned long long)count);
-    uint8_t* T = ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
+    // The machine re-reads what it just wrote, byte by byte: in global memory every such read is an L2 round trip
+    // (stores do not allocate in L1).  Tier 1 therefore keeps its small scratch in SHARED memory (smem_stride != 0,
+    // skewed by 4 bytes per thread against bank conflicts); tier 2 uses the big global scratch.
+    extern __shared__ __align__(16) uint8_t gen_smem[];
+    uint8_t* T = smem_stride ? gen_smem + (size_t)(threadIdx.x >> 5) * smem_stride : ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
     uint8_t* kscr = T + tcap;
 
     for (uint32_t q = worker; q < count; q += n_workers) {
@@ -306,16 +315,22 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if ((err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                                        out_bias, tt, stream)) != cudaSuccess)
         return err;
-    // tier 1: IE_GENERAL_SMALL_WORKERS workers with IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY bytes each (they fit
-    // the same scratch allocation as tier 2); tier 2: ws.general_workers workers with the caller's full limits
+    // tier 1: three blocks of 16 warps per SM, one template per warp, IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY bytes
+    // of shared memory per warp; tier 2: ws.general_workers warps with the caller's full limits in global memory
     const uint32_t small_t = tcap < IE_GENERAL_SMALL_TEXT ? tcap : IE_GENERAL_SMALL_TEXT;
-    ie_resolve_general_kernel<<<IE_GENERAL_SMALL_WORKERS / 64, 64, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+    const uint32_t stride = IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY + 4;
+    const size_t smem = (size_t)(IE_GENERAL_SMALL_THREADS / 32) * stride;
+    if ((err = cudaFuncSetAttribute(ie_resolve_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ie_resolve_general_kernel<<<sms * 3, IE_GENERAL_SMALL_THREADS, smem, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                                 d_status, d_aux, ws, d_info, max_expansions, small_t,
                                                                                 IE_GENERAL_SMALL_KEY, out_bias, ws.general_list, ws.general_count,
-                                                                                ws.retry_list, ws.retry_count);
+                                                                                ws.retry_list, ws.retry_count, stride);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    ie_resolve_general_kernel<<<ws.general_workers / 64, 64, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+    ie_resolve_general_kernel<<<ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32), IE_GENERAL_SMALL_THREADS, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH,
-                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr);
+                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr, 0u);
     return cudaGetLastError();
 }

@@ -24,6 +24,22 @@ for frac in (0.0, 0.01, 0.1, 0.5):
     table = eng.pack(st)
     eng.resolve_batch(table, tmpl)
     r = eng.resolve_batch(table, tmpl)
+    # device-resident timing of the kernels alone
+    import torch
+    dev = torch.device("cuda", 0)
+    d_t = torch.from_numpy(tmpl.bytes).to(dev); d_o = torch.from_numpy(tmpl.offs.view(np.int64)).to(dev)
+    cap = int(tmpl.bytes.nbytes * 3) + (1 << 20)
+    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int64, device=dev)] + [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3)] + [torch.zeros(32, dtype=torch.uint8, device=dev)]
+    sdev = torch.cuda.Stream(device=dev)
+    def step():
+        eng.resolve_batch_device(table, d_t.data_ptr(), d_o.data_ptr(), n, bufs[0].data_ptr(), cap, bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr(), stream=sdev.cuda_stream)
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(sdev)
+    for _ in range(5): step()
+    e1.record(sdev); torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / 5
     out, offs, status, aux = orc.build_table(st).resolve_batch(tmpl.bytes, tmpl.offs, threads=16)
     ok = np.array_equal(r.status, status) and orc.first_mismatch(r.out, r.offs, out, offs[:-1], (offs[1:] - offs[:-1]).astype(np.uint32)) is None
-    print(f"frac {frac:4.2f}: general-path templates {r.n_general:7d} of {n}, kernel_ms {r.kernel_ms:8.3f}, parity {'ok' if ok else 'MISMATCH'}")
+    print(f"frac {frac:4.2f}: general-path templates {r.n_general:7d} of {n}, host-API kernel_ms {r.kernel_ms:8.3f}, device-resident ms/step {dev_ms:7.3f}, parity {'ok' if ok else 'MISMATCH'}")
