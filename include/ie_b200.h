@@ -65,6 +65,11 @@ typedef struct {
     uint32_t avg_template_bytes; /* device-buffer calls only: mean template length, used to size the
                                   CTA tiles (0 = short templates, <= 230 bytes); the host-buffer
                                   calls measure it themselves                                   */
+    uint32_t rescan_rounds;    /* interp.rs:81-83 rescans every spliced value.  Values whose own groups nest
+                                  properly are resolved by running the template through the fast kernel again
+                                  ("round"), up to this many times (max 3); what is left, and every other kind
+                                  of rescan, takes the general path.  0 = default: 2 for the host-buffer calls,
+                                  none for the device-buffer call (fewer launches; same results either way) */
 } ie_limits;
 
 typedef struct {

@@ -84,8 +84,10 @@ struct ie_table {
 namespace {
 
 // Lays the per-batch workspace out for n items; returns the kernel-side view.
-ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws, uint64_t tiles) {
-    const size_t zero_bytes = 64 + (size_t)(tiles + 1) * sizeof(uint64_t);
+ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need_general, IeWorkspace* ws, uint64_t tiles,
+                              bool need_rounds = false) {
+    static_assert(sizeof(IeRoundCtl) <= 64, "round control block has a 64-byte slot");
+    const size_t zero_bytes = 128 + (size_t)(tiles + 1) * sizeof(uint64_t);  // [counters 64][round control 64][tile states]
     CU(e->ws_zero.ensure(zero_bytes, e->stream));
     ws->zero_base = (uint8_t*)e->ws_zero.p;
     ws->zero_bytes = zero_bytes;
@@ -97,14 +99,25 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     ws->retry_list = nullptr;
     ws->fix_list = nullptr;
     ws->tile_first = nullptr;
-    ws->tile_state = (uint64_t*)((uint8_t*)e->ws_zero.p + 64);
+    ws->tile_state = (uint64_t*)((uint8_t*)e->ws_zero.p + 128);
+    ws->round_ctl = nullptr;
+    ws->round_list[0] = ws->round_list[1] = ws->round_list[2] = nullptr;
+    ws->round_offs = nullptr;
     ws->general_list = nullptr;
     ws->scratch = nullptr;
     ws->general_workers = IE_GENERAL_WORKERS;
     if (need_general) {
-        CU(e->ws_list.ensure((size_t)std::max<uint64_t>(n, 1) * 2 * sizeof(uint32_t), e->stream));
+        const uint64_t m = std::max<uint64_t>(n, 1);
+        // general list, retry list [, three round lists, round offsets (8-byte aligned: 5 m u32 precede them, m padded even)]
+        const uint64_t me = (m + 1) & ~uint64_t(1);
+        CU(e->ws_list.ensure((size_t)me * (need_rounds ? 6 : 2) * sizeof(uint32_t) + (need_rounds ? (size_t)(m + 1) * sizeof(uint64_t) : 0), e->stream));
         ws->general_list = (uint32_t*)e->ws_list.p;
-        ws->retry_list = ws->general_list + std::max<uint64_t>(n, 1);
+        ws->retry_list = ws->general_list + me;
+        if (need_rounds) {
+            ws->round_ctl = (IeRoundCtl*)((uint8_t*)e->ws_zero.p + 64);
+            for (int k = 0; k < 3; ++k) ws->round_list[k] = ws->general_list + me * (2 + k);
+            ws->round_offs = (uint64_t*)(ws->general_list + me * 6);  // me even: 24 me bytes, 8-byte aligned
+        }
         if (tcap > e->tcap || !e->ws_scratch.p) {
             CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH), e->stream));
             e->tcap = tcap;
@@ -113,6 +126,10 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     }
     return IE_OK;
 }
+
+// Rescan rounds of the host-buffer calls: two by default (their few extra launches hide behind the PCIe copies);
+// the device-buffer call runs exactly limits->rescan_rounds of them (default none: every launch is on its clock).
+uint32_t host_rounds(const ie_limits* in) { return (in && in->rescan_rounds) ? in->rescan_rounds : 2u; }
 
 void resolve_limits(const ie_limits* in, uint32_t* max_exp, uint32_t* tcap) {
     *max_exp = (in && in->max_expansions) ? in->max_expansions : kDefaultExpansions;
@@ -287,17 +304,19 @@ uint64_t ie_table_device_bytes(const ie_table* t) { return t ? t->bytes : 0; }
 static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
                                   const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
                                   uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, uint64_t out_bias,
-                                  cudaStream_t s, uint64_t avg_bytes = 0) {
+                                  cudaStream_t s, uint64_t avg_bytes = 0, uint32_t rounds = 0) {
     uint32_t max_exp, tcap;
     resolve_limits(limits, &max_exp, &tcap);
     if (!avg_bytes && limits) avg_bytes = limits->avg_template_bytes;
     const uint32_t tt = ie_pick_tile(avg_bytes);
     IeWorkspace ws;
     if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
-    ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0);
+    if (rounds > 3) rounds = 3;
+    if (t->n_states != 1) rounds = 0;
+    ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0, rounds != 0);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->d_views, t->n_states, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                         max_exp, tcap, out_bias, tt, s));
+                         max_exp, tcap, out_bias, tt, rounds, s));
     return IE_OK;
 }
 
@@ -309,7 +328,7 @@ ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8
     if (n >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "ie_resolve_batch_device: at most 2^32-2 templates per batch");
     CU(cudaSetDevice(e->device));
     return resolve_device(e, t, d_tmpl, d_tmpl_offs, n, limits, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, d_info, 0,
-                          stream ? (cudaStream_t)stream : e->stream);
+                          stream ? (cudaStream_t)stream : e->stream, 0, limits ? limits->rescan_rounds : 0);
 }
 
 // Host-buffer batches of at least this many templates are cut into chunks whose H2D copy, kernels and
@@ -356,7 +375,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         uint32_t max_exp, tcap;
         resolve_limits(limits, &max_exp, &tcap);
         IeWorkspace ws;
-        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, 0);
+        ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, 0, true);
         if (st != IE_OK) return st;
     }
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
@@ -371,7 +390,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
                                         (uint8_t*)e->d_out.p + base[k], base[k + 1] - base[k], (uint64_t*)e->d_out_offs.p + lo,
                                         (uint32_t*)e->d_out_lens.p + lo, (int32_t*)e->d_status.p + lo, (uint32_t*)e->d_aux.p + lo,
-                                        (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n);
+                                        (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n, host_rounds(limits));
         if (st != IE_OK) return st;
         CU(cudaMemcpyAsync(hinfo + k, (ie_batch_info*)e->d_info.p + k, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, sc));
         CU(cudaEventRecord(e->ev_done[k], sc));
@@ -446,7 +465,7 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
                                         (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p,
                                         (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, (ie_batch_info*)e->d_info.p, 0, s,
-                                        n ? in_bytes / n : 0);
+                                        n ? in_bytes / n : 0, host_rounds(limits));
         if (st != IE_OK) return st;
         CU(cudaEventRecord(e->ev1, s));
         CU(cudaMemcpyAsync(hinfo, e->d_info.p, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, s));

@@ -22,6 +22,8 @@
 #define IE_VF_QUIRK 4u     // contains E3 80 A0 ("〠"), contains ".\}" or starts with "\}":
                            //   the sentinel encoding of interp.rs:40-43 is not injective there
 #define IE_VF_ANY 7u
+#define IE_VF_BALANCED 8u  // with IE_VF_BRACE and nothing else: the unescaped braces nest properly, so rescanning the
+                           //   spliced value equals resolving the value's own groups in place (tile kernel: "splice")
 
 // internal per-template status while a batch is in flight
 #define IE_RES_PUNT 0xFF  // fast path declined; the general kernel resolves it
@@ -31,7 +33,7 @@
 struct __align__(16) IeSlot {
     uint32_t hash;       // murmur3_32(key)
     uint32_t key_len;    // IE_SLOT_EMPTY when free
-    uint32_t vl_tf;      // value length (26 bits) | tag << 26 | value flags << 29
+    uint32_t vl_tf;      // value length (25 bits) | tag << 25 | value flags << 28
     uint32_t val_off16;  // value bytes at base + 16 * val_off16
     uint32_t entry;      // index of the insert in the caller's packed arrays (n, n+1: clock keys)
     uint32_t key_off16;  // key bytes at base + 16 * key_off16
@@ -39,10 +41,10 @@ struct __align__(16) IeSlot {
     uint8_t key_inline[IE_INLINE_BYTES];
     uint8_t val_inline[IE_INLINE_BYTES];
 };
-#define IE_VLEN_MAX 0x03FFFFFFu
+#define IE_VLEN_MAX 0x01FFFFFFu
 #define IE_SLOT_VLEN(x) ((x) & IE_VLEN_MAX)
-#define IE_SLOT_TAG(x) (((x) >> 26) & 7u)
-#define IE_SLOT_FLAGS(x) ((x) >> 29)
+#define IE_SLOT_TAG(x) (((x) >> 25) & 7u)
+#define IE_SLOT_FLAGS(x) ((x) >> 28)
 static_assert(sizeof(IeSlot) == 64, "slot must be 64 bytes");
 
 struct IeTableView {

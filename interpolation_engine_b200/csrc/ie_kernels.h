@@ -8,7 +8,7 @@
 #define IE_RESOLVE_TILE 128   // templates per CTA tile of the resolve kernel at most
 #endif
 #ifndef IE_M_PER
-#define IE_M_PER 18              // 16-byte chunks of template text per template a tile can hold (chunk-mask table)
+#define IE_M_PER 17              // 16-byte chunks of template text per template a tile can hold (chunk-mask table)
 #endif
 #define IE_TILE_TEXT_BYTES (IE_M_PER * IE_RESOLVE_TILE * 16u - 864u)  // longer tiles take the per-thread path
 #define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
@@ -31,6 +31,11 @@ struct IeWorkspace {
     uint32_t* general_list;   // [n]
     uint32_t* retry_list;     // [n] templates that outgrew the small scratch of the general path's first tier
     uint32_t* retry_count;
+    // rescan rounds (nullptr when rounds are off): control block in the zeroed region, three index lists of n
+    // entries (two alternate as again lists, one is the current round's result map), offsets of the round's templates
+    struct IeRoundCtl* round_ctl;
+    uint32_t* round_list[3];
+    uint64_t* round_offs;     // [n + 1]
     uint8_t* scratch;         // general_workers * (tcap + IE_KEY_SCRATCH)
     uint32_t general_workers;
 };
@@ -40,11 +45,39 @@ struct IeWorkspace {
 cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, uint32_t tt, cudaStream_t stream);
+                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, cudaStream_t stream);
+
+// Rescan rounds (interp.rs:81-83 rescans every spliced value): a template whose lookups returned values with properly
+// nested groups of their own is written out with those values in place ("spliced") and resolved again as a template
+// of the next round, on the same tile kernel.  A round's inputs are gathered contiguously behind the results in the
+// out arena; again_list / result_map entries = result index | simple-path layers of the caller's text << 28.
+#define IE_AGAIN_INDEX_MASK 0x0FFFFFFFu
+#define IE_AGAIN_LAYER_SHIFT 28
+#define IE_AGAIN_LAYER_MAX 14u
+#define IE_RES_AGAIN 0xFE  // internal status while a batch is in flight (like IE_RES_PUNT)
+#define IE_ROUND_MIN_TILE 32u  // rounds >= 2 are launched with one CTA per 32 templates; the kernel uses fewer, larger tiles when the texts are short
+struct IeRoundCtl {       // lives in the workspace's zeroed region
+    uint32_t count[2];    // again-list lengths, alternating per round
+    uint32_t pad[2];
+    uint64_t bytes[2];    // bytes of the texts of the templates on each list
+    uint64_t base;        // where the current round's template arena starts in the out arena
+    uint64_t packed;      // gather: templates placed << 40 | bytes placed
+};
+struct IeRound {
+    const uint32_t* n_dev;       // rounds >= 2: number of templates (device counter); nullptr in round 1
+    const uint64_t* bytes_dev;   // rounds >= 2: bytes of their texts (the kernel sizes its tiles from the mean length)
+    const uint32_t* result_map;  // rounds >= 2: [n] result index | layers << 28
+    uint32_t* again_list;        // out: templates that need another round
+    uint32_t* again_count;
+    uint64_t* again_bytes;       // out: bytes of their texts, each rounded up to 16
+    uint32_t allow_splice;       // 0: values with groups of their own are punted to the general path (no rounds)
+    uint32_t last_round;         // 1: what would need yet another round goes to the general path instead
+};
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream);
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, const IeRound& rd,
+                                    cudaStream_t stream);
 
 // Templates per tile for a batch whose templates average `avg_bytes` (0 = unknown, assume short): the
 // largest power of two <= IE_RESOLVE_TILE whose expected text fits a tile with 25 % headroom.

@@ -295,6 +295,48 @@ __global__ void __launch_bounds__(256) ie_lookup_kernel(IeTableView tv, const ui
     entry_out[k] = s ? s->entry : IE_AUX_NONE;
 }
 
+// ---- rescan rounds: plumbing between two launches of the tile kernel --------------------------------------------
+// Claims room for the next round's template arena behind the results (same bump allocator as the tiles) and resets the
+// counters the round will write.  `in` = which again list the round reads.
+__global__ void ie_round_reserve_kernel(IeRoundCtl* ctl, uint32_t in, ie_batch_info* info, uint64_t out_cap, uint32_t* overflow) {
+    const uint64_t bytes = ctl->bytes[in];
+    const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)((bytes + 15) & ~15ull));
+    if (base + bytes > out_cap) { *overflow = 1u; ctl->count[in] = 0; }  // the caller regrows the arena and reruns the batch
+    ctl->base = base;
+    ctl->packed = 0;
+    ctl->count[in ^ 1] = 0;
+    ctl->bytes[in ^ 1] = 0;
+}
+// One warp per unfinished template: its text so far (a result of the previous round) is copied to the round's arena.
+// One packed atomic hands out (index, byte offset) together, so the texts are contiguous in index order - the layout
+// the tile kernel streams.
+__global__ void __launch_bounds__(256) ie_round_gather_kernel(IeRoundCtl* ctl, uint32_t in, const uint32_t* __restrict__ list,
+                                                              uint8_t* __restrict__ out, const uint64_t* __restrict__ out_offs,
+                                                              const uint32_t* __restrict__ out_lens, uint64_t out_bias,
+                                                              uint64_t* __restrict__ offs2, uint32_t* __restrict__ map2) {
+    const uint32_t count = ctl->count[in];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < count; q += warps) {
+        const uint32_t entry = list[q];
+        const uint32_t r = entry & IE_AGAIN_INDEX_MASK;
+        const uint32_t len = out_lens[r];
+        const uint8_t* src = out + (out_offs[r] - out_bias);
+        unsigned long long old = 0;
+        if (lane == 0) old = atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->packed), (1ull << 40) | (unsigned long long)len);
+        old = __shfl_sync(0xFFFFFFFFu, old, 0);
+        const uint32_t idx = (uint32_t)(old >> 40);
+        const uint64_t at = ctl->base + (old & ((1ull << 40) - 1));
+        if (lane == 0) {
+            offs2[idx] = at;
+            map2[idx] = entry;
+            if (idx + 1 == count) offs2[count] = at + len;
+        }
+        uint8_t* dst = out + at;
+        for (uint32_t k = lane; k < len; k += 32) dst[k] = src[k];
+    }
+}
+
 }  // namespace
 
 cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const uint64_t* d_offs, uint64_t n, int32_t* d_tag,
@@ -307,14 +349,41 @@ cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const
 cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
+                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, cudaStream_t stream) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
+    // rounds need one snapshot (the table must stay tile-uniform) and result indices that fit the round map
+    if (!ws.round_ctl || n_states != 1 || n > IE_AGAIN_INDEX_MASK) rescan_rounds = 0;
+    IeRound rd{};
+    rd.allow_splice = rescan_rounds ? 1u : 0u;
+    if (rescan_rounds) { rd.again_list = ws.round_list[0]; rd.again_count = &ws.round_ctl->count[0]; rd.again_bytes = &ws.round_ctl->bytes[0]; }
     if ((err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                                       out_bias, tt, stream)) != cudaSuccess)
+                                       out_bias, tt, rd, stream)) != cudaSuccess)
         return err;
+    for (uint32_t k = 0; k < rescan_rounds; ++k) {
+        // round k + 2 reads again list (k & 1), maps results through list 2 and fills again list ((k + 1) & 1)
+        const uint32_t in = k & 1;
+        ie_round_reserve_kernel<<<1, 1, 0, stream>>>(ws.round_ctl, in, d_info, out_cap, ws.overflow);
+        ie_round_gather_kernel<<<296, 256, 0, stream>>>(ws.round_ctl, in, ws.round_list[in], d_out, d_out_offs, d_out_lens, out_bias, ws.round_offs,
+                                                        ws.round_list[2]);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+        IeRound r2{};
+        r2.n_dev = &ws.round_ctl->count[in];
+        r2.bytes_dev = &ws.round_ctl->bytes[in];
+        r2.result_map = ws.round_list[2];
+        r2.again_list = ws.round_list[in ^ 1];
+        r2.again_count = &ws.round_ctl->count[in ^ 1];
+        r2.again_bytes = &ws.round_ctl->bytes[in ^ 1];
+        r2.allow_splice = 1;
+        r2.last_round = k + 1 == rescan_rounds;
+        // templates = the gathered texts inside the out arena (absolute offsets in round_offs); results still go to
+        // the caller's arrays at the original result indices
+        if ((err = ie_launch_resolve_tiles(d_views, 1, d_out, ws.round_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+                                           d_info, out_bias, tt, r2, stream)) != cudaSuccess)
+            return err;
+    }
     // tier 1: three blocks of 16 warps per SM, one template per warp, IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY bytes
     // of shared memory per warp; tier 2: ws.general_workers warps with the caller's full limits in global memory
     const uint32_t small_t = tcap < IE_GENERAL_SMALL_TEXT ? tcap : IE_GENERAL_SMALL_TEXT;

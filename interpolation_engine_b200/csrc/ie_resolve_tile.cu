@@ -62,13 +62,17 @@ constexpr int Q_CAP = E_CAP / 2;     // groups per tile
 constexpr int E_PAD = E_CAP + E_CAP / 32 + 2;
 constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks per tile (288 bytes of template text per template)
 constexpr int S_CAP = IE_S_PER * TT;  // copy segments per tile
-constexpr int C_CAP = 16 * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
+#ifndef IE_C_PER
+#define IE_C_PER 16
+#endif
+constexpr int C_CAP = IE_C_PER * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
 constexpr uint32_t EV_CLOSE = 1u << 24;
+constexpr uint32_t EV_DONE = 1u << 26;   // open event: the group is resolved, ev_a[open] / ev_a[close] hold its value
 constexpr uint32_t EV_PUNT = 1u << 25;   // a byte the tile kernel does not interpret (sentinel collisions): the template is punted
 constexpr uint32_t NONE16 = 0xFFFFu;
-enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2 };
+enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2, TF_AGAIN = 4 };
 
 __device__ __forceinline__ uint32_t EI(uint32_t e) { return e + (e >> 5); }  // padded event index
 
@@ -94,16 +98,22 @@ struct Smem {
     } u;
     uint32_t t_start[TT + 1];  // template start, tile-relative
     uint32_t t_err[TT];        // max over failing groups of (open event << 8 | IE_RES_*)
+    uint32_t t_splice[TT];     // 1 + the rightmost group whose value holds (balanced) groups of its own: another round
     uint32_t t_aux[TT];        // entry index of a typed (simple path) result
     uint32_t t_flags[TT];
     uint16_t t_eb[TT];         // first event of the template
     uint16_t t_ne[TT];         // its events
     uint8_t t_tag[TT];
+    uint8_t t_layers[TT];      // simple-path layers of the template (interp.rs:45-52)
     uint32_t warp_scan[NW];
     uint32_t q_n[1];
     uint32_t ev_n;             // events allocated
     uint32_t overflow;
 };
+
+// Five CTAs per SM must fit the 196 KB shared-memory carve-out step (each CTA also reserves 1 KB): one step further
+// (228 KB) leaves the SM 28 KB of L1 instead of 60 KB, which costs this kernel 10 % (measured: 0.378 -> 0.415 ms).
+static_assert(IE_RESOLVE_TILE != 128 || CTAS_PER_SM != 5 || 5 * (sizeof(Smem) + 1024) <= 196 * 1024, "Smem outgrew the 196 KB carve-out");
 
 __device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 in every byte of w equal to pat's
     const uint32_t x = w ^ pat;
@@ -289,15 +299,19 @@ __device__ __forceinline__ void walk_key_pieces(const Smem& sm, const IeTableVie
         e = ce + 1;
     }
 }
-// Calls f(src, len) for each non-empty output piece of a successfully resolved template.
-template <class F>
+// Calls f(src, len) for each non-empty output piece of a template: its text with every RESOLVED group (outermost
+// first) replaced by the group's value.  ROUNDS: unresolved groups (only in templates that go another round) stay
+// as text, with their own resolved descendants replaced; without rounds every top-level group is resolved here.
+template <bool ROUNDS, class F>
 __device__ __forceinline__ void walk_output_pieces(const Smem& sm, const IeTableView& tv, const uint8_t* tp, uint32_t t, F& f) {
     uint32_t pos = sm.t_start[t];
     const uint32_t end = sm.t_start[t + 1];
     uint32_t e = sm.t_eb[t];
     const uint32_t ee = e + sm.t_ne[t];
     while (e < ee) {
-        const uint32_t o = sm.ev_pos[EI(e)] & POS_MASK;
+        const uint32_t v = sm.ev_pos[EI(e)];
+        if (ROUNDS && (v & (EV_CLOSE | EV_DONE)) != EV_DONE) { ++e; continue; }  // a close, or an open that stays text
+        const uint32_t o = v & POS_MASK;
         if (o > pos) f(tp + pos, o - pos);
         const uint32_t ce = sm.ev_match[EI(e)];
         if (sm.ev_a[EI(ce)]) f(tv.base + (size_t)sm.ev_a[EI(e)] * 16u, sm.ev_a[EI(ce)]);
@@ -373,6 +387,7 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
 
 // Resolves group g and then, while g was the last unresolved child of its parent, the parent too
 // (a `{q-{idx-{slot-A}}}` chain is one thread's work instead of one queue round per level).
+template <bool ROUNDS>
 __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
   uint32_t carry_e = NONE16;
   uint4 carry_v = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
@@ -433,13 +448,25 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
             err = ac.ok ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
         }
     }
+    bool splice = false;
     if (hit && !simple) {
         if (!tag_splices(IE_SLOT_TAG(vl_tf))) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
-        else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
+        else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) {
+            // interp.rs:81-83 rescans the spliced value.  Properly nested groups in it resolve in place: the value's
+            // text takes the group's place and the template goes another round; anything else is the general path's.
+            if (ROUNDS && IE_SLOT_FLAGS(vl_tf) == (IE_VF_BRACE | IE_VF_BALANCED)) splice = true;
+            else { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
+        }
     }
     if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
     sm.ev_a[EI(g)] = val_off16;
     sm.ev_a[EI(c)] = IE_SLOT_VLEN(vl_tf);
+    if (ROUNDS) sm.ev_pos[EI(g)] |= EV_DONE;
+    if (ROUNDS && splice) {  // the groups enclosing g cannot be looked up yet: they stay text for the next round
+        atomicMax(&sm.t_splice[t], g + 1u);
+        atomicOr(&sm.t_flags[t], TF_AGAIN);
+        return;
+    }
     const uint32_t parent = sm.ev_c[EI(g)];
     if (parent == NONE16) {
         if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
@@ -456,24 +483,41 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   }
 }
 
+// ROUNDS = false is the single-pass kernel (values with groups of their own are punted); ROUNDS = true adds the
+// splice bookkeeping of the rescan rounds.  Two instantiations, so the single-pass path pays nothing for it.
+template <bool ROUNDS>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const IeTableView* __restrict__ views, uint32_t tiles_per_state,
                                                              const uint8_t* __restrict__ tmpl,
                                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
                                                              uint64_t out_cap, uint64_t* __restrict__ out_offs,
                                                              uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
                                                              uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias,
-                                                             uint32_t tt) {
+                                                             uint32_t tt, IeRound rd) {
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
     // a tile = up to tt consecutive templates resolved against ONE snapshot: the table is tile-uniform
+    if (ROUNDS && rd.n_dev) {  // a rescan round: the templates are the previous round's unfinished texts, counted on the device
+        n = *rd.n_dev;
+        if (n == 0) return;
+        // texts grow from round to round (values are spliced in): the tile size follows their mean length
+        const uint64_t avg = *rd.bytes_dev / n;
+        tt = IE_RESOLVE_TILE;
+        while (tt > IE_ROUND_MIN_TILE && (uint64_t)tt * avg * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
+        if ((uint64_t)blockIdx.x * tt >= n) return;
+        tiles_per_state = gridDim.x;
+    }
     const uint32_t state = blockIdx.x / tiles_per_state, tile = blockIdx.x - state * tiles_per_state;
     const IeTableView tv = views[state];
     const uint64_t i0 = (uint64_t)tile * tt;
     const uint32_t nt = (uint32_t)min((uint64_t)tt, n - i0);
     const uint64_t i = i0 + tid;                    // template
-    const uint64_t r = (uint64_t)state * n + i;      // result index
     const bool active = tid < nt;
+    // result index; in a rescan round the map also says whether the ORIGINAL template was one whole group (only
+    // those may take the typed simple path, interp.rs:45-52 is decided once, on the caller's text)
+    const uint32_t mapped = (ROUNDS && rd.result_map && active) ? __ldg(rd.result_map + i) : 0u;
+    const uint64_t r = (ROUNDS && rd.result_map) ? (uint64_t)(mapped & IE_AGAIN_INDEX_MASK) : (uint64_t)state * n + i;
+    const uint32_t layer_cap = (ROUNDS && rd.result_map) ? mapped >> IE_AGAIN_LAYER_SHIFT : 0xFFFFFFFFu;  // never more layers than the caller's text had
     const bool last_tile = blockIdx.x + 1 == gridDim.x;
 
     // ---- P0: tile extent ----------------------------------------------------------------------
@@ -484,7 +528,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     const uint64_t tile_bytes64 = off_end - off0;
     if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
     if (NT == TT && tid == 0) sm.t_start[TT] = (uint32_t)(off_end - off0);
-    if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; }
+    if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; sm.t_splice[tid] = 0; }
     if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; }
     const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
     const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
@@ -620,17 +664,19 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             if (punt) flags = TF_PUNT;
             else if (n_open == 0) flags = TF_VERBATIM;              // the loop at interp.rs:54 is never entered (stray '}' stay)
             else if (stray || cur_open != NONE16) flags = TF_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
-            if (flags == 0) {
+            uint32_t layers = 0;
+            if (flags == 0 && layer_cap) {
                 // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
                 uint32_t ld = 0, tr = 0;
                 while (ld < ne && sm.ev_pos[EI(eb + ld)] == start + ld) ++ld;
                 while (tr < ne && sm.ev_pos[EI(eb + ne - 1 - tr)] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
-                const uint32_t m0 = min(ld, tr);
-                for (uint32_t j = 0; j < m0; ++j) {
-                    if (sm.ev_match[EI(eb + j)] != eb + ne - 1 - j) break;
-                    sm.ev_pos[EI(eb + j)] |= EV_SIMPLE;
+                const uint32_t m0 = min(min(ld, tr), layer_cap);
+                for (; layers < m0; ++layers) {
+                    if (sm.ev_match[EI(eb + layers)] != eb + ne - 1 - layers) break;
+                    sm.ev_pos[EI(eb + layers)] |= EV_SIMPLE;
                 }
             }
+            if (ROUNDS) sm.t_layers[tid] = (uint8_t)min(layers, 255u);
         }
         sm.t_eb[tid] = (uint16_t)eb;
         sm.t_ne[tid] = (uint16_t)ne;
@@ -661,7 +707,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
         uint64_t tile_total16;
         const uint64_t loc = ie_scan::local_scan(sm.scan, olen, 15, &tile_total16);
         const uint64_t off = ie_scan::allocate(sm.scan, &info->out_bytes, tile_total16) + loc;
-        if (tid == 0 && last_tile) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
+        if (tid == 0 && last_tile && !(ROUNDS && rd.n_dev)) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
         if (!active) return;
         out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
         if (olen == 0) return;
@@ -676,8 +722,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
         const uint32_t nq = sm.q_n[0];
         for (uint32_t k = tid; k < nq; k += NT) {
             const uint32_t item = sm.u.scan.q[k];
-            if (sm.t_flags[item >> 16]) continue;  // punted after some of its leaves were queued
-            resolve_group(sm, tv, tp, item >> 16, item & 0xFFFFu);
+            if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
+            resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
     }
     PHASE_MARK(5);
@@ -697,7 +743,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             olen = sm.t_start[tid + 1] - sm.t_start[tid];
             nseg = olen ? 1 : 0;
             mode = 1;
-        } else if (err) {
+        } else if (err && (!ROUNDS || (err >> 8) + 1u > sm.t_splice[tid])) {
+            // the rightmost failing group lies right of every spliced value: it is the first failure in the
+            // reference's rightmost-first order, and final.  (A failure LEFT of a splice is not: the groups inside
+            // the spliced text are resolved first and may fail first - the template goes another round.)
             status = err & 0xFF;
             err_g = err >> 8;
             PieceCount pc;
@@ -706,10 +755,18 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             mode = 2;
         } else {
             PieceCount pc;
-            walk_output_pieces(sm, tv, tp, tid, pc);
+            walk_output_pieces<ROUNDS>(sm, tv, tp, tid, pc);
             olen = pc.bytes; nseg = pc.n;
             mode = 3;
-            if (sm.ev_pos[EI(sm.t_eb[tid])] & EV_SIMPLE) {  // the whole template is one group: typed result
+            if (ROUNDS && (flags & TF_AGAIN) && (sm.t_layers[tid] > IE_AGAIN_LAYER_MAX || rd.last_round)) {
+                // no further round (or more simple layers than the round map can carry): the general path redoes it
+                status = IE_RES_PUNT; olen = 0; nseg = 0; mode = 0;
+                ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r;
+            } else if (ROUNDS && (flags & TF_AGAIN)) {  // its text so far becomes a template of the next round
+                status = IE_RES_AGAIN;
+                rd.again_list[atomicAdd(rd.again_count, 1u)] = (uint32_t)r | ((uint32_t)sm.t_layers[tid] << IE_AGAIN_LAYER_SHIFT);
+                atomicAdd(reinterpret_cast<unsigned long long*>(rd.again_bytes), (unsigned long long)olen);
+            } else if (sm.ev_pos[EI(sm.t_eb[tid])] & EV_SIMPLE) {  // the whole template is one group: typed result
                 status = IE_RES_TYPED | ((uint32_t)sm.t_tag[tid] << 8);
                 aux = sm.t_aux[tid];
             }
@@ -747,7 +804,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             PieceEmit em{sm, sbase, loc, olead, index_chunks};
             if (mode == 1) em(tp + sm.t_start[tid], olen);
             else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
-            else walk_output_pieces(sm, tv, tp, tid, em);
+            else walk_output_pieces<ROUNDS>(sm, tv, tp, tid, em);
         }
         if (tid == 0) { sm.u.seg.cs[0] = 0; sm.u.seg.out[total_seg] = tile_out; }
     }
@@ -758,7 +815,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     const uint64_t tile_begin = ie_scan::allocate(sm.scan, &info->out_bytes, tile_pad64);
     const uint64_t tile_end = tile_begin + tile_pad64;
     const uint64_t off = tile_begin + loc;
-    if (tid == 0 && last_tile) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
+    if (tid == 0 && last_tile && !(ROUNDS && rd.n_dev)) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
     if (active) {
         out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
     }
@@ -769,7 +826,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             PieceCopy cp{out + off};
             if (mode == 1) cp(tp + sm.t_start[tid], olen);
             else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, cp);
-            else if (mode == 3) walk_output_pieces(sm, tv, tp, tid, cp);
+            else if (mode == 3) walk_output_pieces<ROUNDS>(sm, tv, tp, tid, cp);
         }
         return;
     }
@@ -856,10 +913,17 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
-                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, const IeRound& rd,
+                                    cudaStream_t stream) {
+    if (rd.n_dev) tt = IE_ROUND_MIN_TILE;       // rounds >= 2: n is the upper bound, the kernel reads the real count and picks tt >= this
     const uint64_t tiles = (n + tt - 1) / tt;
-    ie_resolve_tile_kernel<<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
-                                                              d_aux, ws, d_info, out_bias, tt);
+    if (rd.allow_splice)
+        ie_resolve_tile_kernel<true><<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap,
+                                                                                      d_out_offs, d_out_lens, d_status, d_aux, ws, d_info, out_bias,
+                                                                                      tt, rd);
+    else
+    ie_resolve_tile_kernel<false><<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
+                                                              d_aux, ws, d_info, out_bias, tt, rd);
     return cudaGetLastError();
 }
 

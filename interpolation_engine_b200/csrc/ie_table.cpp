@@ -15,15 +15,22 @@ namespace {
 // into text (interp.rs:81-83 rescans the spliced value; interp.rs:40-43's sentinels collide).
 uint32_t classify_value(const uint8_t* v, uint64_t n) {
     uint32_t f = 0;
+    int64_t depth = 0;
+    bool nested_ok = true;
     if (n && v[n - 1] == '\\') f |= IE_VF_TRAIL_BS;
     for (uint64_t i = 0; i < n; ++i) {
         const uint8_t c = v[i];
         if (c == '{' || c == '}') {
             const bool esc = i > 0 && v[i - 1] == '\\';
-            if (!esc) f |= IE_VF_BRACE;
+            if (!esc) {
+                f |= IE_VF_BRACE;
+                depth += c == '{' ? 1 : -1;
+                if (depth < 0) nested_ok = false;
+            }
             else if (c == '}' && (i == 1 || v[i - 2] == '.' || v[i - 2] == '}')) f |= IE_VF_QUIRK;
         } else if (c == 0xA0 && i >= 2 && v[i - 1] == 0x80 && v[i - 2] == 0xE3) f |= IE_VF_QUIRK;
     }
+    if (f == IE_VF_BRACE && nested_ok && depth == 0) f |= IE_VF_BALANCED;
     return f;
 }
 
@@ -43,7 +50,7 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
     entries.reserve(n + 2);
     for (uint64_t i = 0; i < n; ++i) {
         if (key_offs[i + 1] < key_offs[i] || val_offs[i + 1] < val_offs[i]) { *why = "offsets not monotone"; return false; }
-        if (key_offs[i + 1] - key_offs[i] >= 0xFFFFFFFFull || val_offs[i + 1] - val_offs[i] > IE_VLEN_MAX) { *why = "key longer than 4 GiB or value longer than 64 MiB"; return false; }
+        if (key_offs[i + 1] - key_offs[i] >= 0xFFFFFFFFull || val_offs[i + 1] - val_offs[i] > IE_VLEN_MAX) { *why = "key longer than 4 GiB or value longer than 32 MiB"; return false; }
         if (tags[i] > IE_TAG_OBJECT) { *why = "bad tag"; return false; }
         entries.push_back(Entry{keys + key_offs[i], key_offs[i + 1] - key_offs[i], vals + val_offs[i], val_offs[i + 1] - val_offs[i], tags[i], (uint32_t)i});
     }
@@ -100,7 +107,7 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
                 kcur += pad16(en.key_len);
             }
         }
-        s->vl_tf = (uint32_t)en.val_len | (en.tag << 26) | (classify_value(en.val, en.val_len) << 29);
+        s->vl_tf = (uint32_t)en.val_len | (en.tag << 25) | (classify_value(en.val, en.val_len) << 28);
         s->entry = en.index;
         if (en.val_len <= IE_INLINE_BYTES) {
             std::memset(s->val_inline, 0, IE_INLINE_BYTES);

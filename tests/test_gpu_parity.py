@@ -282,6 +282,70 @@ def test_c3_many_states_one_launch(eng, oracle):
         assert np.array_equal(one.aux[typed], got.aux[s * n:(s + 1) * n][typed])  # entry index within the state's own inserts
 
 
+# ---- rescan rounds: values that hold groups of their own (interp.rs:81-83) ------------------------------------------
+def _resolve_device_rounds(eng, table, arena, rounds):
+    n, nb = arena.n, arena.bytes.nbytes
+    cap = nb * 8 + (1 << 16)
+    d_t, d_o = eng.alloc(nb + 64).upload(arena.bytes), eng.alloc((n + 1) * 8).upload(arena.offs)
+    d_out, d_oo, d_ol, d_st, d_ax, d_info = (eng.alloc(cap + 16), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
+    eng.resolve_batch_device(table, d_t.ptr, d_o.ptr, n, d_out.ptr, cap, d_oo.ptr, d_ol.ptr, d_st.ptr, d_ax.ptr, d_info.ptr, limits=(0, 0, 0, rounds))
+    eng.sync()
+    info = d_info.download(np.uint64, 3)
+    assert int(info[1]) <= cap
+    return d_out.download(np.uint8, cap), d_oo.download(np.uint64, n), d_ol.download(np.uint32, n), d_st.download(np.int32, n), int(info[2])
+
+
+def test_rescan_rounds(eng, oracle):
+    """A value whose own groups nest properly is spliced and the template resolved again on the fast kernel
+    ("round").  Every number of rounds (0 = everything rescanned goes to the general path) must give the oracle's
+    bytes and statuses, including WHICH error is reported when several groups fail."""
+    ins = {"a": "{b}", "b": "B", "c": "{a}-{a}", "deep": "{c}/{c}", "n": 3, "e": "", "t": True, "nul": None, "obj": {"k": 1},
+           "bad": "{missing}", "bad2": "x{missing2}y{a}", "tb": "{t}", "sq": "[{n}]", "key": "b", "ind": "{{key}}", "esc": "\\{a\\}",
+           "mix": "{esc} {a}", "unb": "{a", "unb2": "a}", "loop": "{loop}", "arr": ["{a}", 1], "qa": "{q-{n}}", "q-3": "three {b}",
+           "lead": "{b}tail", "two": "{e}{a}", "A1": "{A2}", "A2": "{A3}", "A3": "{A4}", "A4": "{A5}", "A5": "end"}
+    templates = ["{a}", "x{a}", "{a}x", "x{a}y{c}z", "{deep}", "a {deep} b", "{q-{n}}", "x{qa}", "x{q-{n}}y", "{bad} {a}", "{a} {bad}", "x{bad2}",
+                 "{bad2} {bad}", "x{tb}", "{tb}", "x{sq}{sq}", "x{ind}", "{ind}", "{{key}}", "x{{key}}", "{e}{a}", "{two}", "x{two}", "{{two}}", "{{e}{a}}",
+                 "x{mix}", "{mix}", "x{unb}", "x{unb2}", "x{unb}{unb2}", "x{loop}", "x{arr}", "{arr}", "x{A1}", "x{A1}{A1}{missing9}", "{missing9} {A1}",
+                 "x{nul}{a}", "x{a}{nul}", "x{obj}", "plain", "", "x{lead}", "{{lead}}", "x{{lead}}", "{a}{a}{a}{a}{a}{a}{a}{a}{a}{a}"]
+    rng = random.Random(42)
+    names = list(ins)
+    for _ in range(600):
+        parts = []
+        for _ in range(rng.randint(1, 5)):
+            r = rng.random()
+            if r < 0.55:
+                parts.append("{" + rng.choice(names) + "}")
+            elif r < 0.65:
+                parts.append("{q-{" + rng.choice(["n", "a", "key", "missing"]) + "}}")
+            elif r < 0.75:
+                parts.append("{{" + rng.choice(names) + "}}")
+            else:
+                parts.append(rng.choice(["x", " ", "\\{", "\\}", "lit"]))
+        templates.append("".join(parts))
+    arena = ie.Arena.from_strings(templates)
+    packed = ie.PackedInserts.from_dict(ins)
+    table = eng.pack(packed)
+    out, offs, status, aux = oracle.build_table(packed).resolve_batch(arena.bytes, arena.offs)
+    lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+    limit = KIND_TO_CODE["limit"]
+    keep = (status & 0xFF) != limit  # self-referential values: both sides report the limit, thresholds differ
+    assert keep.sum() > len(templates) * 0.8
+    generals = []
+    for rounds in (0, 1, 2, 3):
+        g_out, g_offs, g_lens, g_status, n_general = _resolve_device_rounds(eng, table, arena, rounds)
+        generals.append(n_general)
+        assert np.array_equal((g_status & 0xFF)[~keep], (status & 0xFF)[~keep])
+        assert np.array_equal((g_status & 0xFF)[keep], (status & 0xFF)[keep]), (rounds, [templates[i] for i in np.nonzero((g_status & 0xFF) != (status & 0xFF))[0][:5]])
+        assert np.array_equal(g_lens[keep], lens[keep]), rounds
+        for i in np.nonzero(keep)[0]:
+            a = g_out[int(g_offs[i]):int(g_offs[i]) + int(g_lens[i])].tobytes()
+            assert a == out[int(offs[i]):int(offs[i + 1])].tobytes(), (rounds, templates[i], a)
+    assert generals[0] > generals[1] >= generals[2] >= generals[3]  # rounds take work off the general path
+    got = eng.resolve_batch(table, arena)                             # host API: two rounds by default
+    assert np.array_equal((got.status_raw & 0xFF)[keep], (status & 0xFF)[keep])
+    assert oracle.first_mismatch(got.out, got.offs[keep], out, offs[:-1][keep], lens[keep]) is None
+
+
 # ---- replace_map / goto_map (SURVEY.md §8 f: the callers that loop over the resolver) ------------------------
 def test_replace_map_goto_map_on_gpu(eng, oracle):
     from tests.test_oracle_golden import REPLACE_GOTO_VECTORS, TA_PRINTED_MAPS, _norm
