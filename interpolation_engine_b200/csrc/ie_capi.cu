@@ -79,6 +79,7 @@ struct ie_table {
     IeTableView view{};           // snapshot 0 (ie_lookup_batch)
     const IeTableView* d_views = nullptr;
     uint32_t n_states = 1;
+    bool has_balanced = false;    // some value holds properly nested groups of its own: rescan rounds can do work
 };
 
 namespace {
@@ -248,9 +249,12 @@ ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const u
     std::vector<std::vector<uint8_t>> images(1);
     std::vector<uint32_t> caps(1, 0), counts(1, (uint32_t)n);
     std::string why;
-    if (!ie_host::build_table_image(n, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, &images[0], &caps[0], &why))
+    bool balanced = false;
+    if (!ie_host::build_table_image(n, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, &images[0], &caps[0], &why, false, &balanced))
         return fail(IE_E_INVALID, "ie_table_pack: " + why);
-    return upload_tables(e, images, caps, counts, out, "ie_table_pack");
+    ie_status_t st = upload_tables(e, images, caps, counts, out, "ie_table_pack");
+    if (st == IE_OK) (*out)->has_balanced = balanced;
+    return st;
 }
 
 ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys, const uint64_t* key_offs,
@@ -312,7 +316,7 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     IeWorkspace ws;
     if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
     if (rounds > 3) rounds = 3;
-    if (t->n_states != 1) rounds = 0;
+    if (t->n_states != 1 || !t->has_balanced) rounds = 0;  // no value could be spliced: the rounds would be empty launches
     ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0, rounds != 0);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->d_views, t->n_states, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,

@@ -13,7 +13,7 @@ namespace ie_host {
 // Builds the byte image of the device table (slots + key arena + value arena, ie_common.cuh).
 bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
                        const uint8_t* tags, const char* hhmm, const char* hhmmss, std::vector<uint8_t>* image, uint32_t* capacity,
-                       std::string* why, bool compact = false);
+                       std::string* why, bool compact = false, bool* any_balanced = nullptr);
 
 ie_status_t call_json(ie_engine* e, const std::string& args_json, std::string* out_json, std::string* why);
 

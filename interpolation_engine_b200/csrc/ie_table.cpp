@@ -44,7 +44,8 @@ struct Entry {
 
 bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
                        const uint8_t* tags, const char* hhmm, const char* hhmmss, std::vector<uint8_t>* image, uint32_t* capacity,
-                       std::string* why, bool compact) {
+                       std::string* why, bool compact, bool* any_balanced) {
+    if (any_balanced) *any_balanced = false;
     if (n > 0x3FFFFFFFull) { *why = "too many inserts (max 2^30 - 1)"; return false; }
     std::vector<Entry> entries;
     entries.reserve(n + 2);
@@ -107,7 +108,9 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
                 kcur += pad16(en.key_len);
             }
         }
-        s->vl_tf = (uint32_t)en.val_len | (en.tag << 25) | (classify_value(en.val, en.val_len) << 28);
+        const uint32_t vflags = classify_value(en.val, en.val_len);
+        if (any_balanced && (vflags & IE_VF_BALANCED)) *any_balanced = true;
+        s->vl_tf = (uint32_t)en.val_len | (en.tag << 25) | (vflags << 28);
         s->entry = en.index;
         if (en.val_len <= IE_INLINE_BYTES) {
             std::memset(s->val_inline, 0, IE_INLINE_BYTES);
