@@ -70,6 +70,9 @@ struct ie_engine {
     // host-API staging
     DevBuf d_in, d_in_offs, d_out, d_out_offs, d_out_lens, d_status, d_aux, d_info, d_mask, d_misc;
     PinBuf h_out, h_out_offs, h_out_lens, h_status, h_aux, h_info;
+    // small batches (one task at a time, the reference's interactive shape): one staging block each way
+    DevBuf d_small_in, d_small_res;
+    PinBuf h_small_in, h_small_res;
 };
 
 struct ie_table {
@@ -80,6 +83,8 @@ struct ie_table {
     const IeTableView* d_views = nullptr;
     uint32_t n_states = 1;
     bool has_balanced = false;    // some value holds properly nested groups of its own: rescan rounds can do work
+    bool pooled = false;          // small table: allocated from the stream-ordered pool (no cudaMalloc / cudaFree per snapshot)
+    cudaEvent_t ready = nullptr;  // upload finished (calls on a caller's stream wait for it)
 };
 
 namespace {
@@ -169,6 +174,13 @@ ie_status_t ie_engine_create(int device, ie_engine** out) {
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
     if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
+    if (err == cudaSuccess) {  // the pool keeps what small tables release instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = 64ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (err != cudaSuccess) { ie_engine_destroy(e); return cuda_fail(err, "ie_engine_create"); }
     *out = e;
     return IE_OK;
@@ -179,9 +191,10 @@ void ie_engine_destroy(ie_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (DevBuf* b : {&e->ws_zero, &e->ws_list, &e->ws_scratch, &e->d_in, &e->d_in_offs, &e->d_out, &e->d_out_offs, &e->d_out_lens,
-                      &e->d_status, &e->d_aux, &e->d_info, &e->d_mask, &e->d_misc})
+                      &e->d_status, &e->d_aux, &e->d_info, &e->d_mask, &e->d_misc, &e->d_small_in, &e->d_small_res})
         b->release();
-    for (PinBuf* b : {&e->h_out, &e->h_out_offs, &e->h_out_lens, &e->h_status, &e->h_aux, &e->h_info}) b->release();
+    for (PinBuf* b : {&e->h_out, &e->h_out_offs, &e->h_out_lens, &e->h_status, &e->h_aux, &e->h_info, &e->h_small_in, &e->h_small_res})
+        b->release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
@@ -215,26 +228,33 @@ static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uin
     t->e = e;
     t->bytes = total;
     t->n_states = (uint32_t)S;
-    cudaError_t err = cudaMalloc(&t->d_base, total);
+    // Small tables (one snapshot of an interactive run) come from the device's stream-ordered pool and are uploaded
+    // with ONE copy and no host synchronisation: a pageable cudaMemcpyAsync returns once the bytes are staged, and
+    // everything that uses the table is ordered behind it (same stream, or the `ready` event).
+    const bool small = S == 1 && total <= (1u << 20);
+    cudaError_t err = small ? cudaMallocAsync(&t->d_base, total, e->stream) : cudaMalloc(&t->d_base, total);
     if (err != cudaSuccess) { delete t; return cuda_fail(err, who); }
+    t->pooled = small;
     std::vector<IeTableView> views(S);
     for (size_t s = 0; s < S; ++s) {
         views[s].base = (const uint8_t*)t->d_base + at[s];
         views[s].mask = caps[s] - 1;
         views[s].n_entries = counts[s];
     }
-    if (S == 1) {
-        err = cudaMemcpyAsync(t->d_base, images[0].data(), images[0].size(), cudaMemcpyHostToDevice, e->stream);
-    } else {  // one staged copy instead of thousands of small ones
-        std::vector<uint8_t> all(views_at, 0);
+    if (small || S > 1) {  // images and the view array in one staged block, one copy
+        std::vector<uint8_t> all(total, 0);
         for (size_t s = 0; s < S; ++s) std::memcpy(all.data() + at[s], images[s].data(), images[s].size());
+        std::memcpy(all.data() + views_at, views.data(), S * sizeof(IeTableView));
         err = cudaMemcpyAsync(t->d_base, all.data(), all.size(), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess && !small) err = cudaStreamSynchronize(e->stream);
+    } else {               // one large snapshot: no second host copy of its image
+        err = cudaMemcpyAsync(t->d_base, images[0].data(), images[0].size(), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, views.data(), sizeof(IeTableView), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     }
-    if (err == cudaSuccess)
-        err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, views.data(), S * sizeof(IeTableView), cudaMemcpyHostToDevice, e->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    if (err != cudaSuccess) { cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(t->ready, e->stream);
+    if (err != cudaSuccess) { if (small) cudaFreeAsync(t->d_base, e->stream); else cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
     t->view = views[0];
     t->d_views = (const IeTableView*)((uint8_t*)t->d_base + views_at);
     *out = t;
@@ -298,8 +318,13 @@ uint32_t ie_table_states(const ie_table* t) { return t ? t->n_states : 0; }
 void ie_table_free(ie_table* t) {
     if (!t) return;
     cudaSetDevice(t->e->device);
-    cudaStreamSynchronize(t->e->stream);
-    if (t->d_base) cudaFree(t->d_base);
+    if (t->ready) cudaEventDestroy(t->ready);
+    if (t->pooled) {  // stream-ordered: freed once everything queued on the engine's stream so far has run
+        if (t->d_base) cudaFreeAsync(t->d_base, t->e->stream);
+    } else {
+        cudaStreamSynchronize(t->e->stream);
+        if (t->d_base) cudaFree(t->d_base);
+    }
     delete t;
 }
 
@@ -315,6 +340,7 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     const uint32_t tt = ie_pick_tile(avg_bytes);
     IeWorkspace ws;
     if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
+    if (s != e->stream && t->ready) CU(cudaStreamWaitEvent(s, t->ready, 0));
     if (rounds > 3) rounds = 3;
     if (t->n_states != 1 || !t->has_balanced) rounds = 0;  // no value could be spliced: the rounds would be empty launches
     ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0, rounds != 0);
@@ -437,6 +463,59 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
     return IE_OK;
 }
 
+// Small batches (the reference's interactive shape: one task, a handful of strings): one copy in, the kernels, one copy
+// out, ONE host synchronisation.  Inputs travel as [offsets | text] in one pinned block; results come back as
+// [info | out_offs | out_lens | status | aux | first bytes of the out arena] in another.  *done = false: the results did
+// not fit the block's arena and the caller takes the general route.
+static constexpr uint64_t kSmallTemplates = 4096, kSmallBytes = 128u << 10, kSmallArena = 512u << 10;
+static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs, uint64_t n,
+                                 const ie_limits* limits, ie_result* res, bool* done) {
+    *done = false;
+    cudaStream_t s = e->stream;
+    const uint64_t in_bytes = tmpl_offs[n], nr = n * t->n_states;
+    const size_t offs_bytes = (n + 1) * 8, in_total = offs_bytes + in_bytes;
+    const size_t a_info = 0, a_offs = 64, a_lens = a_offs + nr * 8, a_stat = a_lens + nr * 4, a_aux = a_stat + nr * 4;
+    const size_t a_arena = (a_aux + nr * 4 + 15) & ~size_t(15), res_total = a_arena + kSmallArena;
+    CU(e->d_small_in.ensure(in_total + 64, s));
+    CU(e->d_small_res.ensure(res_total + 64, s));
+    CU(e->h_small_in.ensure(in_total + 64));
+    CU(e->h_small_res.ensure(res_total + 64));
+    uint8_t* hin = (uint8_t*)e->h_small_in.p;
+    std::memcpy(hin, tmpl_offs, offs_bytes);
+    if (in_bytes) std::memcpy(hin + offs_bytes, tmpl, in_bytes);
+    CU(cudaMemcpyAsync(e->d_small_in.p, hin, in_total, cudaMemcpyHostToDevice, s));
+    uint8_t* dres = (uint8_t*)e->d_small_res.p;
+    CU(cudaEventRecord(e->ev0, s));
+    ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_small_in.p + offs_bytes, (const uint64_t*)e->d_small_in.p, n, limits,
+                                    dres + a_arena, kSmallArena, (uint64_t*)(dres + a_offs), (uint32_t*)(dres + a_lens), (int32_t*)(dres + a_stat),
+                                    (uint32_t*)(dres + a_aux), (ie_batch_info*)(dres + a_info), 0, s, n ? in_bytes / n : 0, host_rounds(limits));
+    if (st != IE_OK) return st;
+    CU(cudaEventRecord(e->ev1, s));
+    // results + the first part of the arena in one copy; the rest of the arena only if the batch produced more
+    const size_t first = a_arena + std::min<size_t>(kSmallArena, std::max<size_t>(4 * in_bytes + 4096, 16384));
+    uint8_t* hres = (uint8_t*)e->h_small_res.p;
+    CU(cudaMemcpyAsync(hres, dres, first, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const ie_batch_info* hi = (const ie_batch_info*)(hres + a_info);
+    if (hi->out_bytes > kSmallArena) return IE_OK;  // too much output for this route
+    if (a_arena + hi->out_bytes > first) {
+        CU(cudaMemcpyAsync(hres + first, dres + first, a_arena + hi->out_bytes - first, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    res->out = hres + a_arena;
+    res->out_offs = (const uint64_t*)(hres + a_offs);
+    res->out_lens = (const uint32_t*)(hres + a_lens);
+    res->status = (const int32_t*)(hres + a_stat);
+    res->aux = (const uint32_t*)(hres + a_aux);
+    res->info = *hi;
+    res->info.n = nr;
+    res->info.kernel_ms = ms;
+    *done = true;
+    return IE_OK;
+}
+
 ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs, uint64_t n,
                              const ie_limits* limits, ie_result* res) {
     if (!e || !t || !res || (n && (!tmpl_offs))) return fail(IE_E_INVALID, "ie_resolve_batch: NULL argument");
@@ -446,6 +525,11 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     if (in_bytes && !tmpl) return fail(IE_E_INVALID, "ie_resolve_batch: NULL template arena");
     cudaStream_t s = e->stream;
     const uint64_t S = t->n_states, nr = n * S;  // every snapshot resolves all n templates: nr results, index = snapshot * n + template
+    if (n && nr <= kSmallTemplates && in_bytes <= kSmallBytes) {
+        bool done = false;
+        ie_status_t st = resolve_small(e, t, tmpl, tmpl_offs, n, limits, res, &done);
+        if (st != IE_OK || done) return st;
+    }
     if (S == 1 && n >= 2 * kPipeChunk) {
         bool done = false;
         ie_status_t st = resolve_pipelined(e, t, tmpl, tmpl_offs, n, limits, res, &done);
