@@ -282,6 +282,33 @@ def test_c3_many_states_one_launch(eng, oracle):
         assert np.array_equal(one.aux[typed], got.aux[s * n:(s + 1) * n][typed])  # entry index within the state's own inserts
 
 
+def test_edge_shapes(eng, oracle):
+    """Empty and ragged batches, tile-boundary counts, a template longer than a tile can hold (per-thread path), values
+    longer than a tile, one template with hundreds of groups, degenerate glob / escape inputs."""
+    ins = {"a": "A", "b": "{a}", "n": 5, "big": "x" * 5000, "e": ""}
+    pk = ie.PackedInserts.from_dict(ins)
+    tab, ot = eng.pack(pk), oracle.build_table(pk)
+    batches = [[], [""], [""] * 1000, ["{a}" * 3] * 127, ["x{a}"] * 128, ["x{a}y"] * 129,
+               ["{" * 40 + "}" * 40, "}" * 10, "{" * 10, "{}{}", "{{{{a}}}}"], ["lit " * 250000 + "{a}"], ["{big}" * 20, "x{big}y" * 13],
+               ["{a}{n}{e}" * 700], [("t%d {a} " % i) * (i % 50) for i in range(3000)], ["{b} {a}"] * 5000 + ["{missing} {b}"] * 100]
+    for templates in batches:
+        ar = ie.Arena.from_strings(templates)
+        got = eng.resolve_batch(tab, ar)
+        out, offs, status, aux = ot.resolve_batch(ar.bytes, ar.offs)
+        assert np.array_equal(got.status_raw & 0xFF, status & 0xFF)
+        lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+        assert np.array_equal(got.lens, lens)
+        assert oracle.first_mismatch(got.out, got.offs, out, offs[:-1], lens) is None
+    m, nd = eng.glob_sweep([], ["*"])
+    assert len(m) == 0 and nd == 0
+    m, nd = eng.glob_sweep(["a", "b"], [])
+    assert int(m[0]) == 0 and nd == 0
+    m, nd = eng.glob_sweep(["a", "b"], [], invert=True)
+    assert int(m[0]) == 3 and nd == 2
+    assert eng.escape_batch([], 1).n == 0 and eng.escape_batch([""], 0).strings() == [b""]
+    assert int(eng.escape_batch(["{" * 100000], 1).offs[-1]) == 200000
+
+
 # ---- rescan rounds: values that hold groups of their own (interp.rs:81-83) ------------------------------------------
 def _resolve_device_rounds(eng, table, arena, rounds):
     n, nb = arena.n, arena.bytes.nbytes
