@@ -8,6 +8,12 @@
  * thread.  There is no CPU fallback: every resolve/escape/glob call runs CUDA kernels on the
  * engine's device and fails with IE_E_CUDA when no device is usable.
  *
+ * Threading: an engine owns its streams, staging buffers and workspace; calls on ONE engine must not
+ * overlap (the reference calls the resolver from one thread, interp.rs is synchronous).  Use one engine
+ * per host thread or per GPU; tables belong to the engine that packed them.  Host-buffer results stay
+ * owned by the engine until its next call.  Device-buffer calls are asynchronous on the given stream
+ * and share the engine's workspace: issue them on one stream at a time.
+ *
  * Data layout conventions
  *   string arenas   : `bytes` + `offs[n+1]` (uint64, offs[0]=0, offs[n]=total bytes), no separators
  *   packed inserts  : key arena + value arena + tags[n]; a value is the value_to_string()
