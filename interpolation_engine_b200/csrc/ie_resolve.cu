@@ -359,9 +359,13 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     IeRound rd{};
     rd.allow_splice = rescan_rounds ? 1u : 0u;
     if (rescan_rounds) { rd.again_list = ws.round_list[0]; rd.again_count = &ws.round_ctl->count[0]; rd.again_bytes = &ws.round_ctl->bytes[0]; }
-    if ((err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                                       out_bias, tt, rd, stream)) != cudaSuccess)
-        return err;
+    // many snapshots with a handful of templates each: 32-template tiles on 64-thread CTAs (a tile never mixes snapshots)
+    const bool small_tiles = n_states > 1 && n <= IE_SMALL_TILE;
+    if (small_tiles) err = ie_launch_resolve_tiles_small(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+                                                         d_info, out_bias, tt < IE_SMALL_TILE ? tt : IE_SMALL_TILE, rd, stream);
+    else err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
+                                       out_bias, tt, rd, stream);
+    if (err != cudaSuccess) return err;
     for (uint32_t k = 0; k < rescan_rounds; ++k) {
         // round k + 2 reads again list (k & 1), maps results through list 2 and fills again list ((k + 1) & 1)
         const uint32_t in = k & 1;

@@ -21,6 +21,16 @@
 // bracket matching, and the reference's error is the failing group with the largest '{' position.
 // Anything else (flagged values, uneven or improper braces, sentinel collisions, capacity overflow of
 // the per-tile tables) is handed to the general kernel or to the per-thread fallback, both exact.
+//
+// This file is compiled TWICE: as is (128-template tiles, 256 threads, 5 CTAs per SM) and with IE_TILE_SMALL
+// (32-template tiles, 64 threads: many snapshots x a handful of templates each — the cloned-states shape, where a
+// tile is one snapshot's templates and a 128-template tile would be a quarter full).
+#ifdef IE_TILE_SMALL
+#define IE_RESOLVE_TILE 32
+#define IE_TILE_NT 64
+#define IE_TILE_CTAS 20
+#define ie_launch_resolve_tiles ie_launch_resolve_tiles_small
+#endif
 #include <cuda_runtime.h>
 
 #include "ie_common.cuh"
@@ -28,7 +38,7 @@
 #include "ie_kernels.h"
 #include "ie_scan.cuh"
 
-#ifdef IE_PHASE_TIMING
+#if defined(IE_PHASE_TIMING) && !defined(IE_TILE_SMALL)
 __device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
 #define PHASE_INIT() long long t_phase_ = clock64()
@@ -927,7 +937,7 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
     return cudaGetLastError();
 }
 
-#ifdef IE_PHASE_TIMING
+#if defined(IE_PHASE_TIMING) && !defined(IE_TILE_SMALL)
 extern "C" int ie_debug_phase_cycles(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
