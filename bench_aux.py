@@ -2,7 +2,10 @@
 """Secondary measurements (not the driver's contract line — that is bench.py): the other configs of
 BASELINE.json on one B200, one JSON line each, same roofline / cpu_baseline conventions.
 
-    python bench_aux.py [--which c5,escape,c3]
+    python bench_aux.py [--which c5,escape,c3,c1c2]
+
+The CPU oracle (oracle/, test infrastructure) is loaded here ONLY for the `cpu_baseline` legs and, in c1c2, as the parity
+check of the three calls it times; nothing that is measured as "ours" touches it.
 
   c5      wildcard delete sweep over 10 M keys x 64 pattern sets (runtime.rs:1198-1239, 1633-1647)
   escape  recursive_escape / recursive_unescape over the 1 Mi C4 templates (interp.rs:147-177)
