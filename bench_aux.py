@@ -59,12 +59,29 @@ def bench_c5(eng, ie, workloads, torch, dev, orc):
     ms = device_time_ms(torch, stream, step, 2 * len(arenas))
     alg = keys.bytes.nbytes + (n + 1) * 8 + (n + 7) // 8
     peak, src = measured_peak()
-    # e2e through the host-buffer call
+    # e2e through the host-buffer call, key arena and offsets in pinned host memory (like bench.py's e2e)
+    import ctypes
+
+    def pinned(arr):
+        p = ctypes.c_void_p()
+        eng._check(eng.lib.ie_host_alloc(arr.nbytes, ctypes.byref(p)))
+        ctypes.memmove(p.value, arr.ctypes.data, arr.nbytes)
+        return p
+    h_k, h_o = pinned(keys.bytes), pinned(keys.offs)
+    mask = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+    nd = ctypes.c_uint64(0)
+
+    def sweep(k):
+        pa = arenas[k]
+        eng._check(eng.lib.ie_glob_sweep(eng.handle, h_k, h_o, n, pa.bytes.ctypes.data, pa.offs.ctypes.data, pa.n, k & 1, mask.ctypes.data, ctypes.byref(nd)))
+    sweep(0)
     t0 = time.perf_counter()
-    reps = 4
+    reps = 8
     for k in range(reps):
-        eng.glob_sweep(keys, arenas[k], invert=bool(k & 1))
+        sweep(k)
     e2e_s = (time.perf_counter() - t0) / reps
+    eng.lib.ie_host_free(h_k)
+    eng.lib.ie_host_free(h_o)
     threads = os.cpu_count() or 1
     sub = 1 << 21
     ksub = ie.Arena(keys.bytes[:int(keys.offs[sub])], keys.offs[:sub + 1])
