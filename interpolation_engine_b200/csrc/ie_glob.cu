@@ -39,13 +39,24 @@ constexpr uint32_t FRONT_PAD = 32, BACK_PAD = 48;  // the 32-byte windows of the
 constexpr uint32_t BUF_BYTES = FRONT_PAD + STAGE_BYTES + BACK_PAD;
 constexpr int GLOB_CTAS_PER_SM = 4;      // two stage buffers per CTA
 
-// 32 bytes starting at p (shared memory, any alignment) as 8 little-endian words
-__device__ __forceinline__ void load_window(const uint8_t* p, uint32_t (&w)[8]) {
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+// The staged key text is read through explicit shared-space loads: a pointer that may be shared OR global (the
+// unstaged fallback) makes the compiler emit generic loads, which are slower than LDS.
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// 4 bytes at shared address a (any alignment)
+__device__ __forceinline__ uint32_t lds_word(uint32_t a) {
+    const uint32_t aw = a & ~3u;
+    return __funnelshift_r(lds32(aw), lds32(aw + 4), (a & 3u) * 8);
+}
+// 32 bytes starting at shared address a (any alignment) as 8 little-endian words
+__device__ __forceinline__ void load_window(uint32_t a, uint32_t (&w)[8]) {
+    const uint32_t aw = a & ~3u, sh = (a & 3u) * 8;
     uint32_t x[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = aw[k];
+    for (int k = 0; k < 9; ++k) x[k] = lds32(aw + 4 * k);
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
@@ -56,14 +67,9 @@ __device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const 
     // the last word of the suffix image (the most discriminating ones: "persona-123/" differs from most
     // keys in "123/", "/field-42" in "d-42").  Only keys that pass the probe of a pattern with longer pieces
     // load their full 32-byte windows.
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>((uintptr_t)s & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)((uintptr_t)s & 3) * 8;
+    const uint32_t sa = staged ? (uint32_t)__cvta_generic_to_shared(s) : 0u;  // the key's address in shared memory
     uint32_t t7 = 0;
-    if (staged && pats.any_suf) {
-        const uint8_t* e4 = s + len - 4;
-        const uint32_t* ew = reinterpret_cast<const uint32_t*>((uintptr_t)e4 & ~(uintptr_t)3);
-        t7 = __funnelshift_r(ew[0], ew[1], (uint32_t)((uintptr_t)e4 & 3) * 8);
-    }
+    if (staged && pats.any_suf) t7 = lds_word(sa + len - 4);
     bool any = false;
     uint32_t q = 0;
     for (; q < pats.n_pat && !any; ++q) {
@@ -71,14 +77,13 @@ __device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const 
         const uint4 pb = *(reinterpret_cast<const uint4*>(&pats.probe[q]) + 1);  // min_len, max_len, probe_off, kind
         const uint32_t kind = pb.w & 0xFFu;
         if (staged && kind != IE_GLOB_GENERIC) {
-            const uint32_t* pw = aw + (pb.z >> 2);
-            const uint32_t hw = __funnelshift_r(pw[0], pw[1], sh);
+            const uint32_t hw = lds_word(sa + pb.z);
             bool cand = (((hw ^ pa.x) & pa.y) | ((t7 ^ pa.z) & pa.w)) == 0 && len >= pb.x && len <= pb.y;
             if (cand && (pb.w >> 8) == 0) {  // pieces longer than the probe words: the full 32-byte windows
                 const IeGlobFast& f = pats.fast[q];
                 uint32_t H[8], T[8];  // the key's first / last 32 bytes (bytes outside the key are masked out)
-                load_window(s, H);
-                load_window(s + len - 32, T);
+                load_window(sa, H);
+                load_window(sa + len - 32, T);
                 uint32_t diff = 0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) diff |= ((H[w] ^ f.pre[w]) & f.pre_mask[w]) | ((T[w] ^ f.suf[w]) & f.suf_mask[w]);
@@ -92,7 +97,7 @@ __device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const 
                     // zero-byte test per word), limited to [mid_lo, len - mid_hi]; each candidate (a handful at most)
                     // then compares the piece's first word.
                     uint32_t H[8];
-                    load_window(s, H);
+                    load_window(sa, H);
                     const uint32_t b0 = (f.mid & 0xFFu) * 0x01010101u;
                     uint32_t hits = 0;
 #pragma unroll
@@ -107,9 +112,7 @@ __device__ __forceinline__ uint32_t match_key(const IeGlobPatterns& pats, const 
                     while (hits && !cand) {
                         const uint32_t i = __ffs(hits) - 1;
                         hits &= hits - 1;
-                        const uint8_t* pm = s + i;
-                        const uint32_t* mw = reinterpret_cast<const uint32_t*>((uintptr_t)pm & ~(uintptr_t)3);
-                        const uint32_t wv = __funnelshift_r(mw[0], mw[1], (uint32_t)((uintptr_t)pm & 3) * 8);
+                        const uint32_t wv = lds_word(sa + i);
                         cand = ((wv ^ f.mid) & f.mid_mask) == 0;
                     }
                     if (cand && f.mid_len > 4) cand = glob_match(pats.bytes + pats.off[q], (uint32_t)pats.off[q + 1] - pats.off[q], s, len);
