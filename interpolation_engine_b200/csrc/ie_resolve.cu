@@ -115,6 +115,7 @@ __device__ uint8_t* reserve_out(uint8_t* out, uint64_t out_cap, ie_batch_info* i
     return out + off;
 }
 
+template <bool SMEM>  // tier 1: the scratch lives in shared memory (known address space: LDS / STS instead of generic accesses)
 __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_kernel(const IeTableView* __restrict__ views, uint64_t per_state,
                                                                 const uint8_t* __restrict__ tmpl,
                                                                 const uint64_t* __restrict__ offs, uint8_t* __restrict__ out,
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
     // (stores do not allocate in L1).  Tier 1 therefore keeps its small scratch in SHARED memory (smem_stride != 0,
     // skewed by 4 bytes per thread against bank conflicts); tier 2 uses the big global scratch.
     extern __shared__ __align__(16) uint8_t gen_smem[];
-    uint8_t* T = smem_stride ? gen_smem + (size_t)(threadIdx.x >> 5) * smem_stride : ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
+    uint8_t* T = SMEM ? gen_smem + (size_t)(threadIdx.x >> 5) * smem_stride : ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
     uint8_t* kscr = T + tcap;
 
     for (uint32_t q = worker; q < count; q += n_workers) {
@@ -393,16 +394,16 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     const uint32_t small_t = tcap < IE_GENERAL_SMALL_TEXT ? tcap : IE_GENERAL_SMALL_TEXT;
     const uint32_t stride = IE_GENERAL_SMALL_TEXT + IE_GENERAL_SMALL_KEY + 4;
     const size_t smem = (size_t)(IE_GENERAL_SMALL_THREADS / 32) * stride;
-    if ((err = cudaFuncSetAttribute(ie_resolve_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ie_resolve_general_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ie_resolve_general_kernel<<<sms * 3, IE_GENERAL_SMALL_THREADS, smem, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+    ie_resolve_general_kernel<true><<<sms * 3, IE_GENERAL_SMALL_THREADS, smem, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                                 d_status, d_aux, ws, d_info, max_expansions, small_t,
                                                                                 IE_GENERAL_SMALL_KEY, out_bias, ws.general_list, ws.general_count,
                                                                                 ws.retry_list, ws.retry_count, stride);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    ie_resolve_general_kernel<<<ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32), IE_GENERAL_SMALL_THREADS, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
+    ie_resolve_general_kernel<false><<<ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32), IE_GENERAL_SMALL_THREADS, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH,
                                                                          out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr, 0u);
     return cudaGetLastError();
