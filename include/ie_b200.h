@@ -71,6 +71,9 @@ typedef struct {
     uint32_t avg_template_bytes; /* device-buffer calls only: mean template length, used to size the
                                   CTA tiles (0 = short templates, <= 230 bytes); the host-buffer
                                   calls measure it themselves                                   */
+    uint32_t avg_template_groups; /* device-buffer calls only: mean number of {...} groups per template (0 = at
+                                  most 4); with avg_template_bytes it sizes the CTA tiles so that dense templates
+                                  stay on the fast path.  The host-buffer calls estimate it from the text.   */
     uint32_t rescan_rounds;    /* interp.rs:81-83 rescans every spliced value.  Values whose own groups nest
                                   properly are resolved by running the template through the fast kernel again
                                   ("round"), up to this many times (max 3); what is left, and every other kind

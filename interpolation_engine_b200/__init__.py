@@ -44,7 +44,7 @@ class _Result(ctypes.Structure):
 
 class _Limits(ctypes.Structure):
     _fields_ = [("max_expansions", ctypes.c_uint32), ("max_result_bytes", ctypes.c_uint32), ("avg_template_bytes", ctypes.c_uint32),
-                ("rescan_rounds", ctypes.c_uint32)]
+                ("avg_template_groups", ctypes.c_uint32), ("rescan_rounds", ctypes.c_uint32)]
 
 
 # every symbol include/ie_b200.h declares: name -> (restype, argtypes)

@@ -133,6 +133,17 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
     return IE_OK;
 }
 
+// Groups per template x 16, estimated from the '{' density of a sample of the caller's text (host-buffer calls): sizes
+// the tiles so that brace-dense templates do not overflow a tile's event / segment tables.
+uint64_t sample_groups_x16(const uint8_t* tmpl, uint64_t in_bytes, uint64_t n) {
+    if (!n || !in_bytes) return 0;
+    const uint64_t take = std::min<uint64_t>(in_bytes, 32u << 10);
+    uint64_t opens = 0;
+    for (uint64_t i = 0; i < take; ++i) opens += tmpl[i] == '{';
+    const long double per_byte = (long double)opens / (long double)take;
+    return (uint64_t)(per_byte * (long double)in_bytes / (long double)n * 16.0L + 0.5L);
+}
+
 // Rescan rounds of the host-buffer calls: two by default (their few extra launches hide behind the PCIe copies);
 // the device-buffer call runs exactly limits->rescan_rounds of them (default none: every launch is on its clock).
 uint32_t host_rounds(const ie_limits* in) { return (in && in->rescan_rounds) ? in->rescan_rounds : 2u; }
@@ -333,11 +344,12 @@ uint64_t ie_table_device_bytes(const ie_table* t) { return t ? t->bytes : 0; }
 static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs, uint64_t n,
                                   const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
                                   uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux, ie_batch_info* d_info, uint64_t out_bias,
-                                  cudaStream_t s, uint64_t avg_bytes = 0, uint32_t rounds = 0) {
+                                  cudaStream_t s, uint64_t avg_bytes = 0, uint32_t rounds = 0, uint64_t groups_x16 = 0) {
     uint32_t max_exp, tcap;
     resolve_limits(limits, &max_exp, &tcap);
     if (!avg_bytes && limits) avg_bytes = limits->avg_template_bytes;
-    const uint32_t tt = ie_pick_tile(avg_bytes);
+    if (!groups_x16 && limits) groups_x16 = (uint64_t)limits->avg_template_groups * 16;
+    const uint32_t tt = ie_pick_tile(avg_bytes, groups_x16);
     IeWorkspace ws;
     if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
     if (s != e->stream && t->ready) CU(cudaStreamWaitEvent(s, t->ready, 0));
@@ -424,6 +436,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, 0, true);
         if (st != IE_OK) return st;
     }
+    const uint64_t groups_x16 = sample_groups_x16(tmpl, in_bytes, n);
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
     ie_batch_info* hinfo_dev = nullptr;  // the same pinned block as the device sees it
     CU(cudaHostGetDevicePointer((void**)&hinfo_dev, hinfo, 0));
@@ -438,7 +451,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
                                         (uint8_t*)e->d_out.p + base[k], base[k + 1] - base[k], (uint64_t*)e->d_out_offs.p + lo,
                                         (uint32_t*)e->d_out_lens.p + lo, (int32_t*)e->d_status.p + lo, (uint32_t*)e->d_aux.p + lo,
-                                        (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n, host_rounds(limits));
+                                        (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n, host_rounds(limits), groups_x16);
         if (st != IE_OK) return st;
         ie_publish_info_kernel<<<1, 1, 0, sc>>>((const ie_batch_info*)e->d_info.p + k, hinfo_dev + k);
         CU(cudaGetLastError());
@@ -511,7 +524,8 @@ static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t*
     CU(cudaEventRecord(e->ev0, s));
     ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_small_in.p + offs_bytes, (const uint64_t*)e->d_small_in.p, n, limits,
                                     dres + a_arena, kSmallArena, (uint64_t*)(dres + a_offs), (uint32_t*)(dres + a_lens), (int32_t*)(dres + a_stat),
-                                    (uint32_t*)(dres + a_aux), (ie_batch_info*)(dres + a_info), 0, s, n ? in_bytes / n : 0, host_rounds(limits));
+                                    (uint32_t*)(dres + a_aux), (ie_batch_info*)(dres + a_info), 0, s, n ? in_bytes / n : 0, host_rounds(limits),
+                                    sample_groups_x16(tmpl, in_bytes, n));
     if (st != IE_OK) return st;
     CU(cudaEventRecord(e->ev1, s));
     // results + the first part of the arena in one copy; the rest of the arena only if the batch produced more
@@ -576,7 +590,7 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
                                         (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p,
                                         (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, (ie_batch_info*)e->d_info.p, 0, s,
-                                        n ? in_bytes / n : 0, host_rounds(limits));
+                                        n ? in_bytes / n : 0, host_rounds(limits), sample_groups_x16(tmpl, in_bytes, n));
         if (st != IE_OK) return st;
         CU(cudaEventRecord(e->ev1, s));
         CU(cudaMemcpyAsync(hinfo, e->d_info.p, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, s));

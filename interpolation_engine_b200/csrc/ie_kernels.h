@@ -87,11 +87,18 @@ cudaError_t ie_launch_resolve_tiles_small(const IeTableView* d_views, uint32_t n
                                           uint32_t* d_aux, const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt,
                                           const IeRound& rd, cudaStream_t stream);
 
-// Templates per tile for a batch whose templates average `avg_bytes` (0 = unknown, assume short): the
-// largest power of two <= IE_RESOLVE_TILE whose expected text fits a tile with 25 % headroom.
-inline uint32_t ie_pick_tile(uint64_t avg_bytes) {
+// Templates per tile for a batch whose templates average `avg_bytes` bytes and `avg_groups_x16` / 16 `{...}` groups
+// (0 = unknown, assume short / few): the largest power of two <= IE_RESOLVE_TILE whose expected text, brace events
+// (2 per group) and copy segments (2 per group + 1) fit the tile's tables with 20-25 % headroom.  A tile that outgrows
+// its tables still resolves exactly, but on the slow per-thread path: this keeps dense templates off it.
+#define IE_TILE_EVENTS (12u * 128u)    // ie_resolve_tile.cu: E_CAP of the 128-template build
+#define IE_TILE_SEGMENTS (8u * 128u)   // S_CAP
+inline uint32_t ie_pick_tile(uint64_t avg_bytes, uint64_t avg_groups_x16 = 0) {
     uint32_t tt = IE_RESOLVE_TILE;
-    while (tt > 4 && (uint64_t)tt * avg_bytes * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
+    while (tt > 4 && ((uint64_t)tt * avg_bytes * 5 / 4 > IE_TILE_TEXT_BYTES ||
+                      (uint64_t)tt * avg_groups_x16 * 2 * 5 / 4 > 16ull * IE_TILE_EVENTS ||
+                      (uint64_t)tt * (avg_groups_x16 * 2 + 16) * 5 / 4 > 16ull * IE_TILE_SEGMENTS))
+        tt >>= 1;
     return tt;
 }
 

@@ -34,7 +34,7 @@ for frac in (0.0, 0.01, 0.1, 0.5):
     dev_ms = {}
     for rounds in (0, 2):
         def step():
-            eng.resolve_batch_device(table, d_t.data_ptr(), d_o.data_ptr(), n, bufs[0].data_ptr(), cap, bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr(), stream=sdev.cuda_stream, limits=(0, 0, 0, rounds))
+            eng.resolve_batch_device(table, d_t.data_ptr(), d_o.data_ptr(), n, bufs[0].data_ptr(), cap, bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr(), stream=sdev.cuda_stream, limits=(0, 0, 0, 0, rounds))
         for _ in range(3): step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -30,6 +30,7 @@ pub struct ie_limits {
     pub max_expansions: u32,
     pub max_result_bytes: u32,
     pub avg_template_bytes: u32,
+    pub avg_template_groups: u32,
     pub rescan_rounds: u32,
 }
 

@@ -309,13 +309,48 @@ def test_edge_shapes(eng, oracle):
     assert int(eng.escape_batch(["{" * 100000], 1).offs[-1]) == 200000
 
 
+def test_dense_templates_stay_on_the_tile_path(eng, oracle):
+    """Templates with many groups each: the tile size follows the group density (host calls sample the text, device calls
+    take ie_limits.avg_template_groups), so the tiles' event / segment tables do not overflow onto the per-thread path.
+    Parity either way; the timing bound only catches the 10x cliff."""
+    state = workloads.c4_state()
+    rng = np.random.default_rng(5)
+    n = 20000
+    templates = ["".join("w%d {q-%d} " % (k, rng.integers(0, 32768)) for k in range(14)) for _ in range(n)]
+    arena = ie.Arena.from_strings(templates)
+    table = eng.pack(state)
+    got = eng.resolve_batch(table, arena)
+    out, offs, status, aux = oracle.build_table(state).resolve_batch(arena.bytes, arena.offs, threads=8)
+    lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+    assert np.array_equal(got.status_raw & 0xFF, status & 0xFF) and np.array_equal(got.lens, lens)
+    assert oracle.first_mismatch(got.out, got.offs, out, offs[:-1], lens) is None
+    # device call: without the hint the 128-template tiles overflow their tables (still exact), with it they do not
+    times = {}
+    for groups in (0, 14):
+        nb = arena.bytes.nbytes
+        cap = int(lens.sum()) + (1 << 20)
+        d_t, d_o = eng.alloc(nb + 64).upload(arena.bytes), eng.alloc((n + 1) * 8).upload(arena.offs)
+        bufs = (eng.alloc(cap + 16), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
+        for rep in range(3):
+            eng.sync()
+            t0 = __import__("time").perf_counter()
+            eng.resolve_batch_device(table, d_t.ptr, d_o.ptr, n, bufs[0].ptr, cap, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, bufs[4].ptr, bufs[5].ptr,
+                                     limits=(0, 0, arena.bytes.nbytes // n, groups, 0))
+            eng.sync()
+            times[groups] = __import__("time").perf_counter() - t0
+        g_lens = bufs[2].download(np.uint32, n)
+        assert np.array_equal(g_lens, lens)
+        assert oracle.first_mismatch(bufs[0].download(np.uint8, cap), bufs[1].download(np.uint64, n), out, offs[:-1], lens) is None
+    assert times[14] < times[0], times
+
+
 # ---- rescan rounds: values that hold groups of their own (interp.rs:81-83) ------------------------------------------
 def _resolve_device_rounds(eng, table, arena, rounds):
     n, nb = arena.n, arena.bytes.nbytes
     cap = nb * 8 + (1 << 16)
     d_t, d_o = eng.alloc(nb + 64).upload(arena.bytes), eng.alloc((n + 1) * 8).upload(arena.offs)
     d_out, d_oo, d_ol, d_st, d_ax, d_info = (eng.alloc(cap + 16), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
-    eng.resolve_batch_device(table, d_t.ptr, d_o.ptr, n, d_out.ptr, cap, d_oo.ptr, d_ol.ptr, d_st.ptr, d_ax.ptr, d_info.ptr, limits=(0, 0, 0, rounds))
+    eng.resolve_batch_device(table, d_t.ptr, d_o.ptr, n, d_out.ptr, cap, d_oo.ptr, d_ol.ptr, d_st.ptr, d_ax.ptr, d_info.ptr, limits=(0, 0, 0, 0, rounds))
     eng.sync()
     info = d_info.download(np.uint64, 3)
     assert int(info[1]) <= cap
