@@ -493,34 +493,19 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
   }
 }
 
-// ROUNDS = false is the single-pass kernel (values with groups of their own are punted); ROUNDS = true adds the
-// splice bookkeeping of the rescan rounds.  Two instantiations, so the single-pass path pays nothing for it.
+// Resolves the templates [i0, i0 + nt) of one snapshot as one tile.  Returns false (having written nothing) when the
+// range outgrows the tile's tables and holds more than IE_SPLIT_MIN templates: the caller retries it in halves.  A range
+// of at most IE_SPLIT_MIN templates that still does not fit takes the exact per-thread path instead.
+#define IE_SPLIT_MIN 4u
 template <bool ROUNDS>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const IeTableView* __restrict__ views, uint32_t tiles_per_state,
-                                                             const uint8_t* __restrict__ tmpl,
-                                                             const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
-                                                             uint64_t out_cap, uint64_t* __restrict__ out_offs,
-                                                             uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
-                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias,
-                                                             uint32_t tt, IeRound rd) {
-    __shared__ Smem sm;
+__device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, uint32_t state, const uint8_t* __restrict__ tmpl,
+                                              const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out, uint64_t out_cap,
+                                              uint64_t* __restrict__ out_offs, uint32_t* __restrict__ out_lens,
+                                              int32_t* __restrict__ status_out, uint32_t* __restrict__ aux_out, const IeWorkspace& ws,
+                                              ie_batch_info* info, uint64_t out_bias, const IeRound& rd, uint32_t tiles_per_state,
+                                              uint64_t i0, uint32_t nt) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
-    // a tile = up to tt consecutive templates resolved against ONE snapshot: the table is tile-uniform
-    if (ROUNDS && rd.n_dev) {  // a rescan round: the templates are the previous round's unfinished texts, counted on the device
-        n = *rd.n_dev;
-        if (n == 0) return;
-        // texts grow from round to round (values are spliced in): the tile size follows their mean length
-        const uint64_t avg = *rd.bytes_dev / n;
-        tt = IE_RESOLVE_TILE;
-        while (tt > IE_ROUND_MIN_TILE && (uint64_t)tt * avg * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
-        if ((uint64_t)blockIdx.x * tt >= n) return;
-        tiles_per_state = gridDim.x;
-    }
-    const uint32_t state = blockIdx.x / tiles_per_state, tile = blockIdx.x - state * tiles_per_state;
-    const IeTableView tv = views[state];
-    const uint64_t i0 = (uint64_t)tile * tt;
-    const uint32_t nt = (uint32_t)min((uint64_t)tt, n - i0);
     const uint64_t i = i0 + tid;                    // template
     const bool active = tid < nt;
     // result index; in a rescan round the map also says whether the ORIGINAL template was one whole group (only
@@ -545,6 +530,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     const uint32_t tile_bytes = (uint32_t)tile_bytes64;
     const uint32_t n_chunks = (lead + tile_bytes + 15) >> 4;
     const bool too_big = tile_bytes64 + 32 > (uint64_t)M_CAP * 16;  // does not fit the chunk-mask table
+    if (too_big && nt > IE_SPLIT_MIN) return false;  // the caller retries with half as many templates
 
     // ---- P1: flat brace scan --------------------------------------------------------------------
     // Loads are issued P1_BATCH chunks ahead of the compares so that a thread keeps several HBM
@@ -696,6 +682,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     __syncthreads();
     PHASE_MARK(4);
 
+    if (sm.overflow && nt > IE_SPLIT_MIN) return false;  // more brace events than the tile's tables hold: half as many templates
     if (too_big || sm.overflow) {
         // ---- per-thread exact path for tiles that do not fit the tile tables -----------------------
         uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
@@ -718,13 +705,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
         const uint64_t loc = ie_scan::local_scan(sm.scan, olen, 15, &tile_total16);
         const uint64_t off = ie_scan::allocate(sm.scan, &info->out_bytes, tile_total16) + loc;
         if (tid == 0 && last_tile && !(ROUNDS && rd.n_dev)) info->n = (uint64_t)gridDim.x / tiles_per_state * n;
-        if (!active) return;
+        if (!active) return true;
         out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
-        if (olen == 0) return;
-        if (off + olen > out_cap) { *ws.overflow = 1u; return; }
+        if (olen == 0) return true;
+        if (off + olen > out_cap) { *ws.overflow = 1u; return true; }
         if (verbatim) { uint8_t* wr = out + off; for (uint32_t k = 0; k < len; ++k) wr[k] = __ldg(t + k); }
         else { uint32_t l2, s2, a2; fast_traverse<true>(tv, t, len, m0, out + off + olen, status & 0xFF, l2, s2, a2); }
-        return;
+        return true;
     }
 
     // ---- P3: lookups, one thread per leaf group (and up its parent chain) ------------------------------
@@ -829,7 +816,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     if (active) {
         out_offs[r] = off + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
     }
-    if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return; }
+    if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return true; }
     if (!seg_ok) {
         // segment table overflow: every thread copies its own pieces
         if (active && olen) {
@@ -838,7 +825,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
             else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, cp);
             else if (mode == 3) walk_output_pieces<ROUNDS>(sm, tv, tp, tid, cp);
         }
-        return;
+        return true;
     }
     uint8_t* gout = out + tile_begin;
     const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
@@ -848,7 +835,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     // Pass A: every chunk that lies inside ONE segment (constant source misalignment): 5 aligned words,
     // 4 funnel shifts, one 16-byte store.  Pass B: one thread per segment start handles the chunk that
     // contains it (pieces shifted and OR-ed in registers); the ragged first / last chunk of the tile too.
-    if (tile_out == 0) return;
+    if (tile_out == 0) return true;
     for (uint32_t c = tid; c < o_chunks; c += NT) {
         const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
         if (x0s < 0 || (uint32_t)x0s + 16 > tile_out) continue;   // ragged edge chunk: pass B
@@ -917,6 +904,70 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
         }
     }
     PHASE_MARK(11);
+    return true;
+}
+
+// Which templates a CTA owns: snapshot, first template and count (a tile = up to tt consecutive templates resolved
+// against ONE snapshot, so the table is tile-uniform).  False when the CTA has nothing to do.
+template <bool ROUNDS>
+__device__ __forceinline__ bool tile_geometry(uint32_t bx, uint32_t& tiles_per_state, uint64_t& n, uint32_t tt, const IeRound& rd,
+                                              uint32_t& state, uint64_t& tile_i0, uint32_t& tile_nt) {
+    if (ROUNDS && rd.n_dev) {  // a rescan round: the templates are the previous round's unfinished texts, counted on the device
+        n = *rd.n_dev;
+        if (n == 0) return false;
+        // texts grow from round to round (values are spliced in): the tile size follows their mean length
+        const uint64_t avg = *rd.bytes_dev / n;
+        tt = IE_RESOLVE_TILE;
+        while (tt > IE_ROUND_MIN_TILE && (uint64_t)tt * avg * 5 / 4 > IE_TILE_TEXT_BYTES) tt >>= 1;
+        if ((uint64_t)bx * tt >= n) return false;
+        tiles_per_state = gridDim.x;
+    }
+    state = bx / tiles_per_state;
+    const uint32_t tile = bx - state * tiles_per_state;
+    tile_i0 = (uint64_t)tile * tt;
+    tile_nt = (uint32_t)min((uint64_t)tt, n - tile_i0);
+    return true;
+}
+
+// ROUNDS = false is the single-pass kernel (values with groups of their own are punted); ROUNDS = true adds the
+// splice bookkeeping of the rescan rounds.  Two instantiations, so the single-pass path pays nothing for it.
+template <bool ROUNDS>
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const IeTableView* __restrict__ views, uint32_t tiles_per_state,
+                                                             const uint8_t* __restrict__ tmpl,
+                                                             const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out,
+                                                             uint64_t out_cap, uint64_t* __restrict__ out_offs,
+                                                             uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
+                                                             uint32_t* __restrict__ aux_out, IeWorkspace ws, ie_batch_info* info, uint64_t out_bias,
+                                                             uint32_t tt, IeRound rd) {
+    __shared__ Smem sm;
+    // The tile's templates go through as one range.  A range that outgrows the tile tables (very long or very
+    // brace-dense templates) comes back untouched and is retried in halves, down to IE_SPLIT_MIN templates, before the
+    // per-thread path takes over.  The retry loop is a second, cold copy of the body which recomputes what it needs
+    // (the block index is re-read so that the compiler cannot carry it over), so the common case keeps nothing alive
+    // for it.
+    uint32_t state, tile_nt;
+    uint64_t tile_i0;
+    if (!tile_geometry<ROUNDS>(blockIdx.x, tiles_per_state, n, tt, rd, state, tile_i0, tile_nt)) return;
+    {
+        const IeTableView tv = views[state];
+        if (resolve_range<ROUNDS>(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias, rd,
+                                  tiles_per_state, tile_i0, tile_nt))
+            return;
+    }
+    uint32_t bx;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+    tile_geometry<ROUNDS>(bx, tiles_per_state, n, tt, rd, state, tile_i0, tile_nt);
+    const IeTableView tv = views[state];
+    uint32_t lo = 0, len = (tile_nt + 1) / 2;
+    while (lo < tile_nt) {
+        __syncthreads();  // the next range re-initialises the shared tile state
+        const uint32_t cur = min(len, tile_nt - lo);
+        if (resolve_range<ROUNDS>(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias, rd,
+                                  tiles_per_state, tile_i0 + lo, cur))
+            lo += cur;
+        else
+            len = (cur + 1) / 2;
+    }
 }
 
 }  // namespace

@@ -311,8 +311,9 @@ def test_edge_shapes(eng, oracle):
 
 def test_dense_templates_stay_on_the_tile_path(eng, oracle):
     """Templates with many groups each: the tile size follows the group density (host calls sample the text, device calls
-    take ie_limits.avg_template_groups), so the tiles' event / segment tables do not overflow onto the per-thread path.
-    Parity either way; the timing bound only catches the 10x cliff."""
+    take ie_limits.avg_template_groups), so the tiles' event / segment tables do not overflow.  Without the hint the
+    128-template tiles do overflow and the kernel retries them in halves.  Parity either way; the timing bound only
+    catches the cliff that the per-thread path used to be (7x)."""
     state = workloads.c4_state()
     rng = np.random.default_rng(5)
     n = 20000
@@ -324,7 +325,7 @@ def test_dense_templates_stay_on_the_tile_path(eng, oracle):
     lens = (offs[1:] - offs[:-1]).astype(np.uint32)
     assert np.array_equal(got.status_raw & 0xFF, status & 0xFF) and np.array_equal(got.lens, lens)
     assert oracle.first_mismatch(got.out, got.offs, out, offs[:-1], lens) is None
-    # device call: without the hint the 128-template tiles overflow their tables (still exact), with it they do not
+    # device call: without the hint the 128-template tiles overflow their tables and are split in the kernel
     times = {}
     for groups in (0, 14):
         nb = arena.bytes.nbytes
@@ -341,7 +342,42 @@ def test_dense_templates_stay_on_the_tile_path(eng, oracle):
         g_lens = bufs[2].download(np.uint32, n)
         assert np.array_equal(g_lens, lens)
         assert oracle.first_mismatch(bufs[0].download(np.uint8, cap), bufs[1].download(np.uint64, n), out, offs[:-1], lens) is None
-    assert times[14] < times[0], times
+    assert times[0] < 3 * times[14], times
+
+
+def test_overflowing_tiles_are_split_in_the_kernel(eng, oracle):
+    """One tile in 16 is made of templates ten times longer than the batch's mean, so the tile size picked from the mean
+    cannot hold it: the kernel retries such a tile in halves (down to 4 templates, then the per-thread path; a template
+    longer than a whole tile's text lands there).  Byte parity, and results land at the right indices."""
+    state = workloads.c4_state()
+    rng = np.random.default_rng(23)
+    templates = []
+    for i in range(40000):
+        if (i // 128) % 16 == 3:
+            templates.append("".join("long text %d {q-%d} and more filler text here; " % (k, rng.integers(0, 32768)) for k in range(12)))
+        elif i == 5000:
+            templates.append("x" * 40000 + "{q-7}")                     # longer than a tile's whole text table
+        elif i == 5001:
+            templates.append("{q-1}" * 900)                              # more events than a tile's whole event table
+        else:
+            templates.append("short {q-%d} t" % rng.integers(0, 32768))
+    arena = ie.Arena.from_strings(templates)
+    table = eng.pack(state)
+    out, offs, status, aux = oracle.build_table(state).resolve_batch(arena.bytes, arena.offs, threads=8)
+    lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+    got = eng.resolve_batch(table, arena)
+    assert np.array_equal(got.status_raw & 0xFF, status & 0xFF) and np.array_equal(got.lens, lens)
+    assert oracle.first_mismatch(got.out, got.offs, out, offs[:-1], lens) is None
+    n, nb = arena.n, arena.bytes.nbytes
+    cap = int(lens.sum()) + (1 << 20)
+    d_t, d_o = eng.alloc(nb + 64).upload(arena.bytes), eng.alloc((n + 1) * 8).upload(arena.offs)
+    bufs = (eng.alloc(cap + 16), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
+    eng.resolve_batch_device(table, d_t.ptr, d_o.ptr, n, bufs[0].ptr, cap, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, bufs[4].ptr, bufs[5].ptr,
+                             limits=(0, 0, nb // n, 0, 0))
+    eng.sync()
+    assert np.array_equal(bufs[2].download(np.uint32, n), lens)
+    assert np.array_equal(bufs[3].download(np.int32, n) & 0xFF, status & 0xFF)
+    assert oracle.first_mismatch(bufs[0].download(np.uint8, cap), bufs[1].download(np.uint64, n), out, offs[:-1], lens) is None
 
 
 # ---- rescan rounds: values that hold groups of their own (interp.rs:81-83) ------------------------------------------
