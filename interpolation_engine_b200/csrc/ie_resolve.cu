@@ -247,8 +247,11 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
                 // rendering of the previous result, typed and without rescan (interp.rs:47-51)
                 uint32_t klen = unsentinelise<false>(T + ttop, tcap - ttop, nullptr);
                 const uint8_t* key = kscr;
-                if (klen > kcap) { status = IE_RES_LIMIT; scratch_full = true; }
-                else {
+                if (klen > kcap) {
+                    // the small tier's key buffer is too short: the full-size tier redoes the template
+                    if (retry_list) { retry_list[atomicAdd(retry_count, 1u)] = r; continue; }
+                    status = IE_RES_LIMIT;
+                } else {
                     unsentinelise<true>(T + ttop, tcap - ttop, kscr);
                     for (uint32_t layer = 0; layer < m; ++layer) {
                         payload = key; payload_len = klen;

@@ -1,0 +1,139 @@
+"""Long differential run of the CUDA resolve path against the oracle (a script, not collected by pytest):
+    python tests/fuzz_campaign.py [seconds] [first_seed]
+Every iteration builds one table from a handful of random insert sets and a batch of several thousand templates from the
+brace / escape / sentinel-heavy alphabet of tests/casegen.py — short ones, concatenations of several of them with literals in
+between (so that tiles see long and dense templates next to empty ones), and plain C4-like ones — and compares bytes, status
+and tag of every result through the host-buffer call and through the device-buffer call with 0-3 rescan rounds; the same
+strings then serve as keys of random wildcard sweeps (bitmask against the oracle's matcher) and as input of escape / unescape
+(against the two-pass replace of interp.rs:149,165).
+Prints the first mismatches with the inserts that produced them; exits 1 if there were any."""
+import os, random, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import interpolation_engine_b200 as ie
+from tests import oracle_lib
+from tests.casegen import gen_cases, BS
+from tests.oracle_lib import KIND_TO_CODE
+
+LIMIT = KIND_TO_CODE["limit"]
+
+
+def batch(seed):
+    rng = random.Random(seed)
+    cases = gen_cases(seed * 7919 + 1, rng.choice([300, 1500, 5000]))
+    ins = {}
+    for c_ins, _ in cases[:rng.randint(1, 8)]:
+        ins.update({k: v for k, v in c_ins.items() if not isinstance(v, float)})
+    short = [t for _, t in cases]
+    templates = list(short)
+    for _ in range(len(short) // 3):   # longer / denser templates
+        k = rng.randint(2, 12)
+        glue = rng.choice(["", " ", " lit ", "." + BS + "}", "x" * rng.randint(1, 90)])
+        templates.append(glue.join(rng.choice(short) for _ in range(k)))
+    for _ in range(len(short) // 2):   # the plain shape of the hot path
+        templates.append("text " * rng.randint(0, 12) + "{k%d}" % rng.randint(1, 3) + " and {a-{n1}} " + "{%s}" % rng.choice(list(ins) or ["a"]))
+    templates += ["", "{", "}", BS, "{}", "x" * 5000 + "{a}", "{a}" * 300]
+    rng.shuffle(templates)
+    return ins, templates
+
+
+def compare(label, seed, ins, templates, status_g, lens_g, get_g, tags_g, out, offs, status, aux, bad):
+    for i, t in enumerate(templates):
+        if status[i] == LIMIT:
+            continue
+        w = out[int(offs[i]):int(offs[i + 1])].tobytes()
+        if (status_g[i] & 0xFF) == LIMIT and len(w) > 30000:   # the CUDA path caps a result at 64 KiB, the oracle does not
+            continue
+        ok = (status_g[i] & 0xFF) == (status[i] & 0xFF) and get_g(i) == w
+        if ok and status[i] == ie.RES_TYPED and tags_g is not None:
+            ok = tags_g[i] == aux[i] >> 28
+        if not ok:
+            bad.append((label, seed, t, int(status_g[i]), int(status[i]), get_g(i)[:80], w[:80]))
+            if len(bad) < 6:
+                print("MISMATCH", label, "seed", seed, repr(t)[:200], "gpu", status_g[i] & 0xFF, get_g(i)[:80], "oracle", status[i] & 0xFF, w[:80], flush=True)
+                print("  inserts:", repr(ins)[:1500], flush=True)
+
+
+def two_pass(b, mode):
+    """interp.rs:149 / :165: two sequential non-overlapping replaces."""
+    if mode == 0:
+        return b.replace(b"\\{", b"{").replace(b"\\}", b"}")
+    return b.replace(b"{", b"\\{").replace(b"}", b"\\}")
+
+
+def glob_and_escape(eng, oracle, seed, templates, bad):
+    """The same batch as keys of wildcard sweeps (1-9 random patterns built from pieces of the keys themselves, with up
+    to four '*' runs and pieces around the 32-byte limit of the compiled form) and through escape / unescape."""
+    rng = random.Random(seed ^ 0x5EED)
+    words = ["persona-%d" % rng.randint(0, 30), "/field-%d" % rng.randint(0, 12), "a", "ab", "-", "/", "x" * 31, "y" * 32, "z" * 33, "é", ""]
+    keys = ["".join(rng.choice(words) for _ in range(rng.randint(0, 5))) for _ in range(4000)] + [t for t in templates[:2000] if len(t) < 200]
+    ka = ie.Arena.from_strings(keys)
+    n_cmp = 0
+    for _ in range(6):
+        pats = []
+        for _ in range(rng.randint(0, 9)):
+            pieces = [rng.choice(words + [rng.choice(keys)[:rng.randint(0, 40)]]) for _ in range(rng.randint(1, 5))]
+            pats.append(rng.choice(["", "*"]) + rng.choice(["*", "**", "*"]).join(pieces) + rng.choice(["", "*"]))
+        pa = ie.Arena.from_strings(pats)
+        for invert in (False, True):
+            mask, nd = eng.glob_sweep(ka, pa, invert)
+            want = oracle.glob_sweep(ka.bytes, ka.offs, pa.bytes, pa.offs, invert, threads=4)
+            n_cmp += len(keys)
+            if not np.array_equal(mask, want):
+                bad.append(("glob", seed, pats, invert))
+                if len(bad) < 6:
+                    w = int(np.flatnonzero(mask != want)[0])
+                    bit = int(mask[w] ^ want[w]); k = w * 32 + (bit & -bit).bit_length() - 1
+                    print("MISMATCH glob seed", seed, "invert", invert, "key", repr(keys[k]), "patterns", pats, flush=True)
+    raw = [t.encode() for t in templates]
+    arena = ie.Arena.from_strings(raw)
+    for mode in (0, 1):
+        got = eng.escape_batch(arena, mode).strings()
+        n_cmp += len(raw)
+        for i, g in enumerate(got):
+            if g != two_pass(raw[i], mode):
+                bad.append(("escape", seed, mode, raw[i]))
+                if len(bad) < 6:
+                    print("MISMATCH escape mode", mode, "seed", seed, raw[i][:200], g[:200], flush=True)
+                break
+    return n_cmp
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    eng, oracle = ie.Engine(0), oracle_lib.load()
+    t_end, n_done, bad = time.time() + seconds, 0, []
+    while time.time() < t_end and len(bad) < 20:
+        ins, templates = batch(seed)
+        packed = ie.PackedInserts.from_dict(ins)
+        table = eng.pack(packed, hhmm="12:34", hhmmss="12:34:56")
+        arena = ie.Arena.from_strings(templates)
+        out, offs, status, aux = oracle.build_table(packed).resolve_batch(arena.bytes, arena.offs, threads=8, hhmm="12:34", hhmmss="12:34:56")
+        got = eng.resolve_batch(table, arena, limits=(4096, 1 << 16))
+        compare("host", seed, ins, templates, got.status_raw, got.lens, got.get, got.tags, out, offs, status, aux, bad)
+        # device-buffer call, arenas at odd addresses, every rescan-round setting
+        n, nb = arena.n, arena.bytes.nbytes
+        cap = int((offs[1:] - offs[:-1]).sum()) * 2 + (1 << 20)
+        for rounds in (0, 1, 2, 3):
+            shift = (seed + rounds) % 16
+            d_t = eng.alloc(nb + 64).upload(np.concatenate([np.zeros(shift, np.uint8), arena.bytes]))
+            d_o = eng.alloc((n + 1) * 8).upload(arena.offs)
+            bufs = (eng.alloc(cap + 64), eng.alloc(n * 8), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(n * 4), eng.alloc(64))
+            eng.resolve_batch_device(table, d_t.ptr + shift, d_o.ptr, n, bufs[0].ptr + (shift * 3) % 16, cap, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr,
+                                     bufs[4].ptr, bufs[5].ptr, limits=(4096, 1 << 16, 0, 0, rounds))
+            eng.sync()
+            o = bufs[0].download(np.uint8, cap + 64)[(shift * 3) % 16:]
+            oo, ol, st = bufs[1].download(np.uint64, n), bufs[2].download(np.uint32, n), bufs[3].download(np.int32, n)
+            compare("device r%d" % rounds, seed, ins, templates, st, ol, lambda i: o[int(oo[i]):int(oo[i]) + int(ol[i])].tobytes(), None, out, offs, status,
+                    aux, bad)
+            for b in (d_t, d_o) + bufs:
+                b.free()
+        n_done += len(templates) * 5 + glob_and_escape(eng, oracle, seed, templates, bad)
+        seed += 1
+    print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - (int(sys.argv[2]) if len(sys.argv) > 2 else 1), len(bad)))
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,7 +127,12 @@ def test_edge_cases(eng, oracle):
         "{self}", "s={self}", "{pp}", "p={pp}", "{big}", "b={big}", "{a}" * 300, "lit" * 5000 + "{a}",
         "{missing" + "g" * 300 + "}", "m={missing" + "g" * 300 + "}", "{a}{", "}{a}", "{a}}{", BS * 5 + "{a}",
         "{n}{n}{n}", "é{a}ü", "{é}", "\x00{a}\x00",
+        # one whole group whose resolved key is longer than the small general tier's key buffer (256 B): found by
+        # tests/fuzz_campaign.py seed 1092, the small tier must hand it to the full-size tier, not report a limit
+        "{" + BS + "}{w99}. {w99}lit {w99}.}", "{{w99}{w99}{w99}}", "{x{w99}{w99}{w99}{w99}{w99}}", "{lk-{w99}{w99}{w99}}",
     ]
+    ins["w99"] = "long value " * 9
+    ins["lk-" + "long value " * 27] = "found through a 300-byte key"
     for t in templates:
         got, want = both(eng, oracle, "interpolate_inserts", inserts=ins, content=t, max_iterations=4096)
         assert_same(got, want, t[:80])
