@@ -11,7 +11,7 @@
 #define IE_M_PER 17              // 16-byte chunks of template text per template a tile can hold (chunk-mask table)
 #endif
 #define IE_TILE_TEXT_BYTES (IE_M_PER * IE_RESOLVE_TILE * 16u - 864u)  // longer tiles take the per-thread path
-#define IE_KEY_SCRATCH 4096u  // longest key the general path can look up
+#define IE_KEY_SCRATCH 4096u  // key buffer of the general path's full-size tier (longer keys are restored in place)
 #define IE_GENERAL_WORKERS 2048u       // tier 2 of the general path: full-size scratch (tcap + IE_KEY_SCRATCH each)
 #define IE_GENERAL_SMALL_THREADS 512     // general path: 16 warps per block, one template per warp (tier 1: scratch in shared memory)
 #define IE_GENERAL_SMALL_TEXT 1792u

@@ -190,12 +190,18 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
                 uint32_t idx = ttop;
                 while (idx < tcap && T[idx] != '}') ++idx;
                 if (idx == tcap) { status = IE_RES_PANIC; break; }
-                if (unsentinelise<false>(T + ttop, idx - ttop, nullptr) > kcap) { status = IE_RES_LIMIT; scratch_full = true; break; }
-                const uint32_t klen = unsentinelise<true>(T + ttop, idx - ttop, kscr);
-                payload = kscr; payload_len = klen;
+                // The key text is dead once it has been looked up, and restoring the sentinels never lengthens it: a key
+                // that does not fit the key buffer is restored in place (full-size tier; the small tier hands it on).
+                uint8_t* kbuf = kscr;
+                if (unsentinelise<false>(T + ttop, idx - ttop, nullptr) > kcap) {
+                    if (retry_list) { status = IE_RES_LIMIT; scratch_full = true; break; }
+                    kbuf = T + ttop;
+                }
+                const uint32_t klen = unsentinelise<true>(T + ttop, idx - ttop, kbuf);
+                payload = kbuf; payload_len = klen;
                 if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }
-                const IeSlot* s = ie_lookup(tv, kscr, klen);
-                if (!s) { status = is_arg_key(kscr, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
+                const IeSlot* s = ie_lookup(tv, kbuf, klen);
+                if (!s) { status = is_arg_key(kbuf, klen) ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND; break; }
                 if (!tag_splices(IE_SLOT_TAG(s->vl_tf))) { status = IE_RES_UNSUPPORTED; break; }
                 payload = nullptr; payload_len = 0;
                 ttop = idx + 1; --t_close; --in_open; --f.pos;
@@ -247,12 +253,14 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
                 // rendering of the previous result, typed and without rescan (interp.rs:47-51)
                 uint32_t klen = unsentinelise<false>(T + ttop, tcap - ttop, nullptr);
                 const uint8_t* key = kscr;
-                if (klen > kcap) {
+                if (klen > kcap && retry_list) {
                     // the small tier's key buffer is too short: the full-size tier redoes the template
-                    if (retry_list) { retry_list[atomicAdd(retry_count, 1u)] = r; continue; }
-                    status = IE_RES_LIMIT;
-                } else {
-                    unsentinelise<true>(T + ttop, tcap - ttop, kscr);
+                    retry_list[atomicAdd(retry_count, 1u)] = r;
+                    continue;
+                }
+                {
+                    if (klen > kcap) key = T + ttop;  // restored in place, as above
+                    unsentinelise<true>(T + ttop, tcap - ttop, const_cast<uint8_t*>(key));
                     for (uint32_t layer = 0; layer < m; ++layer) {
                         payload = key; payload_len = klen;
                         if (klen == 0) { status = IE_RES_EMPTY_KEY; break; }

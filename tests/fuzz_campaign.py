@@ -37,6 +37,69 @@ def batch(seed):
     return ins, templates
 
 
+def big_table_batch(seed):
+    """A table of hundreds to tens of thousands of keys (probe sequences, long keys, values at every length class
+    boundary, numbers as chain links, values that refer to lower-numbered keys) and templates over it."""
+    rng = random.Random(seed ^ 0xB16)
+    nk = rng.choice([200, 3000, 20000])
+    lens = [0, 1, 2, 7, 8, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 255, 256, 257, 1000, 4000]
+    ins = {}
+    long_keys = []
+    for i in range(nk):
+        r = rng.random()
+        if r < 0.35:
+            ins["k%d" % i] = ("v%d " % i) + "abcdefghij"[: rng.randint(0, 10)] * rng.randint(0, 3)
+        elif r < 0.50:
+            ins["k%d" % i] = "x" * rng.choice(lens)
+        elif r < 0.65:
+            ins["n%d" % i] = rng.randint(0, nk - 1)                      # chain link: {k{n<i>}}
+        elif r < 0.75 and i > 4:
+            j, j2 = rng.randint(0, i - 1), rng.randint(0, i - 1)           # rescans, always towards lower numbers
+            ins["k%d" % i] = rng.choice(["{k%d}", "see {k%d}.", "{k%d}{k%d}", "a {k{n%d}} b", BS + "{{k%d}" + BS + "}", "{k%d}" + BS])\
+                .replace("%d", str(j), 1).replace("%d", str(j2))
+        elif r < 0.80:
+            lk = "pre-%d-" % i + "y" * rng.choice([20, 60, 100, 250, 300])
+            ins[lk] = "long key %d" % i
+            long_keys.append(lk)
+        elif r < 0.85:
+            ins["k%d" % i] = rng.choice([True, False, None, [1, "a", [2]], {"o": i}, [], 0, -i, 10 ** 15 + i])
+        elif r < 0.90:
+            ins["k%d" % i] = "".join(rng.choice(["{", "}", BS, ".", "a", "〠"]) for _ in range(rng.randint(1, 8)))
+        else:
+            ins["pre-%d-suf" % i] = "p%d" % i
+    keys = list(ins)
+    ids = {p: [int(k[len(p):]) for k in keys if k.startswith(p) and k[len(p):].isdigit()] or [0] for p in ("k", "n")}
+    # chain links mostly land on keys that exist
+    for k in keys:
+        if k.startswith("n") and rng.random() < 0.8:
+            ins[k] = rng.choice(ids["k"])
+            if rng.random() < 0.7:
+                ins["pre-%d-suf" % ins[k]] = "P%d" % ins[k]
+    templates = []
+    for _ in range(rng.choice([2000, 8000])):
+        parts = []
+        for _ in range(rng.randint(0, 7)):
+            r = rng.random()
+            miss = rng.random() < 0.03
+            i = rng.randint(0, nk - 1) if miss else rng.choice(ids["k"])
+            if r < 0.25:   parts.append("{k%d}" % i)
+            if not miss: i = rng.choice(ids["n"])
+            if r < 0.25:   pass
+            elif r < 0.40: parts.append("{k{n%d}}" % i)
+            elif r < 0.50: parts.append("{pre-{n%d}-suf}" % i)
+            elif r < 0.58: parts.append("{%s}" % rng.choice(keys))
+            elif r < 0.62 and long_keys: parts.append("{%s}" % rng.choice(long_keys))
+            elif r < 0.63: parts.append("{k{k{n%d}}}" % i)
+            elif r < 0.70: parts.append(BS + "{lit" + BS + "}")
+            elif r < 0.72: parts.append(rng.choice(["{", "}", "{}", BS, "." + BS + "}"]))
+            else:          parts.append("literal text "[: rng.randint(0, 13)] * rng.randint(0, 6))
+        t = "".join(parts)
+        if rng.random() < 0.08:
+            t = "{" + t + "}"
+        templates.append(t)
+    return ins, templates
+
+
 def compare(label, seed, ins, templates, status_g, lens_g, get_g, tags_g, out, offs, status, aux, bad):
     for i, t in enumerate(templates):
         if status[i] == LIMIT:
@@ -51,7 +114,7 @@ def compare(label, seed, ins, templates, status_g, lens_g, get_g, tags_g, out, o
             bad.append((label, seed, t, int(status_g[i]), int(status[i]), get_g(i)[:80], w[:80]))
             if len(bad) < 6:
                 print("MISMATCH", label, "seed", seed, repr(t)[:200], "gpu", status_g[i] & 0xFF, get_g(i)[:80], "oracle", status[i] & 0xFF, w[:80], flush=True)
-                print("  inserts:", repr(ins)[:1500], flush=True)
+                print("  inserts:", repr(ins)[:300], "... (%d keys; rebuild with the seed)" % len(ins), flush=True)
 
 
 def two_pass(b, mode):
@@ -105,7 +168,7 @@ def main():
     eng, oracle = ie.Engine(0), oracle_lib.load()
     t_end, n_done, bad = time.time() + seconds, 0, []
     while time.time() < t_end and len(bad) < 20:
-        ins, templates = batch(seed)
+        ins, templates = batch(seed) if seed % 3 else big_table_batch(seed)
         packed = ie.PackedInserts.from_dict(ins)
         table = eng.pack(packed, hhmm="12:34", hhmmss="12:34:56")
         arena = ie.Arena.from_strings(templates)

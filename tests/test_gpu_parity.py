@@ -130,8 +130,12 @@ def test_edge_cases(eng, oracle):
         # one whole group whose resolved key is longer than the small general tier's key buffer (256 B): found by
         # tests/fuzz_campaign.py seed 1092, the small tier must hand it to the full-size tier, not report a limit
         "{" + BS + "}{w99}. {w99}lit {w99}.}", "{{w99}{w99}{w99}}", "{x{w99}{w99}{w99}{w99}{w99}}", "{lk-{w99}{w99}{w99}}",
+        # ... and longer than the full-size tier's 4 KiB key buffer (restored in place): fuzz seeds 9000 / 9006
+        "{{w3k}{w3k}}", "z{{w3k}{w3k}}", "{{w3k}" + BS + "}{w3k}}", "{lk3-{w3k}{w3k}}",
     ]
     ins["w99"] = "long value " * 9
+    ins["w3k"] = "y" * 3000
+    ins["lk3-" + "y" * 6000] = "found through a 6 KB key"
     ins["lk-" + "long value " * 27] = "found through a 300-byte key"
     for t in templates:
         got, want = both(eng, oracle, "interpolate_inserts", inserts=ins, content=t, max_iterations=4096)
