@@ -5,7 +5,8 @@ brace / escape / sentinel-heavy alphabet of tests/casegen.py — short ones, con
 between (so that tiles see long and dense templates next to empty ones), and plain C4-like ones — and compares bytes, status
 and tag of every result through the host-buffer call and through the device-buffer call with 0-3 rescan rounds; the same
 strings then serve as keys of random wildcard sweeps (bitmask against the oracle's matcher) and as input of escape / unescape
-(against the two-pass replace of interp.rs:149,165).
+(against the two-pass replace of interp.rs:149,165), and a slice of the batch is resolved against many perturbed snapshots
+of the table in one launch (ie_table_pack_many).
 Prints the first mismatches with the inserts that produced them; exits 1 if there were any."""
 import os, random, sys, time
 import numpy as np
@@ -162,6 +163,37 @@ def glob_and_escape(eng, oracle, seed, templates, bad):
     return n_cmp
 
 
+def many_states(eng, oracle, seed, ins, templates, bad):
+    """ie_table_pack_many: S perturbed copies of the table (keys dropped, values swapped or replaced), a slice of the batch
+    resolved against every one of them in one launch; result s * n + j against the oracle's table for state s.  With few
+    templates per state this is the 32-template tile build of the kernel."""
+    rng = random.Random(seed ^ 0x57A7E)
+    keys = list(ins)
+    n_states = rng.choice([2, 5, 33, 200])
+    sub = templates[:rng.choice([3, 32, 33, 150, 700])]
+    states = []
+    for _ in range(n_states):
+        st = dict(ins)
+        for k in rng.sample(keys, min(len(keys), rng.randint(0, 6))):
+            r = rng.random()
+            if r < 0.3: del st[k]
+            elif r < 0.6: st[k] = ins[rng.choice(keys)]
+            else: st[k] = rng.choice(["", "other", "{%s}" % rng.choice(keys), 42, None, ["l", 1]])
+        states.append(st)
+    if rng.random() < 0.3:
+        states[rng.randrange(n_states)] = {}
+    packs = [ie.PackedInserts.from_dict(st) for st in states]
+    table = eng.pack_many(packs, hhmm="12:34", hhmmss="12:34:56")
+    arena = ie.Arena.from_strings(sub)
+    got = eng.resolve_batch(table, arena, limits=(4096, 1 << 16))
+    n = arena.n
+    for si, pk in enumerate(packs):
+        out, offs, status, aux = oracle.build_table(pk).resolve_batch(arena.bytes, arena.offs, threads=4, hhmm="12:34", hhmmss="12:34:56")
+        compare("states[%d/%d]" % (si, n_states), seed, states[si], sub, got.status_raw[si * n:(si + 1) * n], None,
+                lambda j: got.get(si * n + j), got.tags[si * n:(si + 1) * n], out, offs, status, aux, bad)
+    return n * n_states
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -193,6 +225,7 @@ def main():
             for b in (d_t, d_o) + bufs:
                 b.free()
         n_done += len(templates) * 5 + glob_and_escape(eng, oracle, seed, templates, bad)
+        n_done += many_states(eng, oracle, seed, ins, templates, bad)
         seed += 1
     print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - (int(sys.argv[2]) if len(sys.argv) > 2 else 1), len(bad)))
     sys.exit(1 if bad else 0)
