@@ -188,7 +188,7 @@ ie_status_t ie_engine_create(int device, ie_engine** out) {
     if (err == cudaSuccess) {  // the pool keeps what small tables release instead of returning it to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = 64ull << 20;
+            uint64_t keep = 256ull << 20;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
@@ -242,10 +242,14 @@ static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uin
     // Small tables (one snapshot of an interactive run) come from the device's stream-ordered pool and are uploaded
     // with ONE copy and no host synchronisation: a pageable cudaMemcpyAsync returns once the bytes are staged, and
     // everything that uses the table is ordered behind it (same stream, or the `ready` event).
-    const bool small = S == 1 && total <= (1u << 20);
-    cudaError_t err = small ? cudaMallocAsync(&t->d_base, total, e->stream) : cudaMalloc(&t->d_base, total);
+    // Mid-size tables (a few thousand to 64 k inserts) also come from the pool - a cudaMalloc / cudaFree pair costs about
+    // 10 ms per snapshot, which a caller that repacks per task (replace_map: inserts + captures) pays every iteration -
+    // but keep their own two copies instead of a second host image.
+    const bool pooled = S == 1 && total <= (48u << 20);
+    const bool small = pooled && total <= (1u << 20);
+    cudaError_t err = pooled ? cudaMallocAsync(&t->d_base, total, e->stream) : cudaMalloc(&t->d_base, total);
     if (err != cudaSuccess) { delete t; return cuda_fail(err, who); }
-    t->pooled = small;
+    t->pooled = pooled;
     std::vector<IeTableView> views(S);
     for (size_t s = 0; s < S; ++s) {
         views[s].base = (const uint8_t*)t->d_base + at[s];
@@ -261,11 +265,11 @@ static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uin
     } else {               // one large snapshot: no second host copy of its image
         err = cudaMemcpyAsync(t->d_base, images[0].data(), images[0].size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, views.data(), sizeof(IeTableView), cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err == cudaSuccess && !pooled) err = cudaStreamSynchronize(e->stream);
     }
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventRecord(t->ready, e->stream);
-    if (err != cudaSuccess) { if (small) cudaFreeAsync(t->d_base, e->stream); else cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
+    if (err != cudaSuccess) { if (pooled) cudaFreeAsync(t->d_base, e->stream); else cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
     t->view = views[0];
     t->d_views = (const IeTableView*)((uint8_t*)t->d_base + views_at);
     *out = t;

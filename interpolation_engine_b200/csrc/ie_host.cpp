@@ -19,6 +19,7 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 
@@ -651,8 +652,9 @@ std::vector<MapEntry> map_entries(const JVal& maps) {
 // runtime.rs:1658-1692.  Per iteration: ONE resolve batch (the text and every map key), one first-match sweep,
 // and — for the entry that matched — one resolve of its value against inserts + captures.
 std::string replace_str(ie_engine* e, const JVal& args, Session& s, std::string text, const std::vector<MapEntry>& maps, bool repeat) {
+    std::set<std::string> seen;  // a text that comes back can only repeat its cycle: the reference would not terminate
     for (int guard = 0;; ++guard) {
-        if (guard > 10000) throw ApiError{IE_RES_LIMIT, message_for(IE_RES_LIMIT, ""), ""};  // the reference would not terminate
+        if (guard > 10000 || !seen.insert(text).second) throw ApiError{IE_RES_LIMIT, message_for(IE_RES_LIMIT, ""), ""};
         std::vector<std::string> batch{text};
         for (auto& m : maps) if (m.is_obj && !m.empty) batch.push_back(m.key);
         const std::vector<Outcome> res = s.resolve(batch);

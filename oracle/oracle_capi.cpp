@@ -37,6 +37,7 @@ Ctx ctx_from(const Value& args) {
     }
     if (const Value* d = field(args, "inserts_dir")) if (d->kind == Value::String) ctx.inserts_dir = d->s;
     if (const Value* m = field(args, "max_iterations")) ctx.max_iterations = (long)m->i;
+    if (const Value* m = field(args, "max_bytes")) ctx.max_bytes = (size_t)m->i;
     return ctx;
 }
 char* dup_out(const std::string& s, size_t* out_len) {

@@ -23,6 +23,7 @@
 #include <fstream>
 #include <functional>
 #include <optional>
+#include <set>
 #include <sstream>
 #include <sys/stat.h>
 
@@ -404,7 +405,7 @@ inline std::optional<Value> find_null_map_value(const Array& maps, const Object&
             if (kv.first.find('{') != std::string::npos) {
                 try {
                     if (value_to_string(interpolate_inserts(inserts, kv.first, ctx)) == "NULL") return kv.second.deep_clone();
-                } catch (const InterpError&) {}
+                } catch (const InterpError& e) { if (e.code == ERR_PANIC) throw; }  // `if let Ok(..)` does not catch the unwrap panic of interp.rs:63-66
             }
         }
     }
@@ -413,8 +414,9 @@ inline std::optional<Value> find_null_map_value(const Array& maps, const Object&
 
 // runtime.rs:1658-1692 (the nested fn replace_str)
 inline std::string replace_str(std::string text, const Array& maps, const Object& inserts, const Ctx& ctx, bool repeat_until_done) {
+    std::set<std::string> seen;  // a text that comes back can only repeat its cycle
     for (long guard = 0;; ++guard) {
-        if (guard > 10000) throw InterpError{ERR_LIMIT, "", "expansion limit exceeded"};  // the reference would spin forever
+        if (guard > 10000 || !seen.insert(text).second) throw InterpError{ERR_LIMIT, "", "expansion limit exceeded"};  // the reference would spin forever
         const std::string current = value_to_string(interpolate_inserts(inserts, text, ctx));
         std::optional<std::string> replaced;
         for (auto& map : maps) {

@@ -6,7 +6,8 @@ between (so that tiles see long and dense templates next to empty ones), and pla
 and tag of every result through the host-buffer call and through the device-buffer call with 0-3 rescan rounds; the same
 strings then serve as keys of random wildcard sweeps (bitmask against the oracle's matcher) and as input of escape / unescape
 (against the two-pass replace of interp.rs:149,165), and a slice of the batch is resolved against many perturbed snapshots
-of the table in one launch (ie_table_pack_many).
+of the table in one launch (ie_table_pack_many); finally the JSON-level mirror of the module API (tree walkers, replace_map,
+goto_map, wildcard_captures, get_interpdata) runs on random values built from the same strings.
 Prints the first mismatches with the inserts that produced them; exits 1 if there were any."""
 import os, random, sys, time
 import numpy as np
@@ -194,6 +195,67 @@ def many_states(eng, oracle, seed, ins, templates, bad):
     return n * n_states
 
 
+CLOCK = {"hhmm": "12:34", "hhmmss": "12:34:56"}
+
+
+def host_mirror(eng, oracle, seed, ins, templates, bad):
+    """The JSON-level mirror of the reference's module API (ie_host.cpp) against the oracle's: tree walkers over random
+    nested values whose keys and strings are templates of the batch, replace_map / goto_map with random wildcard maps."""
+    rng = random.Random(seed ^ 0x40057)
+    ins = {k: v for k, v in list(ins.items())[:400]}
+    short = [t for t in templates if len(t) < 120][:500] or [""]
+
+    def tree(depth):
+        r = rng.random()
+        if depth == 0 or r < 0.45: return rng.choice(short)
+        if r < 0.55: return rng.choice([None, True, 3, -1.5, 10 ** 12])
+        if r < 0.75: return [tree(depth - 1) for _ in range(rng.randint(0, 4))]
+        d = {rng.choice(short): tree(depth - 1) for _ in range(rng.randint(0, 4))}
+        if rng.random() < 0.3:
+            d["cmd"] = rng.choice(["print", "goto_map", "replace_map", "serial", "for", "parallel_race", "parallel_wait", "set"])
+            if rng.random() < 0.7: d["tasks"] = rng.choice([rng.choice(short), [rng.choice(short), 5], "{%s}" % rng.choice(list(ins) or ["a"])])
+        return d
+
+    def check(fn, **kw):
+        t0 = time.time()
+        got = eng.call(fn, clock=CLOCK, **kw)
+        t1 = time.time()
+        # self-referential values make the reference's loop explode; the oracle gives up early and the case is skipped
+        want = oracle.call(fn, clock=CLOCK, max_iterations=600, max_bytes=1 << 17, **{k: v for k, v in kw.items() if k != "max_iterations"})
+        if time.time() - t0 > 2.0:
+            print("SLOW %s seed %d: engine %.1f s, oracle %.1f s: %s" % (fn, seed, t1 - t0, time.time() - t1, repr({k: v for k, v in kw.items() if k != "inserts"})[:400]), flush=True)
+        if want[0] == "err" and want[1]["code"] == LIMIT:
+            return 0
+        ok = got == want
+        if not ok:
+            bad.append((fn, seed, kw))
+            if len(bad) < 6:
+                print("MISMATCH", fn, "seed", seed, repr({k: v for k, v in kw.items() if k != "inserts"})[:600], "\n  gpu   ", repr(got)[:400], "\n  oracle", repr(want)[:400], flush=True)
+        return 1
+
+    n = 0
+    for _ in range(25):
+        v = tree(3)
+        n += check("recursive_interpolate", inserts=ins, value=v)
+        n += check("recursive_escape", value=v)
+        n += check("recursive_unescape", value=v)
+        maps = []
+        for _ in range(rng.randint(0, 5)):
+            k = "".join(rng.choice(["*", "*", rng.choice(short)[:rng.randint(0, 8)], " ", "a", "{%s}" % rng.choice(list(ins) or ["a"])]) for _ in range(rng.randint(0, 4)))
+            val = "".join(rng.choice(["{1}", "{2}", "{3}", " ", "z", rng.choice(short)[:12]]) for _ in range(rng.randint(0, 3)))
+            maps.append({k: val})
+        if rng.random() < 0.3:
+            maps.append({"NULL": rng.choice(["nil", "{1}", ""])})
+        item = rng.choice(short)
+        for rep in (False, True):
+            n += check("replace_map", inserts=ins, item=item, wildcard_maps=maps, repeat_until_done=rep)
+        n += check("goto_map", inserts=ins, text=item, target_maps=[{k: "T" + v} for m in maps for k, v in m.items()])
+        n += check("wildcard_captures", pattern="".join(rng.choice(["*", "a", "b", " ", item[:3]]) for _ in range(rng.randint(0, 6))), text=item)
+        n += check("interpolate_inserts", inserts=ins, content=item, max_iterations=4096)
+        n += check("get_interpdata", inserts=ins, key=rng.choice(list(ins) + ["", "ARG3", "nope", "HH:MM"]))
+    return n
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -226,6 +288,7 @@ def main():
                 b.free()
         n_done += len(templates) * 5 + glob_and_escape(eng, oracle, seed, templates, bad)
         n_done += many_states(eng, oracle, seed, ins, templates, bad)
+        n_done += host_mirror(eng, oracle, seed, ins, templates, bad)
         seed += 1
     print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - (int(sys.argv[2]) if len(sys.argv) > 2 else 1), len(bad)))
     sys.exit(1 if bad else 0)
