@@ -170,7 +170,10 @@ ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint
                                  uint32_t* d_mask, uint64_t* d_n_deleted, void* stream);
 
 /* First-match form for goto_map / replace_map (runtime.rs:1085-1133, 1649-1692: the FIRST wildcard of an
- * ordered list that matches wins): first[k] = index of the first pattern matching key k, 0xFFFFFFFF if none. */
+ * ordered list that matches wins): first[k] = index of the first pattern matching key k, 0xFFFFFFFF if none.
+ * Up to 256 keys (the callers above test ONE text, possibly kilobytes long) run one CTA per key with the patterns
+ * in global memory: any number and length of patterns.  More keys take the sweep kernel and its limits
+ * (IE_MAX_PATTERNS patterns, 3584 bytes of pattern text). */
 ie_status_t ie_glob_first_match(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n,
                                 const uint8_t* pats, const uint64_t* pat_offs, uint32_t n_pat, uint32_t* first);
 

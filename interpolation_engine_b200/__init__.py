@@ -26,6 +26,7 @@ RES_STRING, RES_TYPED, RES_UNEVEN, RES_UNSUPPORTED, RES_EMPTY_KEY, RES_ARG_MISSI
 STATUS_NAMES = {0: "string", 1: "typed", 2: "uneven", 3: "unsupported", 4: "empty", 5: "arg", 6: "not_found",
                 7: "panic", 8: "limit", 9: "io"}
 TAG_NULL, TAG_BOOL, TAG_NUMBER, TAG_STRING, TAG_ARRAY, TAG_OBJECT = range(6)
+AUX_NONE = 0xFFFFFFFF  # IE_AUX_NONE
 
 
 class EngineError(RuntimeError):
@@ -371,6 +372,15 @@ class Engine:
         first = np.zeros(max(ka.n, 1), dtype=np.uint32)
         self._check(self.lib.ie_glob_first_match(self.handle, _ptr(ka.bytes), _ptr(ka.offs), ka.n, _ptr(pa.bytes), _ptr(pa.offs), pa.n, _ptr(first)))
         return first[:ka.n].view(np.int32).copy() if ka.n else np.zeros(0, np.int32)
+
+    def lookup_batch(self, table, keys):
+        """get_interpdata's map probe for a batch of literal keys (interp.rs:118-120): (tags, entries); tag -1 and
+        entry AUX_NONE on a miss, entries n / n + 1 = the clock keys."""
+        ka = keys if isinstance(keys, Arena) else Arena.from_strings(keys)
+        tags = np.full(max(ka.n, 1), -1, dtype=np.int32)
+        entries = np.zeros(max(ka.n, 1), dtype=np.uint32)
+        self._check(self.lib.ie_lookup_batch(self.handle, table.handle, _ptr(ka.bytes), _ptr(ka.offs), ka.n, _ptr(tags), _ptr(entries)))
+        return tags[:ka.n], entries[:ka.n]
 
     def glob_sweep_device(self, d_keys, d_key_offs, n, patterns, invert, d_mask, d_n_deleted, stream=None):
         pa = patterns if isinstance(patterns, Arena) else Arena.from_strings(patterns)

@@ -718,9 +718,34 @@ ie_status_t ie_glob_sweep_device(ie_engine* e, const uint8_t* d_keys, const uint
     return IE_OK;
 }
 
+static const uint64_t kFirstMatchFewKeys = 256;  // up to here ie_glob_first_match runs one CTA per text
+
 ie_status_t ie_glob_first_match(ie_engine* e, const uint8_t* keys, const uint64_t* key_offs, uint64_t n, const uint8_t* pats,
                                 const uint64_t* pat_offs, uint32_t n_pat, uint32_t* first) {
     if (!e || (n && (!key_offs || !first))) return fail(IE_E_INVALID, "ie_glob_first_match: NULL argument");
+    if (n && n <= kFirstMatchFewKeys) {
+        // A handful of texts (replace_map / goto_map test ONE): a CTA per text instead of a thread per key, patterns of
+        // any length and number from global memory.
+        if (n_pat && !pat_offs) return fail(IE_E_INVALID, "ie_glob_first_match: NULL argument");
+        CU(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        const uint64_t bytes = key_offs[n], pbytes = n_pat ? pat_offs[n_pat] : 0;
+        const uint64_t zero = 0;
+        CU(e->d_in.ensure(bytes + 16, s));
+        CU(e->d_in_offs.ensure((n + 1) * 8, s));
+        CU(e->d_mask.ensure(pbytes + 16, s));
+        CU(e->d_misc.ensure(((uint64_t)n_pat + 1) * 8, s));
+        CU(e->d_aux.ensure(n * 4 + 4, s));
+        if (bytes) CU(cudaMemcpyAsync(e->d_in.p, keys, bytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->d_in_offs.p, key_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (pbytes) CU(cudaMemcpyAsync(e->d_mask.p, pats, pbytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->d_misc.p, n_pat ? pat_offs : &zero, ((uint64_t)n_pat + 1) * 8, cudaMemcpyHostToDevice, s));
+        CU(ie_launch_glob_first_long((const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (const uint8_t*)e->d_mask.p,
+                                     (const uint64_t*)e->d_misc.p, n_pat, (uint32_t*)e->d_aux.p, s));
+        CU(cudaMemcpyAsync(first, e->d_aux.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return IE_OK;
+    }
     IeGlobPatterns gp;
     ie_status_t st = pack_patterns(pats, pat_offs, n_pat, 0, &gp);
     if (st != IE_OK) return st;

@@ -270,6 +270,111 @@ void ie_glob_compile(IeGlobPatterns* pats) {
     }
 }
 
+// ---- a few long texts against a list of patterns: one CTA per text --------------------------------------------------
+// replace_map / goto_map (runtime.rs:1649-1731, 1085-1133) test ONE text - an LLM answer of kilobytes - against a dozen
+// patterns and want the first that matches.  One thread per key would walk those kilobytes alone, byte by byte and pattern
+// after pattern; here the CTA works on one (text, pattern) pair together.  A pattern is literal pieces separated by star
+// runs: the text must start with the first piece and end with the last one, and the middle pieces must be found in
+// order, each at its LEFTMOST position behind the previous one (greedy placement decides the language of
+// "^lit(.*)lit...(.*)lit$" exactly).  Prefix / suffix: strided compare + barrier vote; a middle piece: every thread tests
+// four start positions per round, a shared atomicMin picks the leftmost hit.  Patterns come from global memory (no limit
+// on their length or number); one of up to LONG_PAT_STAGE bytes is staged in shared memory first.
+namespace {
+constexpr int LONG_CTA = 256;
+constexpr uint32_t LONG_PAT_STAGE = 4096;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ bool cta_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
+    bool ok = true;
+    for (uint32_t i = threadIdx.x; i < n; i += LONG_CTA) ok &= a[i] == b[i];
+    return __syncthreads_and(ok) != 0;
+}
+
+// leftmost p in [from, last] with key[p, p + ln) == lit, NONE if there is none; uniform arguments, uniform result
+__device__ uint32_t cta_find(const uint8_t* key, const uint8_t* lit, uint32_t ln, uint32_t from, uint32_t last, uint32_t* best) {
+    for (uint64_t base = from; base <= last; base += LONG_CTA * 4) {
+        uint32_t mine = NONE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // ascending per thread: the first hit is this thread's leftmost
+            const uint64_t p = base + (uint64_t)k * LONG_CTA + threadIdx.x;
+            if (mine == NONE && p <= last) {
+                uint32_t j = 0;
+                while (j < ln && key[p + j] == lit[j]) ++j;
+                if (j == ln) mine = (uint32_t)p;
+            }
+        }
+        if (threadIdx.x == 0) *best = NONE;
+        __syncthreads();
+        if (mine != NONE) atomicMin(best, mine);
+        __syncthreads();
+        const uint32_t b = *best;
+        __syncthreads();  // everyone has read it before the next round resets it
+        if (b != NONE) return b;
+    }
+    return NONE;
+}
+
+__device__ bool cta_match(const uint8_t* pat, uint32_t pn, const uint8_t* key, uint32_t len, uint32_t* best) {
+    uint32_t a = 0;
+    while (a < pn && pat[a] != '*') ++a;                 // [0, a) = the piece before the first star
+    if (a == pn) return len == pn && cta_equal(pat, key, pn);
+    uint32_t b = pn;
+    while (pat[b - 1] != '*') --b;                       // [b, pn) = the piece behind the last star
+    const uint32_t suf = pn - b;
+    if ((uint64_t)a + suf > len) return false;
+    if (!cta_equal(pat, key, a)) return false;
+    if (!cta_equal(pat + b, key + (len - suf), suf)) return false;
+    uint32_t pos = a;
+    const uint32_t limit = len - suf;                    // middle pieces live in [pos, limit)
+    uint32_t i = a;
+    while (i < b) {
+        while (i < b && pat[i] == '*') ++i;
+        uint32_t j = i;
+        while (j < b && pat[j] != '*') ++j;
+        const uint32_t ln = j - i;
+        if (ln) {
+            if ((uint64_t)pos + ln > limit) return false;
+            const uint32_t p = cta_find(key, pat + i, ln, pos, limit - ln, best);
+            if (p == NONE) return false;
+            pos = p + ln;
+        }
+        i = j;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(LONG_CTA) ie_glob_first_long_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ offs, uint64_t n,
+                                                                      const uint8_t* __restrict__ pats, const uint64_t* __restrict__ pat_offs,
+                                                                      uint32_t n_pat, uint32_t* __restrict__ first) {
+    __shared__ uint32_t best;
+    __shared__ uint8_t stage[LONG_PAT_STAGE];
+    for (uint64_t k = blockIdx.x; k < n; k += gridDim.x) {
+        const uint8_t* key = keys + offs[k];
+        const uint32_t len = (uint32_t)(offs[k + 1] - offs[k]);
+        uint32_t res = NONE;
+        for (uint32_t q = 0; q < n_pat; ++q) {
+            const uint8_t* pat = pats + pat_offs[q];
+            const uint32_t pn = (uint32_t)(pat_offs[q + 1] - pat_offs[q]);
+            if (pn <= LONG_PAT_STAGE) {
+                __syncthreads();  // the previous pattern is no longer being read
+                for (uint32_t i = threadIdx.x; i < pn; i += LONG_CTA) stage[i] = pat[i];
+                __syncthreads();
+                pat = stage;
+            }
+            if (cta_match(pat, pn, key, len, &best)) { res = q; break; }
+        }
+        if (threadIdx.x == 0) first[k] = res;
+    }
+}
+}  // namespace
+
+cudaError_t ie_launch_glob_first_long(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const uint8_t* d_pats,
+                                      const uint64_t* d_pat_offs, uint32_t n_pat, uint32_t* d_first, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ie_glob_first_long_kernel<<<(unsigned)(n < 1184 ? n : 1184), LONG_CTA, 0, stream>>>(d_keys, d_key_offs, n, d_pats, d_pat_offs, n_pat, d_first);
+    return cudaGetLastError();
+}
+
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
                            uint32_t* d_mask, uint64_t* d_n_deleted, uint32_t* d_first, cudaStream_t stream) {
     cudaError_t err;

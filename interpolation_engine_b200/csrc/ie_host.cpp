@@ -609,27 +609,14 @@ std::vector<std::string> wildcard_captures(const std::string& p, const std::stri
     return caps;
 }
 
-// index of the first pattern that matches `text`, -1 if none: one launch of the glob kernel
+// index of the first pattern that matches `text`, -1 if none: one launch (one CTA works on the text, ie_glob.cu)
 int first_match(ie_engine* e, const std::string& text, const std::vector<std::string>& patterns) {
-    for (size_t p0 = 0; p0 < patterns.size(); p0 += IE_MAX_PATTERNS) {
-        Arena keys, pats;
-        keys.push(text);
-        const size_t np = std::min<size_t>(IE_MAX_PATTERNS, patterns.size() - p0);
-        for (size_t i = 0; i < np; ++i) pats.push(patterns[p0 + i]);
-        uint32_t first = 0xFFFFFFFFu;
-        if (pats.offs[np] > 3584) {  // longer than the kernel's pattern block: one pattern per launch
-            for (size_t i = 0; i < np; ++i) {
-                Arena one;
-                one.push(patterns[p0 + i]);
-                check(ie_glob_first_match(e, keys.data(), keys.offs.data(), 1, one.data(), one.offs.data(), 1, &first));
-                if (first != 0xFFFFFFFFu) return (int)(p0 + i);
-            }
-            continue;
-        }
-        check(ie_glob_first_match(e, keys.data(), keys.offs.data(), 1, pats.data(), pats.offs.data(), (uint32_t)np, &first));
-        if (first != 0xFFFFFFFFu) return (int)(p0 + first);
-    }
-    return -1;
+    Arena keys, pats;
+    keys.push(text);
+    for (auto& p : patterns) pats.push(p);
+    uint32_t first = 0xFFFFFFFFu;
+    check(ie_glob_first_match(e, keys.data(), keys.offs.data(), 1, pats.data(), pats.offs.data(), (uint32_t)patterns.size(), &first));
+    return first == 0xFFFFFFFFu ? -1 : (int)first;
 }
 
 struct MapEntry { bool is_obj = false, empty = true; std::string key, val; };

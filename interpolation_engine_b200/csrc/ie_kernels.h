@@ -147,5 +147,8 @@ struct IeGlobPatterns {  // passed by value as a kernel parameter (about 12 KiB;
 };
 void ie_glob_compile(IeGlobPatterns* pats);  // host: fills fast[] / any_pre / any_suf from bytes / off
 // d_first (may be NULL): [n] index of the first matching pattern, 0xFFFFFFFF when none
+// a few (long) texts, any number / length of patterns in global memory: one CTA per text
+cudaError_t ie_launch_glob_first_long(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const uint8_t* d_pats,
+                                      const uint64_t* d_pat_offs, uint32_t n_pat, uint32_t* d_first, cudaStream_t stream);
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
                            uint32_t* d_mask, uint64_t* d_n_deleted, uint32_t* d_first, cudaStream_t stream);

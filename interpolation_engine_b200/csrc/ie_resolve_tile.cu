@@ -496,7 +496,7 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
 // Resolves the templates [i0, i0 + nt) of one snapshot as one tile.  Returns false (having written nothing) when the
 // range outgrows the tile's tables and holds more than IE_SPLIT_MIN templates: the caller retries it in halves.  A range
 // of at most IE_SPLIT_MIN templates that still does not fit takes the exact per-thread path instead.
-#define IE_SPLIT_MIN 4u
+#define IE_SPLIT_MIN 1u
 template <bool ROUNDS>
 __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, uint32_t state, const uint8_t* __restrict__ tmpl,
                                               const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out, uint64_t out_cap,

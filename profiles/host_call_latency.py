@@ -25,3 +25,10 @@ t("replace_map, same with 5004 inserts", "replace_map", 30, inserts=ins_big, ite
 grow = [{"*": "z{1} "}]
 for n_it in ():
     dt = t("replace_map, repeat_until_done, text grows 2 B per iteration (limit)", "replace_map", 1, inserts=ins, item="s", wildcard_maps=grow, repeat_until_done=True)
+# a text of kilobytes against the 12 replace_map patterns of examples/text_adventure.json5:33-59 (shapes only)
+long_text = ("The guard looks at you. " * 40) + "<q>What brings you here?</q>" + (" He waits." * 150)
+ta_maps = [{"*<%s>*</%s>*" % (t, t): "{1}{3}"} for t in ("think", "aside", "ooc", "meta", "note", "plan")] + \
+          [{"*[[*]]*": "{1}{3}"}, {"* \n*": "{1}\n{2}"}, {"*\n\n\n*": "{1}\n\n{2}"}, {"*  *": "{1} {2}"}, {"\n*": "{1}"}, {"* ": "{1}"}]
+t("replace_map, %d B text, 12 patterns, none matches" % len(long_text), "replace_map", 100, inserts=ins, item=long_text, wildcard_maps=ta_maps[:7], repeat_until_done=False)
+t("replace_map, same text, repeat_until_done (strips 150 double spaces..)", "replace_map", 5, inserts=ins, item=long_text.replace(". He", ".  He"), wildcard_maps=ta_maps, repeat_until_done=True)
+t("goto_map, same text, 12 targets", "goto_map", 100, inserts=ins, text=long_text, target_maps=[{list(m)[0]: "@t%d" % i} for i, m in enumerate(ta_maps[:7])] + [{"*waits.": "@end"}])

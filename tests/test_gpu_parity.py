@@ -162,6 +162,30 @@ def test_clock_keys_and_inserts_dir(eng, oracle, tmp_path):
         assert_same(got, want, key)
 
 
+def test_lookup_batch(eng):
+    """ie_lookup_batch = the map probe of get_interpdata (interp.rs:96-120) for many literal keys at once: the tag and the
+    insert index of every hit, misses, the clock keys shadowing inserts of the same name, keys of every length class."""
+    rng = random.Random(9)
+    ins = {"k%d" % i: rng.choice(["v%d" % i, i, True, None, ["a", i], {"o": i}, ""]) for i in range(20000)}
+    ins.update({"long-" + "y" * n: n for n in (1, 15, 16, 17, 31, 32, 33, 100, 300, 5000)})
+    ins.update({"": "empty key", "é〠": "utf-8", "HH:MM": "shadowed", "a{b}": "braces are just bytes here"})
+    packed = ie.PackedInserts.from_dict(ins)
+    table = eng.pack(packed, **CLOCK)
+    names = sorted(ins, key=lambda k: k.encode("utf-8"))
+    keys = rng.sample(names, 3000) + ["missing-%d" % i for i in range(500)] + ["", "HH:MM", "HH:MM:SS", "k", "k20000", "long-" + "y" * 299, "é"]
+    rng.shuffle(keys)
+    tags, entries = eng.lookup_batch(table, keys)
+    for k, tag, entry in zip(keys, tags, entries):
+        if k == "HH:MM" or k == "HH:MM:SS":
+            assert (tag, entry) == (ie.TAG_STRING, packed.n + (k == "HH:MM:SS")), k     # interp.rs:96-104: the clock wins
+        elif k in ins and k != "":   # "" is an error before the probe (interp.rs:105): the batch reports a miss
+            assert names[entry] == k and tag == packed.tags[entry], (k, tag, entry)
+        else:
+            assert tag == -1 and entry == ie.AUX_NONE, (k, tag, entry)
+    t0, e0 = eng.lookup_batch(table, [])
+    assert len(t0) == 0 and len(e0) == 0
+
+
 # ---- tree walkers ---------------------------------------------------------------------------------
 def test_recursive_interpolate_tasks(eng, oracle):
     ins = dict(APPENDIX_B_INSERTS)
@@ -356,7 +380,7 @@ def test_dense_templates_stay_on_the_tile_path(eng, oracle):
 
 def test_overflowing_tiles_are_split_in_the_kernel(eng, oracle):
     """One tile in 16 is made of templates ten times longer than the batch's mean, so the tile size picked from the mean
-    cannot hold it: the kernel retries such a tile in halves (down to 4 templates, then the per-thread path; a template
+    cannot hold it: the kernel retries such a tile in halves (down to one template, then the per-thread path; a template
     longer than a whole tile's text lands there).  Byte parity, and results land at the right indices."""
     state = workloads.c4_state()
     rng = np.random.default_rng(23)
@@ -482,6 +506,39 @@ def test_replace_map_goto_map_on_gpu(eng, oracle):
         assert got == want, (pat, text, got, want)
     first = eng.glob_first_match(["persona-1/a", "zzz", "", "b"], ["b", "persona-*", "*"])
     assert list(first) == [1, 2, 2, 0]
+
+
+def test_first_match_few_long_texts(eng, oracle):
+    """ie_glob_first_match with up to 256 keys runs one CTA per text (ie_glob_first_long_kernel): kilobyte texts, patterns
+    longer than the sweep kernel's 3584-byte block, more than IE_MAX_PATTERNS patterns, every piece arrangement; against
+    the oracle's wildcard_match pattern by pattern.  Above 256 keys the same call takes the sweep kernel: same answers."""
+    rng = random.Random(31)
+    words = ["<q>", "</q>", "a", "ab", "ba", " ", "\n", "persona-7", "x" * 40, "é", "*"]
+    def text(n):
+        return "".join(rng.choice(words[:-1]) for _ in range(n))
+    texts = ["", "a", "ab", text(3), text(50), text(700), text(5000), "x" * 5000 + "<q>mid</q>" + "y" * 7000, "ab" * 3000 + "b", text(2000) + "END"]
+    texts += [text(rng.randint(0, 30)) for _ in range(60)]
+    pats = ["", "*", "**", "a", "a*", "*a", "*<q>*</q>*", "*<q>*</q>", "<q>*", "*END", "*ab*ba*ab*", "ab*b", "*b*b", "*abb", "x*y", "x*<q>mid</q>*y",
+            "*" + "x" * 40 + "*" + "x" * 40 + "*", "*\n*\n*", "a**b", "***", "*" + "ab" * 2000 + "*", "ab" * 3000 + "b", "ab" * 3000 + "*b", "*persona-7*é*"]
+    pats += [texts[6][10:4000], "*" + texts[6][100:3900] + "*", texts[6][:2000] + "*" + texts[6][3000:], texts[7][:4990] + "*"]   # pieces of ~4 KB
+    pats += ["".join(rng.choice(words) for _ in range(rng.randint(0, 6))) for _ in range(80)]                                # > IE_MAX_PATTERNS in all
+    ka, pa = ie.Arena.from_strings(texts), ie.Arena.from_strings(pats)
+    want = np.full(len(texts), -1, dtype=np.int64)
+    for q in reversed(range(len(pats))):
+        one = ie.Arena.from_strings([pats[q]])
+        m = oracle.glob_sweep(ka.bytes, ka.offs, one.bytes, one.offs, False, threads=2)
+        for k in range(len(texts)):
+            if (int(m[k >> 5]) >> (k & 31)) & 1:
+                want[k] = q
+    got = eng.glob_first_match(ka, pa)
+    assert list(got) == list(want), [(texts[k][:40], pats[got[k]][:40] if got[k] >= 0 else None, pats[want[k]][:40] if want[k] >= 0 else None)
+                                     for k in range(len(texts)) if got[k] != want[k]][:5]
+    # the sweep-kernel route (more than 256 keys) on what fits its limits
+    small = [p for p in pats if len(p.encode()) < 100][:60]
+    many = ie.Arena.from_strings(texts * 5)
+    got_many = eng.glob_first_match(many, ie.Arena.from_strings(small))
+    got_few = eng.glob_first_match(ka, ie.Arena.from_strings(small))
+    assert list(got_many) == list(got_few) * 5
 
 
 def test_program_loader_host_vs_oracle(eng, oracle):
