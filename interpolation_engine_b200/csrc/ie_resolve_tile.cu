@@ -497,11 +497,6 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
 // range outgrows the tile's tables and holds more than IE_SPLIT_MIN templates: the caller retries it in halves.  A range
 // of at most IE_SPLIT_MIN templates that still does not fit takes the exact per-thread path instead.
 #define IE_SPLIT_MIN 1u
-#ifdef IE_EXPECT
-#define IE_RARE(x) __builtin_expect(!!(x), 0)
-#else
-#define IE_RARE(x) (x)
-#endif
 template <bool ROUNDS>
 __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, uint32_t state, const uint8_t* __restrict__ tmpl,
                                               const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out, uint64_t out_cap,
@@ -535,7 +530,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     const uint32_t tile_bytes = (uint32_t)tile_bytes64;
     const uint32_t n_chunks = (lead + tile_bytes + 15) >> 4;
     const bool too_big = tile_bytes64 + 32 > (uint64_t)M_CAP * 16;  // does not fit the chunk-mask table
-    if (IE_RARE(too_big && nt > IE_SPLIT_MIN)) return false;  // the caller retries with half as many templates
+    if (too_big && nt > IE_SPLIT_MIN) return false;  // the caller retries with half as many templates
 
     // ---- P1: flat brace scan --------------------------------------------------------------------
     // Loads are issued P1_BATCH chunks ahead of the compares so that a thread keeps several HBM
@@ -687,8 +682,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     __syncthreads();
     PHASE_MARK(4);
 
-    if (IE_RARE(sm.overflow && nt > IE_SPLIT_MIN)) return false;  // more brace events than the tile's tables hold: half as many templates
-    if (IE_RARE(too_big || sm.overflow)) {
+    if (sm.overflow && nt > IE_SPLIT_MIN) return false;  // more brace events than the tile's tables hold: half as many templates
+    if (too_big || sm.overflow) {
         // ---- per-thread exact path for tiles that do not fit the tile tables -----------------------
         uint32_t len = 0, m0 = 0, olen = 0, status = IE_RES_STRING, aux = 0;
         bool verbatim = false;
