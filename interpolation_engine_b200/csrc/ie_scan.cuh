@@ -1,6 +1,7 @@
-// CTA-level exclusive scan of per-thread output lengths plus a decoupled look-back across CTA
-// tiles (single pass, Merrill & Garland style): every variable-length kernel in this engine
-// (resolve, escape) writes a compacted arena in input order without a second pass over HBM.
+// CTA-level exclusive scan of per-thread output lengths, and the two ways a tile finds its place in a compacted
+// arena without a second pass over HBM: a decoupled look-back across ordered tiles (Merrill & Garland style; the escape
+// kernel, whose output must stay in input order) or one atomic claim per tile (the resolve kernel: results carry their
+// own offsets, so tile order in the arena is free).
 #pragma once
 #include <cstdint>
 
@@ -35,91 +36,7 @@ __device__ __forceinline__ uint32_t acquire_tile(TileSmemT<NT>& sm, uint32_t* ti
     return sm.tile;
 }
 
-// Returns the global exclusive prefix of `len` for this thread; *tile_end is the inclusive prefix
-// at the end of this tile and *tile_begin the exclusive prefix at its start (valid on every
-// thread).  Must be called by all NT threads of the CTA.
-template <int NT>
-__device__ __forceinline__ uint64_t exclusive_prefix(TileSmemT<NT>& sm, uint64_t* tile_state, uint32_t tile, uint64_t len,
-                                                     uint64_t* tile_end, uint64_t* tile_begin = nullptr) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t incl = len;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if ((int)lane >= d) incl += y;
-    }
-    if (lane == 31) sm.warp_tot[warp] = incl;
-    __syncthreads();
-    uint64_t warp_off = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) {
-        const uint64_t x = sm.warp_tot[w];
-        if (w < (int)warp) warp_off += x;
-        tile_total += x;
-    }
-    if (warp == 0) {
-        uint64_t base = 0;
-        if (tile == 0) {
-            if (lane == 0) st_state(tile_state, FLAG_INC | tile_total);
-        } else {
-            if (lane == 0) st_state(tile_state + tile, FLAG_AGG | tile_total);
-            int64_t j = (int64_t)tile - 1;
-            for (;;) {
-                const int64_t idx = j - (int64_t)lane;
-                uint64_t sv = FLAG_INC;  // before tile 0: inclusive prefix 0
-                if (idx >= 0) {
-                    sv = ld_state(tile_state + idx);
-                    while ((sv >> 62) == 0) { __nanosleep(40); sv = ld_state(tile_state + idx); }
-                }
-                const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (sv >> 62) == 2);
-                const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-                uint64_t v = ((int)lane <= first) ? (sv & VAL_MASK) : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                base += v;
-                if (inc_mask) break;
-                j -= 32;
-            }
-            if (lane == 0) st_state(tile_state + tile, FLAG_INC | (base + tile_total));
-        }
-        if (lane == 0) sm.base = base;
-    }
-    __syncthreads();
-    *tile_end = sm.base + tile_total;
-    if (tile_begin) *tile_begin = sm.base;
-    return sm.base + warp_off + incl - len;
-}
-
-// Split form of exclusive_prefix: publish() makes this tile's (rounded) total visible to its successors
-// as early as possible and returns the thread's tile-local exclusive prefix; lookback() later collects
-// the totals of all predecessors.  Tile-local work placed between the two calls gives predecessors
-// time to publish, so the look-back rarely waits.  Both must be called by all NT threads.
-template <int NT>
-__device__ __forceinline__ uint64_t publish(TileSmemT<NT>& sm, uint64_t* tile_state, uint32_t tile, uint64_t len, uint64_t round_mask,
-                                            uint64_t* tile_total_rounded, uint64_t* tile_total_raw = nullptr) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t incl = len;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if ((int)lane >= d) incl += y;
-    }
-    if (lane == 31) sm.warp_tot[warp] = incl;
-    __syncthreads();
-    uint64_t warp_off = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) {
-        const uint64_t x = sm.warp_tot[w];
-        if (w < (int)warp) warp_off += x;
-        tile_total += x;
-    }
-    if (tile_total_raw) *tile_total_raw = tile_total;
-    tile_total = (tile_total + round_mask) & ~round_mask;
-    if (threadIdx.x == 0) st_state(tile_state + tile, (tile == 0 ? FLAG_INC : FLAG_AGG) | tile_total);
-    *tile_total_rounded = tile_total;
-    return warp_off + incl - len;
-}
-// Tile-local half of publish() for kernels that do not order their tiles: the thread's exclusive prefix
+// For kernels that do not order their tiles: the thread's exclusive prefix
 // within the tile, the tile total rounded up to round_mask + 1 and (optionally) the exact total.
 template <int NT>
 __device__ __forceinline__ uint64_t local_scan(TileSmemT<NT>& sm, uint64_t len, uint64_t round_mask, uint64_t* tile_total_rounded,
@@ -209,37 +126,6 @@ __device__ __forceinline__ uint64_t lookback_wide(TileSmemT<NT>& sm, uint64_t* t
                 j -= 32 * LB;
             }
             if (lane == 0) st_state(tile_state + tile, FLAG_INC | (base + tile_total));
-        }
-        if (lane == 0) sm.base = base;
-    }
-    __syncthreads();
-    return sm.base;
-}
-
-template <int NT>
-__device__ __forceinline__ uint64_t lookback(TileSmemT<NT>& sm, uint64_t* tile_state, uint32_t tile, uint64_t tile_total_rounded) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) {
-        uint64_t base = 0;
-        if (tile != 0) {
-            int64_t j = (int64_t)tile - 1;
-            for (;;) {
-                const int64_t idx = j - (int64_t)lane;
-                uint64_t sv = FLAG_INC;  // before tile 0: inclusive prefix 0
-                if (idx >= 0) {
-                    sv = ld_state(tile_state + idx);
-                    while ((sv >> 62) == 0) { __nanosleep(40); sv = ld_state(tile_state + idx); }
-                }
-                const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (sv >> 62) == 2);
-                const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-                uint64_t v = ((int)lane <= first) ? (sv & VAL_MASK) : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                base += v;
-                if (inc_mask) break;
-                j -= 32;
-            }
-            if (lane == 0) st_state(tile_state + tile, FLAG_INC | (base + tile_total_rounded));
         }
         if (lane == 0) sm.base = base;
     }
