@@ -448,7 +448,12 @@ void gather(const JVal& v, Gather& g) {
 struct Rebuild {
     const std::vector<Outcome>& res;
     const std::vector<JVal>& looked;
+    const std::vector<std::shared_ptr<ApiError>>& look_errs;  // raised where the traversal reaches the lookup (:217, :224 `?`)
     size_t ti = 0, li = 0;
+    JVal lookup_result() {
+        if (look_errs[li]) throw *look_errs[li];
+        return looked[li++];
+    }
     JVal string_result(const std::string& original) {
         const Outcome& oc = res[ti++];
         if (oc.code == IE_RES_STRING) return JVal::str(oc.bytes);
@@ -466,10 +471,10 @@ struct Rebuild {
                 JObj o = *v.o;
                 auto t = o.find("tasks");
                 if (t != o.end()) {
-                    if (t->second.t == JVal::Str) { if (simple_insertkey(t->second.s, nullptr)) t->second = looked[li++]; }
+                    if (t->second.t == JVal::Str) { if (simple_insertkey(t->second.s, nullptr)) t->second = lookup_result(); }
                     else if (t->second.t == JVal::Arr) {
                         JArr a = *t->second.a;
-                        for (auto& x : a) if (x.t == JVal::Str && simple_insertkey(x.s, nullptr)) x = looked[li++];
+                        for (auto& x : a) if (x.t == JVal::Str && simple_insertkey(x.s, nullptr)) x = lookup_result();
                         t->second = JVal::arr(std::move(a));
                     }
                 }
@@ -487,8 +492,12 @@ struct Rebuild {
 };
 
 // get_interpdata (interp.rs:91-137) for literal keys through the device table
-std::vector<JVal> lookup_keys(Session& s, const std::vector<std::string>& keys) {
+// `errs` (optional): a failed lookup is recorded there instead of thrown, so that the caller can raise it where the
+// reference would have reached it (recursive_interpolate evaluates strings and lookups in one traversal order).
+std::vector<JVal> lookup_keys(Session& s, const std::vector<std::string>& keys, std::vector<std::shared_ptr<ApiError>>* errs = nullptr) {
     std::vector<JVal> out(keys.size());
+    if (errs) errs->assign(keys.size(), nullptr);
+    auto failed = [&](size_t i, ApiError er) { if (!errs) throw er; (*errs)[i] = std::make_shared<ApiError>(std::move(er)); };
     if (keys.empty()) return out;
     if (!s.table) s.pack();
     for (int round = 0; round < 64; ++round) {
@@ -500,13 +509,13 @@ std::vector<JVal> lookup_keys(Session& s, const std::vector<std::string>& keys) 
         bool grew = false;
         for (size_t i = 0; i < keys.size(); ++i) {
             const std::string& k = keys[i];
-            if (tag[i] >= 0) { out[i] = s.entry_value(entry[i]); continue; }
-            if (k.empty()) throw ApiError{IE_RES_EMPTY_KEY, message_for(IE_RES_EMPTY_KEY, ""), ""};
-            if (is_arg_key(k)) throw ApiError{IE_RES_ARG_MISSING, message_for(IE_RES_ARG_MISSING, k), k};
+            if (tag[i] >= 0) { out[i] = s.entry_value(entry[i]); if (errs) (*errs)[i] = nullptr; continue; }
+            if (k.empty()) { failed(i, ApiError{IE_RES_EMPTY_KEY, message_for(IE_RES_EMPTY_KEY, ""), ""}); continue; }
+            if (is_arg_key(k)) { failed(i, ApiError{IE_RES_ARG_MISSING, message_for(IE_RES_ARG_MISSING, k), k}); continue; }
             if (s.has_dir && s.probe_dir(k)) { grew = true; continue; }
             auto de = s.dir_errors.find(k);
-            if (de != s.dir_errors.end()) throw ApiError{9, de->second, k};
-            throw ApiError{IE_RES_NOT_FOUND, message_for(IE_RES_NOT_FOUND, k), k};
+            if (de != s.dir_errors.end()) { failed(i, ApiError{9, de->second, k}); continue; }
+            failed(i, ApiError{IE_RES_NOT_FOUND, message_for(IE_RES_NOT_FOUND, k), k});
         }
         if (!grew) break;
         s.pack();
@@ -883,9 +892,10 @@ JVal dispatch(ie_engine* e, const JVal& args) {
         const JVal& v = arg(args, "value");
         Gather g;
         gather(v, g);
-        const std::vector<JVal> looked = lookup_keys(s, g.lookups);
+        std::vector<std::shared_ptr<ApiError>> look_errs;
+        const std::vector<JVal> looked = lookup_keys(s, g.lookups, &look_errs);
         const std::vector<Outcome> res = s.resolve(g.templates);
-        Rebuild rb{res, looked};
+        Rebuild rb{res, looked, look_errs};
         return rb.walk(v);
     }
     if (fn == "recursive_escape") return escape_tree(e, 1, arg(args, "value"));      // interp.rs:163

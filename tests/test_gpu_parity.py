@@ -199,6 +199,11 @@ def test_recursive_interpolate_tasks(eng, oracle):
         {"cmd": "set", "item": "{b}", "output_name": "{u}"},
         "{question-{i}}", ["{x}", "-{x}-", "{{x}}"], 7, None, {"a{i}": 1, "a3": 2},
         {"cmd": "math", "input": "max(1,2,{result})", "output_name": "result", "line": 8},
+        # one traversal order for strings and `tasks` lookups (fuzz seed 60008): the key "}bad{" panics (no '}' behind the
+        # last '{') BEFORE its value's failing lookup is reached; with the keys the other way round the lookup error wins
+        {"}bad{": {"cmd": "for", "tasks": "{no-such-key}"}},
+        {"a": {"cmd": "for", "tasks": ["{lst}", "{no-such-key}"]}, "}z{": 1},
+        {"a": {"cmd": "serial", "tasks": "{lst}"}, "b{missing}": "{name}", "c": {"cmd": "parallel_wait", "tasks": "{ARG9}"}},
     ]
     for task in tasks:
         got, want = both(eng, oracle, "recursive_interpolate", inserts=ins, value=task)
