@@ -114,6 +114,10 @@ ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const u
 ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys,
                                const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
                                const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out);
+/* A table must outlive the work that reads it: the host-buffer calls are synchronous, but after a *_device call on a
+ * caller's stream free the table only once that stream has passed the call (stream synchronise or an event): tables
+ * up to 48 MiB live in the device's stream-ordered pool and are released in the order of the ENGINE's stream, which
+ * does not see work queued elsewhere. */
 void ie_table_free(ie_table* t);
 uint64_t ie_table_device_bytes(const ie_table* t);
 uint32_t ie_table_states(const ie_table* t); /* snapshots held (1 for ie_table_pack) */
