@@ -1,5 +1,5 @@
 """Long differential run of the CUDA resolve path against the oracle (a script, not collected by pytest):
-    python tests/fuzz_campaign.py [seconds] [first_seed]
+    python tests/fuzz_campaign.py [seconds] [first_seed] [--mirror-only]
 Every iteration builds one table from a handful of random insert sets and a batch of several thousand templates from the
 brace / escape / sentinel-heavy alphabet of tests/casegen.py — short ones, concatenations of several of them with literals in
 between (so that tiles see long and dense templates next to empty ones), and plain C4-like ones — and compares bytes, status
@@ -198,7 +198,7 @@ def many_states(eng, oracle, seed, ins, templates, bad):
 CLOCK = {"hhmm": "12:34", "hhmmss": "12:34:56"}
 
 
-def host_mirror(eng, oracle, seed, ins, templates, bad):
+def host_mirror(eng, oracle, seed, ins, templates, bad, rounds=25):
     """The JSON-level mirror of the reference's module API (ie_host.cpp) against the oracle's: tree walkers over random
     nested values whose keys and strings are templates of the batch, replace_map / goto_map with random wildcard maps."""
     rng = random.Random(seed ^ 0x40057)
@@ -235,7 +235,7 @@ def host_mirror(eng, oracle, seed, ins, templates, bad):
         return 1
 
     n = 0
-    for _ in range(25):
+    for _ in range(rounds):
         v = tree(3)
         n += check("recursive_interpolate", inserts=ins, value=v)
         n += check("recursive_escape", value=v)
@@ -258,12 +258,18 @@ def host_mirror(eng, oracle, seed, ins, templates, bad):
 
 
 def main():
-    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    seconds = float(argv[0]) if argv else 60.0
+    seed = first_seed = int(argv[1]) if len(argv) > 1 else 1
     eng, oracle = ie.Engine(0), oracle_lib.load()
     t_end, n_done, bad = time.time() + seconds, 0, []
+    mirror_only = "--mirror-only" in sys.argv   # only the JSON-level leg (cheap per check: for volume there)
     while time.time() < t_end and len(bad) < 20:
         ins, templates = batch(seed) if seed % 3 else big_table_batch(seed)
+        if mirror_only:
+            n_done += host_mirror(eng, oracle, seed, ins, templates, bad, rounds=200)
+            seed += 1
+            continue
         packed = ie.PackedInserts.from_dict(ins)
         table = eng.pack(packed, hhmm="12:34", hhmmss="12:34:56")
         arena = ie.Arena.from_strings(templates)
@@ -291,7 +297,7 @@ def main():
         n_done += many_states(eng, oracle, seed, ins, templates, bad)
         n_done += host_mirror(eng, oracle, seed, ins, templates, bad)
         seed += 1
-    print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - (int(sys.argv[2]) if len(sys.argv) > 2 else 1), len(bad)))
+    print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - first_seed, len(bad)))
     sys.exit(1 if bad else 0)
 
 
