@@ -20,7 +20,6 @@ namespace {
 
 using namespace ie_dev;
 constexpr uint32_t MAXF = 24;   // splice depth of the general path
-constexpr uint32_t KSCR = IE_KEY_SCRATCH;
 
 // ---- general path ----------------------------------------------------------------------------
 struct Frame {
@@ -161,12 +160,6 @@ template <typename P>
 __device__ __forceinline__ P* warp_bcast_ptr(P* p) {
     return reinterpret_cast<P*>(__shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(p), 0));
 }
-
-struct GenResult {
-    uint32_t status, aux;
-    const uint8_t* payload;  // already-final bytes (key / value), or nullptr when in T / frames
-    uint32_t payload_len;
-};
 
 __device__ uint8_t* reserve_out(uint8_t* out, uint64_t out_cap, ie_batch_info* info, uint32_t* overflow, uint32_t len,
                                 uint64_t& off) {
