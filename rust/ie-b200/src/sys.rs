@@ -89,6 +89,9 @@ extern "C" {
     pub fn ie_glob_sweep_device(e: *mut ie_engine, d_keys: *const u8, d_key_offs: *const u64, n: u64, pats: *const u8,
                                 pat_offs: *const u64, n_pat: u32, invert: c_int, d_mask: *mut u32, d_n_deleted: *mut u64,
                                 stream: *mut c_void) -> c_int;
+    /// first[k] = index of the first pattern matching key k, 0xFFFF_FFFF if none (runtime.rs:1085-1133, 1649-1692)
+    pub fn ie_glob_first_match(e: *mut ie_engine, keys: *const u8, key_offs: *const u64, n: u64, pats: *const u8, pat_offs: *const u64,
+                               n_pat: u32, first: *mut u32) -> c_int;
 
     pub fn ie_device_alloc(e: *mut ie_engine, bytes: u64, d_ptr: *mut *mut c_void) -> c_int;
     pub fn ie_device_free(e: *mut ie_engine, d_ptr: *mut c_void);
