@@ -31,6 +31,14 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_rust_bindings_cover_the_header():
+    """rust/ie-b200/src/sys.rs (sources only: no Rust toolchain in this image) declares every entry point of the header."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ie_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(ie_[a-z_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (ie_[a-z_]+)\s*\(", open(os.path.join(ROOT, "rust", "ie-b200", "src", "sys.rs")).read()))
+    assert declared == bound, declared ^ bound
+
+
 def test_no_cpu_fallback(lib):
     if lib.ie_device_count() > 0:
         pytest.skip("a GPU is present")
