@@ -291,9 +291,9 @@ def main():
                        "l2": "two input/output buffer sets alternated per step; per-step working set %.2f GB > 126 MB L2" % (alg[0] / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks; per-step min/median ms = %.3f/%.3f" % (min(per_step_ms), sorted(per_step_ms)[len(per_step_ms) // 2])},
             "clocks": clocks,
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 3 * args.steps,  # per rank and step: ie_resolve_tile_kernel + the two tiers of ie_resolve_general_kernel (profiles/r01_final_launches.csv)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "ie_resolve_tile_kernel (+ the general kernel and two small memsets in the same step)",
+                         "kernel": "ie_resolve_tile_kernel (+ the two general-tier kernels, empty on this workload, and two small memsets in the same step)",
                          "algorithmic_bytes_per_launch": alg_mean, "peak_source": peak_src + ", of measured"},
         }
         if e2e:
