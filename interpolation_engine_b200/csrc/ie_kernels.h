@@ -91,7 +91,7 @@ cudaError_t ie_launch_resolve_tiles_small(const IeTableView* d_views, uint32_t n
 // (0 = unknown, assume short / few): the largest power of two <= IE_RESOLVE_TILE whose expected text, brace events
 // (2 per group) and copy segments (2 per group + 1) fit the tile's tables with 20-25 % headroom.  A tile that outgrows
 // its tables still resolves exactly, but on the slow per-thread path: this keeps dense templates off it.
-#define IE_TILE_EVENTS (12u * 128u)    // ie_resolve_tile.cu: E_CAP of the 128-template build
+#define IE_TILE_EVENTS (23u * 64u)     // ie_resolve_tile.cu: E_CAP of the 128-template build
 #define IE_TILE_SEGMENTS (8u * 128u)   // S_CAP
 inline uint32_t ie_pick_tile(uint64_t avg_bytes, uint64_t avg_groups_x16 = 0) {
     uint32_t tt = IE_RESOLVE_TILE;

@@ -61,21 +61,21 @@ constexpr int TT = IE_RESOLVE_TILE;  // templates per tile at most (the launch p
 constexpr int NT = IE_TILE_NT;       // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int CTAS_PER_SM = IE_TILE_CTAS;  // resident CTAs the register budget is tuned for (48 registers)
-#ifndef IE_E_PER
-#define IE_E_PER 12
+#ifndef IE_E_PER2
+#define IE_E_PER2 23  // brace events per template x 2 a tile's event arrays hold (ie_kernels.h: IE_TILE_EVENTS)
 #endif
 #ifndef IE_S_PER
 #define IE_S_PER 8
 #endif
-constexpr int E_CAP = IE_E_PER * TT;  // brace events per tile
+constexpr int E_CAP = IE_E_PER2 * TT / 2;  // brace events per tile
 constexpr int Q_CAP = E_CAP / 2;     // groups per tile
 constexpr int E_PAD = E_CAP + E_CAP / 32 + 2;
 constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks per tile (288 bytes of template text per template)
 constexpr int S_CAP = IE_S_PER * TT;  // copy segments per tile
 #ifndef IE_C_PER
-#define IE_C_PER 16
+#define IE_C_PER 18
 #endif
-constexpr int C_CAP = IE_C_PER * TT;       // 32-byte output blocks with a segment index (512 bytes of output per template)
+constexpr int C_CAP = IE_C_PER * TT;       // 16-byte output chunks with a segment index (288 bytes of output per template)
 constexpr uint32_t POS_MASK = 0x00FFFFFFu;
 constexpr uint32_t EV_SIMPLE = 0x80000000u;
 constexpr uint32_t EV_CLOSE = 1u << 24;
@@ -83,6 +83,7 @@ constexpr uint32_t EV_DONE = 1u << 26;   // open event: the group is resolved, e
 constexpr uint32_t EV_PUNT = 1u << 25;   // a byte the tile kernel does not interpret (sentinel collisions): the template is punted
 constexpr uint32_t NONE16 = 0xFFFFu;
 enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2, TF_AGAIN = 4 };
+constexpr uint32_t CS_EDGE = 0x8000u;    // cs[]: the chunk is not covered by ONE segment (pass B assembles it)
 
 __device__ __forceinline__ uint32_t EI(uint32_t e) { return e + (e >> 5); }  // padded event index
 
@@ -96,14 +97,13 @@ struct Smem {
     uint16_t ev_c[E_PAD];      // open: parent open (NONE16 = top level)
     union {
         struct {
-            uint32_t cm[M_CAP];  // P1/P2: per chunk, bit 2j = unescaped '{' at byte j, bit 2j+1 = '}', both = punt marker
+            uint32_t cm[M_CAP];  // P1/P2: per chunk, bit j = unescaped '{' at byte j, bit 16 + j = '}', both = punt marker
             uint32_t q[Q_CAP];   // P2/P3: leaf groups (template << 16 | open event)
-            uint16_t cbase[M_CAP];  // P2: events of the tile before each chunk
         } scan;
         struct {
             uint32_t out[S_CAP + 2];  // P5: tile-local output offset of each segment (+ sentinel)
             uint64_t src[S_CAP];      //     its source address
-            uint16_t cs[C_CAP + 2];   //     segment holding the first byte of each 32-byte aligned output block
+            uint16_t cs[C_CAP + 2];   //     segment holding the first byte of each 16-byte aligned output chunk | CS_EDGE
         } seg;
     } u;
     uint32_t t_start[TT + 1];  // template start, tile-relative
@@ -115,6 +115,7 @@ struct Smem {
     uint16_t t_ne[TT];         // its events
     uint8_t t_tag[TT];
     uint8_t t_layers[TT];      // simple-path layers of the template (interp.rs:45-52)
+    uint4 lowmask[17];         // lowmask[k] = the low k bytes of a 16-byte quantity set (load16_range)
     uint32_t warp_scan[NW];
     uint32_t q_n[1];
     uint32_t ev_n;             // events allocated
@@ -130,11 +131,9 @@ __device__ __forceinline__ uint32_t eqmask(uint32_t w, uint32_t pat) {  // 0x80 
     const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(t | x) & 0x80808080u;
 }
-// 0x80-per-byte flags `o` (open) and `c` (close) of one word -> 8 bits, 2 per byte (open, close)
-__device__ __forceinline__ uint32_t pack2(uint32_t o, uint32_t c) {
-    const uint32_t t = (o >> 7) | (c >> 6);
-    return (t * 0x01041040u) >> 24;
-}
+// Appends the 4 byte flags (0x80 per byte) of one word to a per-chunk mask: acc = acc << 4 | flags.  The multiply
+// gathers bits 7 / 15 / 23 / 31 into the top nibble (no two partial products meet, so no carries).
+__device__ __forceinline__ uint32_t push4(uint32_t acc, uint32_t flags) { return __funnelshift_l(flags * 0x00204081u, acc, 4); }
 
 #ifndef IE_P1_BATCH
 #define IE_P1_BATCH 3
@@ -142,79 +141,61 @@ __device__ __forceinline__ uint32_t pack2(uint32_t o, uint32_t c) {
 constexpr int P1_BATCH = IE_P1_BATCH;
 
 // The two rare corrections of scan_chunk, out of line: the chunk scan is unrolled P1_BATCH times and the kernel's
-// instruction footprint matters (stall_no_instruction 0.8 cycles per issue; measured 0.3822 -> 0.3786 ms).
-__device__ __noinline__ uint32_t scan_chunk_rare(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t e0, uint32_t e1, uint32_t e2,
-                                                 uint32_t e3, int32_t p0, uint32_t tile_bytes, const uint8_t* __restrict__ tp, uint32_t bits) {
-    const uint32_t w[4] = {w0, w1, w2, w3}, ecs[4] = {e0, e1, e2, e3};
-    const uint32_t any_esc_close = e0 | e1 | e2 | e3, hi = w0 | w1 | w2 | w3;
+// instruction footprint matters.  `ec` = escaped '}' per byte (16 bits), `m` = the chunk's mask so far.
+__device__ __noinline__ uint32_t scan_chunk_rare(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t ec, int32_t p0, uint32_t tile_bytes,
+                                                 const uint8_t* __restrict__ tp, uint32_t m) {
+    const uint32_t w[4] = {w0, w1, w2, w3};
     // rare: escaped '}' preceded by '.' or '}' (".\}" / "}\}": '.' + "〠." reads as ".〠" + '.')
-    if (any_esc_close) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t m = ecs[k];
-            while (m) {
-                const int byte = (__ffs(m) - 1) >> 3;
-                m &= m - 1;
-                const int32_t p = p0 + 4 * k + byte;
-                if (p >= 2) {
-                    const uint8_t b2 = __ldg(tp + p - 2);
-                    if (b2 == '.' || b2 == '}') bits |= 3u << (2 * (4 * k + byte));
-                }
-            }
+    while (ec) {
+        const int j = __ffs(ec) - 1;
+        ec &= ec - 1;
+        const int32_t p = p0 + j;
+        if (p >= 2) {
+            const uint8_t b2 = __ldg(tp + p - 2);
+            if (b2 == '.' || b2 == '}') m |= 0x10001u << j;
         }
     }
     // rare: literal U+3020 (E3 80 A0) collides with the reference's sentinels
-    if (hi & 0x80808080u) {
+    if ((w0 | w1 | w2 | w3) & 0x80808080u) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint32_t me = eqmask(w[k], 0xE3E3E3E3u);
             while (me) {
                 const int bit = __ffs(me) - 1;
                 me &= me - 1;
-                const uint32_t p = (uint32_t)(p0 + 4 * k + (bit >> 3));
-                if (p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0)
-                    bits |= 3u << (2 * (4 * k + (bit >> 3)));
+                const int32_t p = p0 + 4 * k + (bit >> 3);
+                if (p >= 0 && (uint32_t)p + 2 < tile_bytes && __ldg(tp + p + 1) == 0x80 && __ldg(tp + p + 2) == 0xA0)
+                    m |= 0x10001u << (4 * k + (bit >> 3));
             }
         }
     }
-    return bits;
+    return m;
 }
 
-// One 16-byte chunk of template text -> 32 bits, 2 per byte: bit 2j = unescaped '{' at byte j,
-// bit 2j+1 = unescaped '}', both = punt marker.  `prev` is the byte before the chunk ("previous byte is
-// a backslash" is evaluated on the flat stream; P2 repairs the first byte of each template).
+// One 16-byte chunk of template text -> 32 bits: bit j = unescaped '{' at byte j, bit 16 + j = unescaped '}', both =
+// punt marker.  `prev` is the byte before the chunk ("previous byte is a backslash" is evaluated on the flat stream;
+// P2 repairs the first byte of each template).
 __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, int32_t p0, uint32_t tile_bytes,
                                                const uint8_t* __restrict__ tp) {
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: blank the bytes outside the tile
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t O = 0, C = 0, B = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t keep = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int32_t p = p0 + 4 * k + j;
-                if (p >= 0 && p < (int32_t)tile_bytes) keep |= 0xFFu << (8 * j);
-            }
-            w[k] &= keep;
-        }
+    for (int k = 3; k >= 0; --k) {
+        O = push4(O, eqmask(w[k], 0x7B7B7B7Bu));
+        C = push4(C, eqmask(w[k], 0x7D7D7D7Du));
+        B = push4(B, eqmask(w[k], 0x5C5C5C5Cu));
     }
-    uint32_t carry = prev == '\\' ? 0x80u : 0u;
-    uint32_t bits = 0, hi = 0, any_esc_close = 0;
-    uint32_t ecs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t mo = eqmask(w[k], 0x7B7B7B7Bu);
-        const uint32_t mc = eqmask(w[k], 0x7D7D7D7Du);
-        const uint32_t mb = eqmask(w[k], 0x5C5C5C5Cu);
-        const uint32_t pb = (mb << 8) | carry;
-        carry = mb >> 24;
-        bits |= pack2(mo & ~pb, mc & ~pb) << (8 * k);
-        ecs[k] = mc & pb;
-        any_esc_close |= ecs[k];
-        hi |= w[k];
+    if (p0 < 0 || p0 + 16 > (int32_t)tile_bytes) {  // first / last chunk: drop the bytes outside the tile
+        const uint32_t lo = p0 < 0 ? (uint32_t)-p0 : 0u;
+        const uint32_t hi = (int32_t)tile_bytes - p0 >= 16 ? 16u : (uint32_t)((int32_t)tile_bytes - p0);
+        const uint32_t keep = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+        O &= keep; C &= keep; B &= keep;
     }
-    if (any_esc_close | (hi & 0x80808080u)) bits = scan_chunk_rare(w[0], w[1], w[2], w[3], ecs[0], ecs[1], ecs[2], ecs[3], p0, tile_bytes, tp, bits);
-    return bits;
+    const uint32_t esc = (B << 1) | (prev == '\\' ? 1u : 0u);
+    uint32_t m = (O & ~esc) | ((C & ~esc) << 16);
+    const uint32_t ec = C & esc;
+    if (ec | ((w[0] | w[1] | w[2] | w[3]) & 0x80808080u)) m = scan_chunk_rare(w[0], w[1], w[2], w[3], ec, p0, tile_bytes, tp, m);
+    return m;
 }
 
 // 16 bytes from an arbitrary address through ALIGNED 16-byte loads (the second one only when the m requested
@@ -233,16 +214,24 @@ __device__ __forceinline__ uint4 load16_any(const uint8_t* __restrict__ p, uint3
     const uint32_t sh = (r & 3) * 8;
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
-// Up to 16 bytes from an arbitrary address as four little-endian words; bytes at index >= m are zero (m >= 1).
-__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* __restrict__ p, uint32_t m) {
-    uint4 v = load16_any(p, m);
-    const uint32_t full = m >> 2, rem = (m & 3) * 8;
-    const uint32_t part = rem ? ((1u << rem) - 1u) : 0u;
-    v.x &= full > 0 ? 0xFFFFFFFFu : (full == 0 ? part : 0u);
-    v.y &= full > 1 ? 0xFFFFFFFFu : (full == 1 ? part : 0u);
-    v.z &= full > 2 ? 0xFFFFFFFFu : (full == 2 ? part : 0u);
-    v.w &= full > 3 ? 0xFFFFFFFFu : (full == 3 ? part : 0u);
-    return v;
+// The 16-byte window at an arbitrary address p, restricted to its bytes [lo, hi) (0 <= lo < hi <= 16): byte j of the
+// result is p[j] inside the range and zero outside.  Only the aligned 16-byte blocks that hold a requested byte are
+// read, so p may be a VIRTUAL address: "where the piece would start if it began at byte 0 of the destination chunk".
+// A piece lands at its place in a destination chunk without any register shift: acc |= load16_range(src - lo, lo, hi).
+__device__ __forceinline__ uint4 load16_range(const uint4* __restrict__ lowmask, const uint8_t* __restrict__ p, uint32_t lo, uint32_t hi) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint4* ap = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint32_t r = (uint32_t)(a & 15);
+    uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+    if (lo + r < 16) A = __ldg(ap);
+    if (hi + r > 16) B = __ldg(ap + 1);
+    uint32_t w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z;
+    if (r & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = B.w; }
+    if (r & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    const uint32_t sh = (r & 3) * 8;
+    const uint4 mh = lowmask[hi], ml = lowmask[lo];
+    return make_uint4(__funnelshift_r(w0, w1, sh) & mh.x & ~ml.x, __funnelshift_r(w1, w2, sh) & mh.y & ~ml.y,
+                      __funnelshift_r(w2, w3, sh) & mh.z & ~ml.z, __funnelshift_r(w3, w4, sh) & mh.w & ~ml.w);
 }
 // acc |= v << (8 * s bytes), s in [0, 15], as one 128-bit little-endian quantity
 __device__ __forceinline__ void or_shifted(uint4& acc, const uint4& v, uint32_t s) {
@@ -352,8 +341,14 @@ struct PieceEmit {
     __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
         sm.u.seg.out[idx] = off;
         sm.u.seg.src[idx] = (uint64_t)(uintptr_t)src;
-        if (index_chunks)  // every 32-byte aligned output block whose first byte lies in this piece points back at it
-            for (uint32_t c = (off + olead + 31) >> 5; (c << 5) < off + olead + len; ++c) sm.u.seg.cs[c] = (uint16_t)idx;
+        if (index_chunks) {
+            // every 16-byte aligned output chunk whose first byte lies in this piece points back at it; only the last
+            // of them can reach beyond the piece's end (CS_EDGE: pass B assembles that chunk)
+            const uint32_t lo = off + olead, hi = lo + len;  // the piece in chunk coordinates
+            uint32_t c = (lo + 15) >> 4;
+            for (; (c << 4) + 16 <= hi; ++c) sm.u.seg.cs[c] = (uint16_t)idx;
+            if ((c << 4) < hi) sm.u.seg.cs[c] = (uint16_t)(idx | CS_EDGE);
+        }
         ++idx;
         off += len;
     }
@@ -381,13 +376,21 @@ __device__ __forceinline__ bool short_key(const Smem& sm, const IeTableView& tv,
         const uint32_t stop = sm.ev_pos[EI(e)] & POS_MASK;
         const uint32_t m = stop - pos;
         if (klen + m > 16) return false;
-        if (m) { or_shifted(key, load_unaligned16(tp + pos, m), klen); klen += m; }
+        if (m) {
+            const uint4 v = load16_range(sm.lowmask, tp + pos - klen, klen, klen + m);
+            key.x |= v.x; key.y |= v.y; key.z |= v.z; key.w |= v.w;
+            klen += m;
+        }
         if (e == c) return true;
         const uint32_t ce = sm.ev_match[EI(e)];
         const uint32_t vl = sm.ev_a[EI(ce)];
         if (klen + vl > 16) return false;
         if (vl) {  // values of <= 16 bytes live zero-padded in their slot's 16-byte aligned inline area
-            or_shifted(key, e == carry_e ? carry_v : __ldg(reinterpret_cast<const uint4*>(tv.base + (size_t)sm.ev_a[EI(e)] * 16u)), klen);
+            if (e == carry_e) or_shifted(key, carry_v, klen);
+            else {
+                const uint4 v = load16_range(sm.lowmask, tv.base + (size_t)sm.ev_a[EI(e)] * 16u - klen, klen, klen + vl);
+                key.x |= v.x; key.y |= v.y; key.z |= v.z; key.w |= v.w;
+            }
             klen += vl;
         }
         pos = (sm.ev_pos[EI(ce)] & POS_MASK) + 1;
@@ -581,6 +584,10 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     if (NT == TT && tid == 0) sm.t_start[TT] = (uint32_t)(off_end - off0);
     if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; sm.t_splice[tid] = 0; }
     if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; }
+    if (tid < 17) {
+        auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
+        sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
+    }
     const uintptr_t a0 = (uintptr_t)tp & ~(uintptr_t)15;
     const uint32_t lead = (uint32_t)((uintptr_t)tp - a0);
     const uint32_t tile_bytes = (uint32_t)tile_bytes64;
@@ -615,124 +622,136 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     __syncthreads();
     PHASE_MARK(2);
 
-    // ---- P2a: flat event extraction ------------------------------------------------------------------------
-    // Every thread takes a contiguous run of chunk masks; one CTA scan of the per-run event counts gives each
-    // event its slot, so the tile's events end up in ONE array sorted by position (a template's events are a
-    // contiguous range of it).  cbase[c] = events before chunk c.
-    if (!too_big) {
-        const uint32_t per = (n_chunks + NT - 1) / NT;
-        const uint32_t c_lo = min(tid * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
-        uint32_t cnt = 0;
-        for (uint32_t c = c_lo; c < c_hi; ++c) {
-            const uint32_t m = sm.u.scan.cm[c];
-            cnt += __popc((m | (m >> 1)) & 0x55555555u);
+    // ---- P2: per-template events and structure ---------------------------------------------------------------
+    // One thread per template walks the masks of its own chunks.  A first pass counts its events; a warp scan plus
+    // one shared atomic per warp hands every template a contiguous range [eb, eb + ne) of the event arrays (ranges
+    // of different templates are in no particular order - nothing downstream relies on one).  The second pass
+    // enumerates the events in position order and does the bracket matching on the fly: stack-free through parent
+    // links; ev_a[open] counts unresolved children until the group resolves; a group that closes without children
+    // is a leaf and goes to the lookup queue right away (P3 skips the queue entries of templates that end up punted).
+    if (!too_big && tid < TT) {
+        const uint32_t start = sm.t_start[min(tid, nt)], end = sm.t_start[min(tid + 1, nt)];
+        const uint32_t ca = lead + start, cz = lead + end;          // the template's extent in chunk coordinates
+        const uint32_t c0 = ca >> 4, c1 = active ? (cz + 15) >> 4 : c0;  // its chunks: [c0, c1)
+        // valid bytes of the first / last chunk, replicated into both halves of a mask
+        const uint32_t keep_first = (0xFFFFu & ~((1u << (ca & 15)) - 1u)) * 0x10001u;
+        const uint32_t keep_last = ((2u << ((cz - 1) & 15)) - 1u) * 0x10001u;
+        // pass 1: count the template's events; `nonempty` = which of its first 32 chunks hold any
+        uint32_t ne = 0, nonempty = 0;
+        for (uint32_t c = c0; c < c1; ++c) {
+            uint32_t m = sm.u.scan.cm[c];
+            if (c == c0) m &= keep_first;
+            if (c + 1 == c1) m &= keep_last;
+            const uint32_t cnt = __popc((m | (m >> 16)) & 0xFFFFu);
+            ne += cnt;
+            if (cnt && c - c0 < 32) nonempty |= 1u << (c - c0);
         }
-        uint32_t incl = cnt;
+        uint32_t incl = ne;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if ((int)lane >= d) incl += y;
         }
-        if (lane == 31) sm.warp_scan[warp] = incl;
-        __syncthreads();
-        uint32_t wi = incl - cnt, total_ev = 0;
+        uint32_t wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(&sm.ev_n, incl);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+        const uint32_t eb = wbase + incl - ne;
+        uint32_t flags = 0, leaf_lo = 0;  // leaf_lo: which of the template's first 32 events are leaf groups
+        bool fits = true;
+        if (active && eb + ne > (uint32_t)E_CAP) { sm.overflow = 1; fits = false; }  // more brace events than the tile's tables hold
+        else if (active) {
+            // The flat scan took "the previous byte is a backslash" across template boundaries: a template that
+            // starts with a brace right after a template ending in '\\' lost that event -> the general path redoes it.
+            if (end > start && start > 0 && __ldg(tp + start - 1) == '\\') {
+                const uint8_t b0 = __ldg(tp + start);
+                if (b0 == '{' || b0 == '}') flags = TF_PUNT;
+            }
+            if (flags == 0) {
+                // pass 2: ONE loop over the events (every lane runs its `ne` iterations of the same body; a loop over
+                // chunks with an inner loop over their events ran at 6 of 32 lanes: templates start at different chunk
+                // phases, so at any chunk step only a few lanes have events)
+                uint32_t n_open = 0, cur_open = NONE16;
+                bool punt = false, stray = false;
+                uint32_t c = c0, m = 0, ev = 0;
+                for (uint32_t k = 0; k < ne; ++k) {
+                    if (ev == 0) {  // next chunk with events: through the bitmap for the first 32 chunks, by search beyond
+                        if (nonempty) { c = c0 + (uint32_t)__ffs(nonempty) - 1u; nonempty &= nonempty - 1u; }
+                        else {
+                            c = max(c + 1, c0 + 32);
+                            for (;; ++c) {
+                                uint32_t mm = sm.u.scan.cm[c];
+                                if (c + 1 == c1) mm &= keep_last;
+                                if (mm) break;
+                            }
+                        }
+                        m = sm.u.scan.cm[c];
+                        if (c == c0) m &= keep_first;
+                        if (c + 1 == c1) m &= keep_last;
+                        ev = (m | (m >> 16)) & 0xFFFFu;
+                    }
+                    const uint32_t j = (uint32_t)__ffs(ev) - 1u;
+                    ev &= ev - 1u;
+                    const uint32_t kind = (m >> j) & 0x10001u;  // 1 open, 0x10000 close, both: a byte the tile kernel does not interpret
+                    if (kind == 0x10001u) { punt = true; break; }
+                    const uint32_t e = eb + k, pos = c * 16 - lead + j;
+                    if (kind == 1u) {
+                        ++n_open;
+                        sm.ev_pos[EI(e)] = pos;
+                        sm.ev_c[EI(e)] = (uint16_t)cur_open;
+                        sm.ev_a[EI(e)] = 0;
+                        if (cur_open != NONE16) sm.ev_a[EI(cur_open)] += 1;
+                        cur_open = e;
+                    } else {
+                        sm.ev_pos[EI(e)] = pos | EV_CLOSE;
+                        if (cur_open == NONE16) stray = true;
+                        else {
+                            const uint32_t o = cur_open;
+                            sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
+                            cur_open = sm.ev_c[EI(o)];
+                            if (o + 1 == e) {  // closes without children: a leaf group
+                                if (k <= 32) leaf_lo |= 1u << (k - 1); else sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | o;
+                            }
+                        }
+                    }
+                }
+                if (punt) flags = TF_PUNT;
+                else if (n_open == 0) flags = TF_VERBATIM;              // the loop at interp.rs:54 is never entered (stray '}' stay)
+                else if (stray || cur_open != NONE16) flags = TF_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
+                uint32_t layers = 0;
+                if (flags == 0 && layer_cap) {
+                    // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
+                    uint32_t ld = 0, tr = 0;
+                    while (ld < ne && sm.ev_pos[EI(eb + ld)] == start + ld) ++ld;
+                    while (tr < ne && sm.ev_pos[EI(eb + ne - 1 - tr)] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
+                    const uint32_t m0 = min(min(ld, tr), layer_cap);
+                    for (; layers < m0; ++layers) {
+                        if (sm.ev_match[EI(eb + layers)] != eb + ne - 1 - layers) break;
+                        sm.ev_pos[EI(eb + layers)] |= EV_SIMPLE;
+                    }
+                }
+                if (ROUNDS) sm.t_layers[tid] = (uint8_t)min(layers, 255u);
+            }
+            sm.t_eb[tid] = (uint16_t)eb;
+            sm.t_ne[tid] = (uint16_t)ne;
+            sm.t_flags[tid] = flags;
+        }
+        // the leaves found above go to the lookup queue: one shared atomic per warp instead of one per leaf
+        const uint32_t nl = (active && fits) ? (uint32_t)__popc(leaf_lo) : 0u;
+        uint32_t lincl = nl;
 #pragma unroll
-        for (int wv = 0; wv < NW; ++wv) {
-            const uint32_t x = sm.warp_scan[wv];
-            if (wv < (int)warp) wi += x;
-            total_ev += x;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, lincl, d);
+            if ((int)lane >= d) lincl += y;
         }
-        if (total_ev > (uint32_t)E_CAP) { if (tid == 0) sm.overflow = 1; }
-        else {
-            if (tid == 0) sm.ev_n = total_ev;
-            for (uint32_t c = c_lo; c < c_hi; ++c) {
-                sm.u.scan.cbase[c] = (uint16_t)wi;
-                const uint32_t m = sm.u.scan.cm[c];
-                wi += __popc((m | (m >> 1)) & 0x55555555u);
-            }
+        uint32_t qbase = 0;
+        if (lane == 31 && lincl) qbase = atomicAdd(&sm.q_n[0], lincl);
+        uint32_t qi = __shfl_sync(0xFFFFFFFFu, qbase, 31) + lincl - nl;
+        const uint32_t eb0 = wbase + incl - ne;
+        while (leaf_lo) {
+            const uint32_t k1 = (uint32_t)__ffs(leaf_lo) - 1u;  // the leaf's close is event k1 + 1 of the template, its open event k1
+            leaf_lo &= leaf_lo - 1u;
+            sm.u.scan.q[qi++] = (tid << 16) | (eb0 + k1);
         }
-        __syncthreads();
-        // extraction, one chunk per thread and round (consecutive lanes take consecutive chunks: balanced); the
-        // first two events of a chunk are written without a loop, the loop takes the rest (dense chunks are rare)
-        if (!sm.overflow) {
-            for (uint32_t c = tid; c < n_chunks; c += NT) {
-                uint32_t m = sm.u.scan.cm[c];
-                if (m == 0) continue;
-                uint32_t w = sm.u.scan.cbase[c];
-                const uint32_t p0 = c * 16 - lead;
-                do {
-                    const int bit = (__ffs(m) - 1) & ~1;
-                    const uint32_t pair = (m >> bit) & 3u;
-                    m &= ~(3u << bit);
-                    sm.ev_pos[EI(w++)] = (p0 + (bit >> 1)) | ((pair - 1u) << 24);  // 1 open, 2 EV_CLOSE, 3 EV_PUNT
-                } while (m);
-            }
-        }
-    }
-    PHASE_MARK(2);
-    __syncthreads();
-
-    // ---- P2b: per-template structure -------------------------------------------------------------------------
-    // One thread per template walks its events: stack-free bracket matching through parent links; ev_a[open]
-    // counts unresolved children until the group resolves; a group that closes without children is a leaf and
-    // goes to the lookup queue right away (P3 skips the queue entries of templates that end up punted).
-    if (!too_big && !sm.overflow && active) {
-        const uint32_t start = sm.t_start[tid], end = sm.t_start[tid + 1];
-        auto event_index = [&](uint32_t p) -> uint32_t {  // events of the tile before byte position p
-            const uint32_t c = (lead + p) >> 4;
-            if (c >= n_chunks) return sm.ev_n;
-            const uint32_t m = sm.u.scan.cm[c] & ((1u << (2 * ((lead + p) & 15))) - 1u);
-            return sm.u.scan.cbase[c] + __popc((m | (m >> 1)) & 0x55555555u);
-        };
-        const uint32_t eb = event_index(start), ee = event_index(end);
-        const uint32_t ne = ee - eb;
-        uint32_t flags = 0;
-        // The flat scan took "the previous byte is a backslash" across template boundaries: a template that
-        // starts with a brace right after a template ending in '\' lost that event -> the general path redoes it.
-        if (end > start && start > 0 && __ldg(tp + start - 1) == '\\') {
-            const uint8_t b0 = __ldg(tp + start);
-            if (b0 == '{' || b0 == '}') flags = TF_PUNT;
-        }
-        if (flags == 0) {
-            uint32_t n_open = 0, cur_open = NONE16;
-            bool punt = false, stray = false;
-            for (uint32_t e = eb; e < ee; ++e) {
-                const uint32_t v = sm.ev_pos[EI(e)];
-                if (v & EV_PUNT) { punt = true; break; }
-                if (!(v & EV_CLOSE)) {
-                    ++n_open;
-                    sm.ev_c[EI(e)] = (uint16_t)cur_open;
-                    sm.ev_a[EI(e)] = 0;
-                    if (cur_open != NONE16) sm.ev_a[EI(cur_open)] += 1;
-                    cur_open = e;
-                } else if (cur_open == NONE16) stray = true;
-                else {
-                    const uint32_t o = cur_open;
-                    sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
-                    cur_open = sm.ev_c[EI(o)];
-                    if (sm.ev_a[EI(o)] == 0) sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | o;
-                }
-            }
-            if (punt) flags = TF_PUNT;
-            else if (n_open == 0) flags = TF_VERBATIM;              // the loop at interp.rs:54 is never entered (stray '}' stay)
-            else if (stray || cur_open != NONE16) flags = TF_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
-            uint32_t layers = 0;
-            if (flags == 0 && layer_cap) {
-                // simple-path layers (interp.rs:45-52): leading '{' run matched symmetrically by the trailing '}' run
-                uint32_t ld = 0, tr = 0;
-                while (ld < ne && sm.ev_pos[EI(eb + ld)] == start + ld) ++ld;
-                while (tr < ne && sm.ev_pos[EI(eb + ne - 1 - tr)] == ((end - 1 - tr) | EV_CLOSE)) ++tr;
-                const uint32_t m0 = min(min(ld, tr), layer_cap);
-                for (; layers < m0; ++layers) {
-                    if (sm.ev_match[EI(eb + layers)] != eb + ne - 1 - layers) break;
-                    sm.ev_pos[EI(eb + layers)] |= EV_SIMPLE;
-                }
-            }
-            if (ROUNDS) sm.t_layers[tid] = (uint8_t)min(layers, 255u);
-        }
-        sm.t_eb[tid] = (uint16_t)eb;
-        sm.t_ne[tid] = (uint16_t)ne;
-        sm.t_flags[tid] = flags;
     }
     PHASE_MARK(3);
     __syncthreads();
@@ -827,7 +846,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     const uint32_t olead = (uint32_t)((uintptr_t)out & 15);  // tile offsets are multiples of 16
     const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
     const bool seg_ok = total_seg <= (uint32_t)S_CAP && tile_out64 <= 0xFFFFFFFFull;
-    const bool index_chunks = o_chunks <= 2 * (uint32_t)C_CAP;
+    const bool index_chunks = o_chunks <= (uint32_t)C_CAP;
     if (seg_ok) {
         if (active && nseg) {
             PieceEmit em{sm, sbase, loc, olead, index_chunks};
@@ -835,7 +854,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
             else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, em);
             else walk_output_pieces<ROUNDS>(sm, tv, tp, tid, em);
         }
-        if (tid == 0) { sm.u.seg.cs[0] = 0; sm.u.seg.out[total_seg] = tile_out; }
+        // chunk 0 starts before the tile's first byte unless the tile's output is 16-byte aligned (then the first piece owns it)
+        if (tid == 0) { if (olead) sm.u.seg.cs[0] = (uint16_t)CS_EDGE; sm.u.seg.out[total_seg] = tile_out; }
     }
     PHASE_MARK(8);
     // The tile's output range is claimed with one atomic add on the batch's byte counter: tiles land in
@@ -863,26 +883,28 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     // 4 funnel shifts, one 16-byte store.  Pass B: one thread per segment start handles the chunk that
     // contains it (pieces shifted and OR-ed in registers); the ragged first / last chunk of the tile too.
     if (tile_out == 0) return true;
-    for (uint32_t c = tid; c < o_chunks; c += NT) {
-        const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
-        if (x0s < 0 || (uint32_t)x0s + 16 > tile_out) continue;   // ragged edge chunk: pass B
-        const uint32_t xb = (uint32_t)x0s;
-        uint32_t sidx;
-        if (index_chunks) {
-            sidx = sm.u.seg.cs[c >> 1];  // segment at the enclosing 32-byte block start, then at most a short walk
-            while (sm.u.seg.out[sidx + 1] <= xb) ++sidx;
+    if (index_chunks) {
+        for (uint32_t c = tid; c < o_chunks; c += NT) {
+            const uint32_t sidx = sm.u.seg.cs[c];
+            if (sidx & CS_EDGE) continue;  // ragged edge of the tile, or a segment ends inside this chunk: pass B
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (c * 16 - olead - sm.u.seg.out[sidx]);
+            *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
         }
-        else {
+    } else {
+        for (uint32_t c = tid; c < o_chunks; c += NT) {
+            const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;  // tile-local output position of the chunk's byte 0
+            if (x0s < 0 || (uint32_t)x0s + 16 > tile_out) continue;   // ragged edge chunk: pass B
+            const uint32_t xb = (uint32_t)x0s;
             uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
             }
-            sidx = lo;
+            const uint32_t sidx = lo;
+            if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (xb - sm.u.seg.out[sidx]);
+            *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
         }
-        if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
-        const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (xb - sm.u.seg.out[sidx]);
-        *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
     }
     PHASE_MARK(10);
     // pass B: item 0 = the tile's first chunk, item j >= 1 = the chunk holding the start of segment j when
@@ -914,10 +936,12 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
         uint4 acc = make_uint4(0, 0, 0, 0);
         uint32_t x = xb;
         for (;;) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (x - so);
-            const uint32_t m = min(xe, se) - x;
-            or_shifted(acc, load_unaligned16(src, m), (uint32_t)((int32_t)x - x0s));
-            x += m;
+            // the piece's bytes land at their place in the chunk through a virtual source address (load16_range)
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + ((int32_t)x0s - (int32_t)so);
+            const uint32_t xn = min(xe, se);
+            const uint4 v = load16_range(sm.lowmask, src, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn - x0s));
+            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+            x = xn;
             if (x >= xe) break;
             ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
         }

@@ -185,5 +185,223 @@ def main():
     print({k: len(v) for k, v in out.items()})
 
 
+# ---- replace_map / goto_map: the twin's execute_task drives them -------------------------
+# interpolation_engine.py:1689-1770 holds both commands inlined in execute_task; runtime.rs:1085-1133, 1649-1752 is the
+# Rust side.  The two differ outside the subset generated here (documented where each restriction is applied):
+#   * Rust resolves goto_map entries lazily and in order, Python resolves every key and value up front
+#     -> every key / value template of a generated case resolves;
+#   * Python's `str()` of a list / bool / float is its repr, Rust's value_to_string concatenates / lower-cases
+#     -> inserts are strings and integers only;
+#   * a replace_map item that IS one simple key is looked up typed by Python and rescanned (`recursive_replace`), Rust
+#     resolves it once -> such items resolve to brace-free strings;
+#   * on a resolver error Python falls back to the literal 'NULL' map for the whole item, Rust only when the item is a
+#     simple key that fails (runtime.rs:1705-1711; every other error propagates through `?`)
+#     -> failing cases with a NULL map use simple-key items; without a NULL map only "it is an error" is compared;
+#   * Python's `$` also matches before a trailing newline -> cases where a tested text ends in a newline and the
+#     pattern does not end in '*' are dropped (detected by wrapping the twin's matcher).
+MAPS_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "python_twin_maps.json")
+EXAMPLES = "/root/reference/examples"
+
+
+def example_map_tasks():
+    """Every replace_map / goto_map task of the reference's example programs, loaded through the oracle's
+    restatement of parser.rs (the twin's own loader needs the json5 package)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    found = []
+
+    def walk(t, src):
+        if isinstance(t, dict):
+            if t.get("cmd") in ("replace_map", "goto_map"):
+                found.append((src, t))
+            for v in t.values():
+                walk(v, src)
+        elif isinstance(t, list):
+            for v in t:
+                walk(v, src)
+
+    for name in sorted(os.listdir(EXAMPLES)):
+        if name.endswith(".json5"):
+            kind, prog = orc.call("load_program", text=open(os.path.join(EXAMPLES, name), encoding="utf-8").read())
+            assert kind == "ok", (name, prog)
+            walk(prog, name)
+    return found
+
+
+def template_keys(twin, text):
+    """Names a template interpolates (top level and nested), by brute force over the text."""
+    return set(re.findall(r"\{([^{}]*)\}", text))
+
+
+def gen_maps():
+    import asyncio
+    twin = load_twin()
+    twin.log_sink = open(os.devnull, "w")
+    rng = random.Random(0x3A95)
+    unsafe = []
+    real_match = twin.is_wildcard_match
+
+    def watched(p, s):
+        if s.endswith("\n") and not p.endswith("*"):
+            unsafe.append((p, s))
+        return real_match(p, s)
+
+    twin.is_wildcard_match = watched
+    signal.signal(signal.SIGALRM, _alarm)
+
+    def run(task, ins):
+        """-> {"ok": value} | {"err": True} | None (dropped: outside the PY == RS subset, or does not terminate)"""
+        del unsafe[:]
+        st = {"inserts": json.loads(json.dumps(ins))}
+        t = dict(task, traceback_label="t")
+        signal.setitimer(signal.ITIMER_REAL, 0.5)
+        try:
+            r = asyncio.run(twin.execute_task(st, t, {}, {}, "x"))
+            if task["cmd"] == "goto_map":
+                res = {"ok": r["goto_target"] if r else "CONTINUE"}
+            else:
+                res = {"ok": st["inserts"][task["output_name"]]}
+        except (twin.InterpolationException, AssertionError):
+            res = {"err": True}
+        except (RecursionError, _Timeout, MemoryError):
+            return None
+        finally:
+            signal.setitimer(signal.ITIMER_REAL, 0)
+        return None if unsafe else res
+
+    words = ["look", "go north", "Hello   world", "a", "", "x  y", "the  door\n\n\n\nopens", " pad ", "1", "2", "3", "(none)",
+             "(unset)", "/undo", "/restart", "/summarize", "(peek)", "true", "false", "0", "first", "action", "query", "undo", "other",
+             "Morning", "Noon", "Evening", "Night", "Benjamin"]
+    tags = ["first-output", "action-output", "query-output", "query", "action"]
+
+    def llm_text():
+        parts = []
+        for _ in range(rng.randint(0, 5)):
+            r = rng.random()
+            if r < 0.5:
+                tg = rng.choice(tags)
+                parts.append("<%s>%s</%s>" % (tg, rng.choice(words), tg))
+            elif r < 0.75:
+                parts.append(rng.choice(["  ", " ", "\n", "\n\n\n", "\n\n\n\n", "   "]))
+            else:
+                parts.append(rng.choice(words))
+        return "".join(parts)
+
+    cases = []
+
+    def add(src, task, ins, loose=False):
+        r = run(task, ins)
+        if r is None:
+            return
+        c = {"src": src, "fn": task["cmd"], "inserts": ins, "py": r}
+        if loose:
+            c["loose"] = True  # both sides fail, with different messages: only "it is an error" is pinned
+        if task["cmd"] == "goto_map":
+            c["args"] = {"text": task["text"], "target_maps": task["target_maps"]}
+        else:
+            c["args"] = {"item": task["item"], "wildcard_maps": task["wildcard_maps"], "repeat_until_done": bool(task.get("repeat_until_done", False))}
+        cases.append(c)
+
+    # 1. the example programs' own maps against synthetic states
+    for src, task in example_map_tasks():
+        texts = [task["text"]] if task["cmd"] == "goto_map" else [task["item"]]
+        maps = task["target_maps"] if task["cmd"] == "goto_map" else task["wildcard_maps"]
+        for m in maps:
+            for k, v in m.items():
+                texts += [k] + ([v] if isinstance(v, str) else [])
+        keys = sorted(set().union(*[template_keys(twin, t) for t in texts]) - {"1", "2", "3", "4", "5", "6"})
+        item_keys = template_keys(twin, texts[0])
+        has_null = any("NULL" in m for m in maps)
+        simple_item = twin.get_simple_insertkey(texts[0]) is not None
+        for trial in range(40):
+            ins = {}
+            for k in keys:
+                if k == "history_text_base":
+                    ins[k] = llm_text()
+                elif simple_item and k in item_keys:
+                    ins[k] = rng.choice(words)  # a simple-key item that resolves to a number stays a number in Python, Rust renders it
+                else:
+                    ins[k] = rng.choice(words + [7, 12])
+            if trial % 8 == 7 and item_keys:  # the text / item does not resolve
+                del ins[sorted(item_keys)[0]]
+                if task["cmd"] == "replace_map" and not simple_item and has_null:
+                    continue  # Python: NULL map; Rust: the error propagates
+                add(src + ":%d" % task.get("line", 0), task, ins, loose=not has_null)
+            else:
+                add(src + ":%d" % task.get("line", 0), task, ins)
+
+    # 2. random maps over a small alphabet
+    lits = ["a", "b", "ab", "-", "/", " ", "x", "", "|"]
+
+    def rand_pattern():
+        return "".join(rng.choice(lits + ["*", "*", "{k}", "{n}"]) for _ in range(rng.randint(0, 5)))
+
+    def rand_value(ncap):
+        # capture references only up to the pattern's star count: without a star Python's findall yields the whole
+        # match as {1}, Rust's captures are empty
+        caps = ["{%d}" % rng.randint(1, ncap)] if ncap else []
+        return "".join(rng.choice(lits + caps + ["{k}", "{n}", "[", "]"]) for _ in range(rng.randint(0, 5)))
+
+    for trial in range(1500):
+        ins = {"k": rng.choice(["a", "b", "ab", "a-b", "", "x/x"]), "n": rng.randint(0, 12), "t": "".join(rng.choice("ab-/ x|") for _ in range(rng.randint(0, 8)))}
+        maps = []
+        for _ in range(rng.randint(1, 5)):
+            p = rand_pattern()
+            ncap = p.count("*")
+            maps.append({p: rand_value(ncap)})
+        if rng.random() < 0.3:
+            maps.insert(rng.randint(0, len(maps)), {"NULL": rng.choice(["fallback", "", "n{n}"])})
+        if rng.random() < 0.5:
+            item = rng.choice(["{t}", "{t}", "{k}", "{missing}", "{{q}}"])  # a simple key (resolves to a brace-free string, or fails)
+            ins["q"] = "k"
+        else:
+            item = "".join(rng.choice(lits + ["{k}", "{n}", "{t}"]) for _ in range(rng.randint(1, 5)))
+            if twin.get_simple_insertkey(item):
+                item += "."
+        fails = item == "{missing}"
+        has_null = any("NULL" in m for m in maps)
+        # entries that cannot resolve (a capture the pattern does not have) are reached only sometimes; with a NULL map
+        # Python would fall back where Rust propagates, so such cases are kept only without one
+        shape = rng.random()
+        if shape >= 0.8:  # goto_map has no captures
+            maps = [{k: re.sub(r"\{\d\}", "", v)} for m in maps for k, v in m.items()]
+        if shape < 0.6:
+            task = {"cmd": "replace_map", "item": item, "output_name": "out", "wildcard_maps": maps, "repeat_until_done": rng.random() < 0.5}
+        elif shape < 0.8:
+            if fails:
+                continue
+            it = rng.choice([[item, 5, None, "b-a"], {"key " + item: item, "z": [item]}])
+            task = {"cmd": "replace_map", "item": it, "output_name": "out", "wildcard_maps": maps, "repeat_until_done": False}
+        else:
+            tm = [{k: "T" + v} for m in maps for k, v in m.items()]
+            task = {"cmd": "goto_map", "text": item, "target_maps": tm}
+        r = run(task, ins)
+        if r is None:
+            continue
+        if task["cmd"] == "goto_map" and any(not resolves(twin, ins, s) for m in task["target_maps"] for kv in m.items() for s in kv):
+            continue  # Python resolves every entry up front, Rust only those it reaches
+        if "err" in r:
+            if has_null and not (task["cmd"] == "goto_map"):
+                continue
+            add("fuzz", task, ins, loose=True)
+        else:
+            add("fuzz", task, ins)
+    with open(MAPS_OUT, "w") as f:
+        json.dump({"cases": cases}, f, ensure_ascii=True, indent=0)
+    print({"maps_cases": len(cases), "errors": sum("err" in c["py"] for c in cases)})
+
+
+def resolves(twin, ins, s):
+    try:
+        twin.interpolate_inserts(ins, s)
+        return True
+    except Exception:
+        return False
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "maps":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "maps":
+        gen_maps()
