@@ -598,6 +598,36 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     // ---- P1: flat brace scan --------------------------------------------------------------------
     // Loads are issued P1_BATCH chunks ahead of the compares so that a thread keeps several HBM
     // requests in flight.
+#ifdef IE_TMA_TEXT
+    // EXPERIMENT (profiles/r02_tma_experiment.md): the tile's text is brought into shared memory by ONE bulk copy of
+    // the TMA unit (cp.async.bulk + mbarrier transaction count); the scan then reads its chunks from shared memory.
+    extern __shared__ __align__(128) uint8_t tma_text[];
+    __shared__ __align__(8) uint64_t tma_bar;
+    if (!too_big) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar), dst = (uint32_t)__cvta_generic_to_shared(tma_text);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_chunks * 16u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(a0),
+                         "r"(n_chunks * 16u), "r"(bar)
+                         : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+        for (uint32_t c = tid; c < n_chunks; c += NT) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tma_text + (size_t)c * 16);
+            const uint32_t pv = c ? tma_text[c * 16 - 1] : 0u;  // the byte before the chunk (chunk 0: before the tile, blanked anyway)
+            sm.u.scan.cm[c] = scan_chunk(v, c * 16 > lead ? pv : 0u, (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
+        }
+        __syncthreads();
+        if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    }
+#else
     if (!too_big) {
         for (uint32_t cb = tid; cb < n_chunks; cb += NT * P1_BATCH) {
             uint4 v[P1_BATCH];
@@ -618,6 +648,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
             }
         }
     }
+#endif
     PHASE_MARK(1);
     __syncthreads();
     PHASE_MARK(2);
@@ -824,24 +855,14 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     // Every tile's output starts 16-byte aligned (totals are rounded up), so the chunk structure of the
     // copy sweep does not depend on the tile's global offset: the total is published first, the segment
     // table is built from tile-local offsets, and only then does the look-back collect the predecessors.
-    uint64_t tile_pad64, tile_out64;  // rounded up to 16 (what successors skip) / bytes actually produced
-    const uint32_t loc = (uint32_t)ie_scan::local_scan(sm.scan, olen, 15, &tile_pad64, &tile_out64);
-    // tile-local exclusive scan of segment counts
-    uint32_t sincl = nseg;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, sincl, d);
-        if ((int)lane >= d) sincl += y;
-    }
-    if (lane == 31) sm.warp_scan[warp] = sincl;
-    __syncthreads();
-    uint32_t sbase = 0, total_seg = 0;
-#pragma unroll
-    for (int wv = 0; wv < NW; ++wv) {
-        if (wv < (int)warp) sbase += sm.warp_scan[wv];
-        total_seg += sm.warp_scan[wv];
-    }
-    sbase += sincl - nseg;
+    // ONE scan carries both per-template quantities: output bytes in the low 40 bits, copy segments above them.
+    constexpr uint64_t LOW40 = (1ull << 40) - 1;
+    const uint64_t packed = ((uint64_t)nseg << 40) | olen;
+    uint64_t tile_packed;
+    const uint64_t excl = ie_scan::local_scan(sm.scan, packed, 0, &tile_packed);
+    const uint32_t loc = (uint32_t)(excl & LOW40), sbase = (uint32_t)(excl >> 40), total_seg = (uint32_t)(tile_packed >> 40);
+    const uint64_t tile_out64 = tile_packed & LOW40;              // bytes actually produced
+    const uint64_t tile_pad64 = (tile_out64 + 15) & ~15ull;       // rounded up to 16: what the tile claims
     const uint32_t tile_out = (uint32_t)tile_out64;
     const uint32_t olead = (uint32_t)((uintptr_t)out & 15);  // tile offsets are multiples of 16
     const uint32_t o_chunks = (olead + tile_out + 15) >> 4;
@@ -999,6 +1020,19 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) ie_resolve_tile_kernel(const 
     uint32_t state, tile_nt;
     uint64_t tile_i0;
     if (!tile_geometry<ROUNDS>(blockIdx.x, tiles_per_state, n, tt, rd, state, tile_i0, tile_nt)) return;
+#ifdef IE_L2_PREFETCH
+    // One thread asks the TMA unit to pull the text of the tile that will run IE_L2_PREFETCH tiles later (about one
+    // wave of resident CTAs) into L2: a single cp.async.bulk.prefetch, no shared memory, no wait.
+    if (threadIdx.x == NT - 1 && !(ROUNDS && rd.n_dev)) {
+        const uint64_t j0 = tile_i0 + (uint64_t)IE_L2_PREFETCH * tt;
+        if (j0 < n) {
+            const uint64_t j1 = min(n, j0 + tt);
+            const uintptr_t a = ((uintptr_t)tmpl + __ldg(offs + j0)) & ~(uintptr_t)15;
+            const uintptr_t b = ((uintptr_t)tmpl + __ldg(offs + j1) + 15) & ~(uintptr_t)15;
+            if (b > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(b - a)) : "memory");
+        }
+    }
+#endif
     {
         const IeTableView tv = views[state];
         if (resolve_range<ROUNDS>(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias, rd,
@@ -1029,12 +1063,21 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
                                     cudaStream_t stream) {
     if (rd.n_dev) tt = IE_ROUND_MIN_TILE;       // rounds >= 2: n is the upper bound, the kernel reads the real count and picks tt >= this
     const uint64_t tiles = (n + tt - 1) / tt;
+#if defined(IE_TMA_TEXT) || defined(IE_DUMMY_DSMEM)
+    // experiment builds: dynamic shared memory for the staged tile text (IE_TMA_TEXT) or the same amount left unused
+    // (IE_DUMMY_DSMEM: the occupancy control of the experiment)
+    const size_t dsm = (size_t)M_CAP * 16;
+    cudaFuncSetAttribute(ie_resolve_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(ie_resolve_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+#else
+    const size_t dsm = 0;
+#endif
     if (rd.allow_splice)
-        ie_resolve_tile_kernel<true><<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap,
+        ie_resolve_tile_kernel<true><<<(unsigned)(tiles * n_states), NT, dsm, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap,
                                                                                       d_out_offs, d_out_lens, d_status, d_aux, ws, d_info, out_bias,
                                                                                       tt, rd);
     else
-    ie_resolve_tile_kernel<false><<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
+    ie_resolve_tile_kernel<false><<<(unsigned)(tiles * n_states), NT, dsm, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status,
                                                               d_aux, ws, d_info, out_bias, tt, rd);
     return cudaGetLastError();
 }

@@ -513,6 +513,59 @@ def test_replace_map_goto_map_on_gpu(eng, oracle):
     assert list(first) == [1, 2, 2, 0]
 
 
+def test_maps_golden_vectors_on_gpu(eng, oracle):
+    """replace_map / goto_map against the vectors the reference's own Python twin produced (oracle/gen_golden.py maps):
+    the example programs' maps on synthetic states + a fuzz set on the PY == RS subset, through the GPU path."""
+    from tests.test_oracle_golden import MAPS_GOLDEN, check_maps_case
+    with open(MAPS_GOLDEN) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) > 2000
+    for c in cases:
+        check_maps_case(eng.call, c)
+        got, want = both(eng, oracle, c["fn"], inserts=c["inserts"], **c["args"])  # and byte-identical to the oracle, messages included
+        assert_same(got, want, c)
+
+
+def test_small_mirror_functions_on_gpu(eng, oracle):
+    """get_simple_insertkey / value_to_string / extract_insert_keys (interp.rs:11-29, 248-322) through ie_call_json, on the
+    golden `simple_key` list (pinned to the Python twin) and on fuzzed trees (against the oracle)."""
+    with open(GOLDEN) as f:
+        golden = json.load(f)
+    for case in golden["simple_key"]:
+        got, want = both(eng, oracle, "get_simple_insertkey", content=case["content"])
+        assert got == want, (case, got, want)
+        if case["py"] is not None:  # the twin reports '' as None (falsy); Rust returns Some("")
+            assert got == ("ok", case["py"]), (case, got)
+    rng = random.Random(0xA10)
+    atoms = ["{", "}", "{", "}", BS, "a", "b", ".", " ", "\u3020", "k-", "\n", "\u00e9"]
+
+    def rand_str():
+        return "".join(rng.choice(atoms) for _ in range(rng.randint(0, 9)))
+
+    def rand_tree(depth=0):
+        r = rng.random()
+        if depth > 2 or r < 0.45:
+            return rand_str()
+        if r < 0.55:
+            return rng.choice([0, -7, 12345678901, 2.5, -0.125, 1e21, True, False, None])
+        if r < 0.78:
+            return [rand_tree(depth + 1) for _ in range(rng.randint(0, 4))]
+        return {rand_str(): rand_tree(depth + 1) for _ in range(rng.randint(0, 4))}
+
+    for _ in range(400):
+        v = rand_tree()
+        for fn in ("value_to_string", "extract_insert_keys"):
+            got, want = both(eng, oracle, fn, value=v)
+            assert got == want, (fn, v, got, want)
+        if isinstance(v, str):
+            got, want = both(eng, oracle, "get_simple_insertkey", content=v)
+            assert got == want, (v, got, want)
+    # hand-checked anchors (interp.rs:273-312: top-level groups only, a backslash drops itself and keeps the next char)
+    assert eng.call("extract_insert_keys", value="a{b{c}}d{e}" + BS + "{f" + BS + "}{g" + BS + "}h}")[1] == ["b{c}", "e", "g}h"]
+    assert eng.call("extract_insert_keys", value={"{k}": ["x{y}", 3, {"z": "{w}"}]})[1] == ["k", "y", "w"]
+    assert eng.call("value_to_string", value=[1, "a", [True, None], {"b": 2, "a": "x"}])[1] == '1atruenull{"a":"x","b":2}'
+
+
 def test_first_match_few_long_texts(eng, oracle):
     """ie_glob_first_match with up to 256 keys runs one CTA per text (ie_glob_first_long_kernel): kilobyte texts, patterns
     longer than the sweep kernel's 3584-byte block, more than IE_MAX_PATTERNS patterns, every piece arrangement; against
