@@ -182,7 +182,7 @@ def main():
         return torch.from_numpy(np.ascontiguousarray(a).view(dtype)).to(dev)
 
     sets = []
-    info_bytes = 32
+    info_bytes = 64  # sizeof(ie_batch_info) = 40
     for sh in shards:
         d_t = to_dev(sh.bytes, np.uint8)
         d_o = to_dev(sh.offs.view(np.int64), np.int64)

@@ -12,7 +12,9 @@
  * overlap (the reference calls the resolver from one thread, interp.rs is synchronous).  Use one engine
  * per host thread or per GPU; tables belong to the engine that packed them.  Host-buffer results stay
  * owned by the engine until its next call.  Device-buffer calls are asynchronous on the given stream
- * and share the engine's workspace: issue them on one stream at a time.
+ * and share the engine's workspace (counters, index lists, the general path's scratch): ONE device-buffer call
+ * in flight per engine - issue them on one stream, or order them with events; a second engine on the same
+ * device gives a second workspace.
  *
  * Data layout conventions
  *   string arenas   : `bytes` + `offs[n+1]` (uint64, offs[0]=0, offs[n]=total bytes), no separators
@@ -63,7 +65,15 @@ typedef struct ie_engine ie_engine; /* one per (process, device): stream, stagin
 typedef struct ie_table ie_table;   /* device-resident packed `inserts` map (immutable snapshot) */
 
 /* Expansion bounds.  The reference has none (a self-referential insert loops forever,
- * interp.rs:54); exceeding one yields IE_RES_LIMIT for that template only. */
+ * interp.rs:54); exceeding one yields IE_RES_LIMIT for that template only.
+ * A field left 0 takes its default, and the defaults are only where a template STARTS: the host-buffer
+ * calls (ie_resolve_batch and everything built on it) re-run a template that hit a default bound with
+ * 8x the bound, again and again, up to IE_HARD_MAX_EXPANSIONS / IE_HARD_MAX_RESULT_BYTES, so that every
+ * input on which the reference terminates within those caps resolves instead of reporting a limit.
+ * A bound the caller sets explicitly is final.  The device-buffer call never escalates (no host in the
+ * loop): ie_batch_info.n_limit tells the caller how many templates stopped at its bounds. */
+#define IE_HARD_MAX_EXPANSIONS (1u << 17)
+#define IE_HARD_MAX_RESULT_BYTES (1u << 26)
 typedef struct {
     uint32_t max_expansions;   /* lookups per template on the general path (default 4096)       */
     uint32_t max_result_bytes; /* bytes of intermediate/final text per template on the general
@@ -85,6 +95,7 @@ typedef struct {
     uint64_t n;           /* templates processed */
     uint64_t out_bytes;   /* bytes used in the out arena (needed size when IE_E_OVERFLOW)        */
     uint64_t n_general;   /* templates that took the general (slow) path                         */
+    uint64_t n_limit;     /* templates whose status is IE_RES_LIMIT                               */
     float kernel_ms;      /* device time of the resolve kernels (CUDA events), host API only     */
 } ie_batch_info;
 
@@ -140,6 +151,9 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
 
 /* Device-buffer form (inputs and outputs already resident in HBM; asynchronous on `stream`,
  * which may be NULL for the engine's own stream).  `d_info` is a device ie_batch_info. */
+/* When the out arena is too small, d_info->out_bytes > out_capacity afterwards; it is then a LOWER bound of the
+ * need (stages behind the overflowing one are skipped) and results whose range lies beyond out_capacity were not
+ * written: regrow to at least twice the capacity and rerun, as ie_resolve_batch does. */
 ie_status_t ie_resolve_batch_device(ie_engine* e, const ie_table* t, const uint8_t* d_tmpl, const uint64_t* d_tmpl_offs,
                                     uint64_t n, const ie_limits* limits, uint8_t* d_out, uint64_t out_capacity,
                                     uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
@@ -157,7 +171,10 @@ ie_status_t ie_lookup_batch(ie_engine* e, const ie_table* t, const uint8_t* keys
 ie_status_t ie_escape_batch(ie_engine* e, int mode, const uint8_t* in, const uint64_t* in_offs, uint64_t n,
                             const uint8_t** out, const uint64_t** out_offs);
 /* device arenas: in_bytes >= d_in_offs[n] - d_in_offs[0] (the caller knows its arena; it sizes the
- * tile bookkeeping without a device->host read); d_out_offs gets n + 1 entries */
+ * tile bookkeeping without a device->host read); d_out_offs gets n + 1 entries.  The call is asynchronous
+ * and cannot report a too-small arena through its return value: d_out_offs[n] always receives the bytes
+ * the output needs, and when it exceeds out_capacity the arena and the other offsets are incomplete
+ * (escape at most doubles its input, unescape never grows it: size the arena accordingly). */
 ie_status_t ie_escape_batch_device(ie_engine* e, int mode, const uint8_t* d_in, const uint64_t* d_in_offs, uint64_t n,
                                    uint64_t in_bytes, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offs,
                                    void* stream);

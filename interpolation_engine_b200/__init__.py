@@ -35,7 +35,7 @@ class EngineError(RuntimeError):
 
 class _BatchInfo(ctypes.Structure):
     _fields_ = [("n", ctypes.c_uint64), ("out_bytes", ctypes.c_uint64), ("n_general", ctypes.c_uint64),
-                ("kernel_ms", ctypes.c_float)]
+                ("n_limit", ctypes.c_uint64), ("kernel_ms", ctypes.c_float)]
 
 
 class _Result(ctypes.Structure):

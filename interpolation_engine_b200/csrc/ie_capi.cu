@@ -49,6 +49,18 @@ struct PinBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grows to at least `bytes`, keeping the first `keep` bytes
+    cudaError_t grow_keep(size_t bytes, size_t keep) {
+        if (bytes <= cap) return cudaSuccess;
+        void* q = nullptr;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (p && keep) std::memcpy(q, p, keep);
+        if (p) cudaFreeHost(p);
+        p = q; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
@@ -68,7 +80,7 @@ struct ie_engine {
     DevBuf ws_zero, ws_list, ws_scratch;
     uint32_t tcap = 0;
     // host-API staging
-    DevBuf d_in, d_in_offs, d_out, d_out_offs, d_out_lens, d_status, d_aux, d_info, d_mask, d_misc;
+    DevBuf d_in, d_in_offs, d_out, d_out_offs, d_out_lens, d_status, d_aux, d_info, d_mask, d_misc, d_esc;
     PinBuf h_out, h_out_offs, h_out_lens, h_status, h_aux, h_info;
     // small batches (one task at a time, the reference's interactive shape): one staging block each way
     DevBuf d_small_in, d_small_res;
@@ -125,7 +137,7 @@ ie_status_t prepare_workspace(ie_engine* e, uint64_t n, uint32_t tcap, bool need
             ws->round_offs = (uint64_t*)(ws->general_list + me * 6);  // me even: 24 me bytes, 8-byte aligned
         }
         if (tcap > e->tcap || !e->ws_scratch.p) {
-            CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ((size_t)tcap + IE_KEY_SCRATCH), e->stream));
+            CU(e->ws_scratch.ensure((size_t)IE_GENERAL_WORKERS * ie_general_worker_bytes(tcap), e->stream));
             e->tcap = tcap;
         }
         ws->scratch = (uint8_t*)e->ws_scratch.p;
@@ -202,7 +214,7 @@ void ie_engine_destroy(ie_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (DevBuf* b : {&e->ws_zero, &e->ws_list, &e->ws_scratch, &e->d_in, &e->d_in_offs, &e->d_out, &e->d_out_offs, &e->d_out_lens,
-                      &e->d_status, &e->d_aux, &e->d_info, &e->d_mask, &e->d_misc, &e->d_small_in, &e->d_small_res})
+                      &e->d_status, &e->d_aux, &e->d_info, &e->d_mask, &e->d_misc, &e->d_esc, &e->d_small_in, &e->d_small_res})
         b->release();
     for (PinBuf* b : {&e->h_out, &e->h_out_offs, &e->h_out_lens, &e->h_status, &e->h_aux, &e->h_info, &e->h_small_in, &e->h_small_res})
         b->release();
@@ -463,7 +475,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
     }
     CU(cudaEventRecord(e->ev1, sc));
     bool overflow = false;
-    uint64_t n_general = 0;
+    uint64_t n_general = 0, n_limit = 0;
     double worst = 0.0;
     for (uint64_t k = 0; k < K; ++k) {
         const uint64_t lo = cut[k], hi = cut[k + 1];
@@ -472,6 +484,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         const uint64_t ib = tmpl_offs[hi] - tmpl_offs[lo];
         if (ib) worst = std::max(worst, (double)ob / (double)ib);
         n_general += hinfo[k].n_general;
+        n_limit += hinfo[k].n_limit;
         if (ob > base[k + 1] - base[k]) { overflow = true; continue; }
         if (overflow) continue;
         if (ob) CU(cudaMemcpyAsync((uint8_t*)e->h_out.p + base[k], (uint8_t*)e->d_out.p + base[k], ob, cudaMemcpyDeviceToHost, e->s_out));
@@ -488,6 +501,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
     CU(cudaStreamSynchronize(sc));
     if (worst * 1.1 > e->expand) e->expand = worst * 1.25;
     if (overflow) return IE_OK;
+    if (n_limit && !(limits && limits->max_expansions && limits->max_result_bytes)) return IE_OK;  // a default bound was hit: the unpipelined route escalates
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     res->out = (const uint8_t*)e->h_out.p;
@@ -498,6 +512,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
     res->info.n = n;
     res->info.out_bytes = base[K];
     res->info.n_general = n_general;
+    res->info.n_limit = n_limit;
     res->info.kernel_ms = ms;  // first launch to last kernel end, copies overlapped
     *done = true;
     return IE_OK;
@@ -539,6 +554,7 @@ static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t*
     CU(cudaStreamSynchronize(s));
     const ie_batch_info* hi = (const ie_batch_info*)(hres + a_info);
     if (hi->out_bytes > kSmallArena) return IE_OK;  // too much output for this route
+    if (hi->n_limit && !(limits && limits->max_expansions && limits->max_result_bytes)) return IE_OK;  // a default bound was hit: the general route escalates
     if (a_arena + hi->out_bytes > first) {
         CU(cudaMemcpyAsync(hres + first, dres + first, a_arena + hi->out_bytes - first, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
@@ -554,6 +570,86 @@ static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t*
     res->info.n = nr;
     res->info.kernel_ms = ms;
     *done = true;
+    return IE_OK;
+}
+
+// Templates that stopped at a DEFAULT bound are run again on the full-size general tier with 8x the bounds, level by
+// level, up to the hard caps of the header: "limit" then means "the reference would not finish within the caps", not
+// "deeper than this engine's first guess".  Works on the engine-buffer layout of the host routes: templates in e->d_in /
+// e->d_in_offs, per-template results in e->d_out_offs ... e->d_aux and their pinned mirrors; escalated result bytes are
+// appended to the host arena at *host_bytes.  A bound the caller fixed is never raised.
+static ie_status_t escalate_limits(ie_engine* e, const ie_table* t, uint64_t n, uint64_t nr, const ie_limits* limits, uint64_t* host_bytes,
+                                   uint64_t* n_limit_left) {
+    cudaStream_t s = e->stream;
+    const bool exp_fixed = limits && limits->max_expansions, rb_fixed = limits && limits->max_result_bytes;
+    uint32_t max_exp, tcap;
+    resolve_limits(limits, &max_exp, &tcap);
+    int32_t* h_status = (int32_t*)e->h_status.p;
+    std::vector<uint32_t> list;
+    for (uint64_t r = 0; r < nr; ++r)
+        if ((h_status[r] & 0xFF) == IE_RES_LIMIT) list.push_back((uint32_t)r);
+    while (!list.empty()) {
+        const uint32_t exp2 = exp_fixed ? max_exp : (uint32_t)std::min<uint64_t>((uint64_t)max_exp * 8, IE_HARD_MAX_EXPANSIONS);
+        const uint32_t tcap2 = rb_fixed ? tcap : (uint32_t)std::min<uint64_t>((uint64_t)tcap * 8, IE_HARD_MAX_RESULT_BYTES);
+        if (exp2 == max_exp && tcap2 == tcap) break;  // nothing left to raise
+        max_exp = exp2; tcap = tcap2;
+        const uint64_t count = list.size();
+        // few workers with a large scratch each: at most 1 GiB of scratch in total
+        const size_t per_worker = ie_general_worker_bytes(tcap);
+        const uint32_t workers = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>({count, (uint64_t)IE_GENERAL_WORKERS, (1ull << 30) / per_worker}));
+        IeWorkspace ws{};
+        CU(e->d_esc.ensure((size_t)workers * per_worker + 256, s));
+        ws.scratch = (uint8_t*)e->d_esc.p;
+        ws.general_workers = workers;
+        static_assert(sizeof(ie_batch_info) <= 112, "d_misc layout: [count, overflow | info at 16 | list at 128]");
+        CU(e->d_misc.ensure(128 + count * 4, s));
+        uint32_t* d_count = (uint32_t*)e->d_misc.p;
+        ie_batch_info* d_info2 = (ie_batch_info*)((uint8_t*)e->d_misc.p + 16);
+        uint32_t* d_list = (uint32_t*)((uint8_t*)e->d_misc.p + 128);
+        ws.overflow = d_count + 1;
+        const uint32_t head[2] = {(uint32_t)count, 0u};
+        CU(cudaMemcpyAsync(d_count, head, sizeof head, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_list, list.data(), count * 4, cudaMemcpyHostToDevice, s));
+        // the escalated results go to the start of the engine's out arena (its content is on the host already)
+        uint64_t cap = e->d_out.cap;
+        ie_batch_info info2{};
+        for (int attempt = 0;; ++attempt) {
+            CU(cudaMemsetAsync(d_info2, 0, sizeof(ie_batch_info), s));
+            CU(ie_launch_general_escalate(t->d_views, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (uint8_t*)e->d_out.p, cap,
+                                          (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p, (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, ws,
+                                          d_info2, max_exp, tcap, *host_bytes, d_list, d_count, s));
+            CU(cudaMemcpyAsync(&info2, d_info2, sizeof info2, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if (info2.out_bytes <= cap) break;
+            if (attempt == 1) return fail(IE_E_OVERFLOW, "ie_resolve_batch: output arena overflow while escalating limits");
+            CU(e->d_out.ensure(info2.out_bytes, s));
+            cap = e->d_out.cap;
+        }
+        // append the bytes, refresh the per-template entries of the escalated templates
+        CU(e->h_out.grow_keep(*host_bytes + info2.out_bytes + 1, *host_bytes));
+        if (info2.out_bytes) CU(cudaMemcpyAsync((uint8_t*)e->h_out.p + *host_bytes, e->d_out.p, info2.out_bytes, cudaMemcpyDeviceToHost, s));
+        if (count <= 64) {
+            for (uint32_t r : list) {
+                CU(cudaMemcpyAsync((uint64_t*)e->h_out_offs.p + r, (uint64_t*)e->d_out_offs.p + r, 8, cudaMemcpyDeviceToHost, s));
+                CU(cudaMemcpyAsync((uint32_t*)e->h_out_lens.p + r, (uint32_t*)e->d_out_lens.p + r, 4, cudaMemcpyDeviceToHost, s));
+                CU(cudaMemcpyAsync((int32_t*)e->h_status.p + r, (int32_t*)e->d_status.p + r, 4, cudaMemcpyDeviceToHost, s));
+                CU(cudaMemcpyAsync((uint32_t*)e->h_aux.p + r, (uint32_t*)e->d_aux.p + r, 4, cudaMemcpyDeviceToHost, s));
+            }
+        } else {
+            CU(cudaMemcpyAsync(e->h_out_offs.p, e->d_out_offs.p, nr * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(e->h_out_lens.p, e->d_out_lens.p, nr * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, nr * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(e->h_aux.p, e->d_aux.p, nr * 4, cudaMemcpyDeviceToHost, s));
+        }
+        CU(cudaStreamSynchronize(s));
+        *host_bytes += (info2.out_bytes + 15) & ~uint64_t(15);
+        h_status = (int32_t*)e->h_status.p;
+        std::vector<uint32_t> next;
+        for (uint32_t r : list)
+            if ((h_status[r] & 0xFF) == IE_RES_LIMIT) next.push_back(r);
+        list.swap(next);
+    }
+    *n_limit_left = list.size();
     return IE_OK;
 }
 
@@ -589,7 +685,11 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, tmpl_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
     float kernel_ms = 0.f;
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    // An overflowing run skips the stages behind the one that overflowed (a rescan round whose gather did not fit
+    // reserves nothing for the rounds after it), so the size it reports is a lower bound: regrow to at least twice the
+    // arena, rerun, and repeat until a run fits - every attempt gets at least one stage further.
+    const int max_attempts = 8;
+    for (int attempt = 0;; ++attempt) {
         CU(cudaEventRecord(e->ev0, s));
         ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
                                         (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p,
@@ -601,8 +701,8 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
         CU(cudaStreamSynchronize(s));
         CU(cudaEventElapsedTime(&kernel_ms, e->ev0, e->ev1));
         if (hinfo->out_bytes <= e->d_out.cap) break;
-        if (attempt == 2) return fail(IE_E_OVERFLOW, "ie_resolve_batch: output arena overflow after regrow");
-        CU(e->d_out.ensure(hinfo->out_bytes, s));  // out arena was too small: regrow to the exact need and rerun
+        if (attempt + 1 == max_attempts) return fail(IE_E_OVERFLOW, "ie_resolve_batch: output arena overflow after regrowing it " + std::to_string(max_attempts - 1) + " times");
+        CU(e->d_out.ensure(std::max<uint64_t>(hinfo->out_bytes, 2 * (uint64_t)e->d_out.cap), s));
     }
     const uint64_t ob = hinfo->out_bytes;
     CU(e->h_out.ensure(ob + 1));
@@ -618,12 +718,20 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
         CU(cudaMemcpyAsync(e->h_aux.p, e->d_aux.p, nr * 4, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
+    ie_batch_info info = *hinfo;
+    if (info.n_limit) {  // templates that stopped at a default bound: larger bounds, up to the hard caps
+        uint64_t host_bytes = (ob + 15) & ~uint64_t(15), left = 0;
+        ie_status_t st = escalate_limits(e, t, n, nr, limits, &host_bytes, &left);
+        if (st != IE_OK) return st;
+        info.out_bytes = host_bytes;
+        info.n_limit = left;
+    }
     res->out = (const uint8_t*)e->h_out.p;
     res->out_offs = (const uint64_t*)e->h_out_offs.p;
     res->out_lens = (const uint32_t*)e->h_out_lens.p;
     res->status = (const int32_t*)e->h_status.p;
     res->aux = (const uint32_t*)e->h_aux.p;
-    res->info = *hinfo;
+    res->info = info;
     res->info.n = nr;
     res->info.kernel_ms = kernel_ms;
     return IE_OK;

@@ -286,7 +286,13 @@ __global__ void __launch_bounds__(NT, ESC_CTAS) ie_escape_kernel(int mode, const
         uint64_t gbase = ie_scan::lookback_wide<NT, 2>(sm.scan, ws.tile_state, span, span_total);
         PHASE_MARK(3);
         TRACE(span, 2);
-        if (gbase + span_total > out_cap) { if (tid == 0) *ws.overflow = 1u; continue; }
+        if (gbase + span_total > out_cap) {
+            // The caller's arena is too small: nothing is written for this span.  The LAST span still publishes the
+            // total the output needs as out_offs[n], so that the caller can tell (out_offs[n] > out_capacity) and size
+            // its arena; the other offsets are incomplete then.
+            if (tid == 0) { *ws.overflow = 1u; if (tile_lo + nt == tiles) out_offs[n] = gbase + span_total; }
+            continue;
+        }
 
         // ---- pass 2: tile by tile, positions known ---------------------------------------------------------------
         for (uint32_t m = 0; m < nt; ++m) {

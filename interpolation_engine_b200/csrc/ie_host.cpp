@@ -365,17 +365,22 @@ struct Session {
             ie_result r;
             check(ie_resolve_batch(e, table, t.data(), t.offs.data(), t.n(), nullptr, &r));
             bool grew = false;
+            // First everything out of the engine's result buffers (they are only valid until the next call on the
+            // engine) ...
             for (size_t i = 0; i < templates.size(); ++i) {
                 Outcome& oc = out[i];
                 oc.code = IE_RES_CODE(r.status[i]);
                 oc.bytes.assign((const char*)r.out + r.out_offs[i], r.out_lens[i]);
                 if (oc.code == IE_RES_TYPED) oc.typed = entry_value(r.aux[i]);
-                if (oc.code == IE_RES_NOT_FOUND && has_dir) {
+            }
+            // ... then the directory probes: escaping a file's value is another call on the same engine
+            if (has_dir)
+                for (Outcome& oc : out) {
+                    if (oc.code != IE_RES_NOT_FOUND) continue;
                     if (probe_dir(oc.bytes)) grew = true;
                     auto de = dir_errors.find(oc.bytes);
                     if (de != dir_errors.end()) oc.io_error = de->second;
                 }
-            }
             if (!grew) break;
             pack();
         }
@@ -934,6 +939,17 @@ JVal dispatch(ie_engine* e, const JVal& args) {
         for (auto& kv : ins) { const bool m = (any[k >> 5] >> (k & 31)) & 1u; if (m != except) doomed.push_back(kv.first); ++k; }
         for (auto& d : doomed) { ins.erase(d); deleted.push_back(JVal::str(d)); }
         return JVal::obj({{"deleted", JVal::arr(std::move(deleted))}, {"inserts", JVal::obj(std::move(ins))}});
+    }
+    if (fn == "interpolation_trace") {  // what recursive_interpolate(value) sends to the resolver, in order: the batch of a replayed program
+        Gather g;
+        gather(arg(args, "value"), g);
+        JArr t, l;
+        for (auto& x : g.templates) t.push_back(JVal::str(x));
+        for (auto& x : g.lookups) l.push_back(JVal::str(x));
+        JObj o;
+        o["templates"] = JVal::arr(std::move(t));
+        o["lookups"] = JVal::arr(std::move(l));
+        return JVal::obj(std::move(o));
     }
     if (fn == "add_line_numbers") return JVal::str(add_line_numbers(sarg(args, "text")));  // parser.rs:74
     if (fn == "load_program") return load_program(sarg(args, "text"));                      // parser.rs:8

@@ -17,6 +17,11 @@
 #define IE_GENERAL_SMALL_TEXT 1792u
 #define IE_GENERAL_SMALL_KEY 256u
 
+// Frame-stack entries (16 bytes each) of a full-size general-path worker with a text scratch of tcap bytes, and the
+// worker's whole scratch: [text tcap][key IE_KEY_SCRATCH][frames].
+inline uint32_t ie_general_fcap(uint32_t tcap) { return tcap / 64 + 64; }
+inline size_t ie_general_worker_bytes(uint32_t tcap) { return (size_t)tcap + IE_KEY_SCRATCH + (size_t)ie_general_fcap(tcap) * 16; }
+
 // Per-engine device workspace.  [zero_base, zero_base + zero_bytes) is cleared before a batch.
 struct IeWorkspace {
     uint8_t* zero_base;
@@ -36,7 +41,7 @@ struct IeWorkspace {
     struct IeRoundCtl* round_ctl;
     uint32_t* round_list[3];
     uint64_t* round_offs;     // [n + 1]
-    uint8_t* scratch;         // general_workers * (tcap + IE_KEY_SCRATCH)
+    uint8_t* scratch;         // general_workers * ie_general_worker_bytes(tcap)
     uint32_t general_workers;
 };
 
@@ -46,6 +51,11 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
                               uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, cudaStream_t stream);
+
+cudaError_t ie_launch_general_escalate(const IeTableView* d_views, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                                       uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                       const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap, uint64_t out_bias,
+                                       const uint32_t* d_list, const uint32_t* d_count, cudaStream_t stream);
 
 // Rescan rounds (interp.rs:81-83 rescans every spliced value): a template whose lookups returned values with properly
 // nested groups of their own is written out with those values in place ("spliced") and resolved again as a template

@@ -19,7 +19,8 @@
 namespace {
 
 using namespace ie_dev;
-constexpr uint32_t MAXF = 24;   // splice depth of the general path
+constexpr uint32_t MAXF = 24;   // splice depth of the general path's first tier (frames in registers / local memory); deeper
+                                // stacks go to the full-size tier, whose frames live in its global scratch
 
 // ---- general path ----------------------------------------------------------------------------
 struct Frame {
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
                                                                 uint32_t max_expansions, uint32_t tcap, uint32_t kcap, uint64_t out_bias,
                                                                 const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
                                                                 uint32_t* __restrict__ retry_list, uint32_t* __restrict__ retry_count,
-                                                                uint32_t smem_stride) {
+                                                                uint32_t smem_stride, uint32_t fcap) {
     // Two tiers share this kernel: many workers with a small scratch each take the punted templates first
     // (retry_list != nullptr: a template that outgrows the small scratch is queued there, nothing is written for
     // it), then a few workers with the full-size scratch take the queue.
@@ -188,15 +189,23 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
     // lanes join for the bulk passes around the machine (brace count, result copies).
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t worker = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_workers = (gridDim.x * blockDim.x) >> 5;
+    // the full-size tier has ws.general_workers scratch areas, which need not fill the last block
+    const uint32_t grid_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_workers = SMEM ? grid_warps : min(grid_warps, ws.general_workers);
+    if (worker >= n_workers) return;
     const uint32_t count = *list_count;
     if (worker == 0 && lane == 0 && count && retry_list) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_general), (unsigned long long)count);
     // The machine re-reads what it just wrote, byte by byte: in global memory every such read is an L2 round trip
     // (stores do not allocate in L1).  Tier 1 therefore keeps its small scratch in SHARED memory (smem_stride != 0,
     // skewed by 4 bytes per thread against bank conflicts); tier 2 uses the big global scratch.
     extern __shared__ __align__(16) uint8_t gen_smem[];
-    uint8_t* T = SMEM ? gen_smem + (size_t)(threadIdx.x >> 5) * smem_stride : ws.scratch + (size_t)worker * ((size_t)tcap + kcap);
+    // per worker: [text tcap][key kcap][frame stack fcap * 16]  (tier 1: text and key in shared memory, MAXF local frames)
+    uint8_t* T = SMEM ? gen_smem + (size_t)(threadIdx.x >> 5) * smem_stride
+                      : ws.scratch + (size_t)worker * ((size_t)tcap + kcap + (size_t)fcap * sizeof(Frame));
     uint8_t* kscr = T + tcap;
+    Frame local_frames[SMEM ? MAXF : 1];
+    Frame* const frames = SMEM ? local_frames : reinterpret_cast<Frame*>(kscr + kcap);
+    const uint32_t max_frames = SMEM ? MAXF : fcap;
 
     for (uint32_t q = worker; q < count; q += n_workers) {
         const uint32_t r = list[q];                         // result index = state * per_state + template
@@ -210,7 +219,6 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
         if (lane == 0) while (is_simple_range(t, lo, hi)) { ++lo; --hi; ++m; }
         lo = __shfl_sync(FULL, lo, 0); hi = __shfl_sync(FULL, hi, 0); m = __shfl_sync(FULL, m, 0);
 
-        Frame frames[MAXF];
         uint32_t nf = 0, ttop = tcap, in_open = 0, in_close = 0, t_close = 0, expansions = 0;
         uint32_t status = IE_RES_STRING, aux = 0;
         const uint8_t* payload = nullptr;  // final bytes when not in T
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
                 if (f.pos == 0) --nf;
                 const uint32_t vlen = IE_SLOT_VLEN(s->vl_tf);
                 if (vlen) {
-                    if (nf == MAXF) { status = IE_RES_LIMIT; break; }
+                    if (nf == max_frames) { status = IE_RES_LIMIT; scratch_full = true; break; }  // tier 1: the full-size tier redoes it
                     const uint8_t* v = tv.base + (size_t)s->val_off16 * 16u;
                     frames[nf++] = Frame{v, vlen, vlen};
                     count_braces(v, vlen, in_open, in_close);
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
         out_lens[r] = olen;
         status_out[r] = (int32_t)status;
         aux_out[r] = aux;
+        if ((status & 0xFF) == IE_RES_LIMIT) atomicAdd(reinterpret_cast<unsigned long long*>(&info->n_limit), 1ull);
     }
 }
 
@@ -441,7 +450,8 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
     if (n == 0) return cudaSuccess;
     // rounds need one snapshot (the table must stay tile-uniform) and result indices that fit the round map
-    if (!ws.round_ctl || n_states != 1 || n > IE_AGAIN_INDEX_MASK) rescan_rounds = 0;
+    // (the gather hands out index and byte offset in one 64-bit atomic, 24 bits of it for the index)
+    if (!ws.round_ctl || n_states != 1 || n >= (1u << 24)) rescan_rounds = 0;
     IeRound rd{};
     rd.allow_splice = rescan_rounds ? 1u : 0u;
     if (rescan_rounds) { rd.again_list = ws.round_list[0]; rd.again_count = &ws.round_ctl->count[0]; rd.again_bytes = &ws.round_ctl->bytes[0]; }
@@ -486,10 +496,24 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     ie_resolve_general_kernel<true><<<sms * 3, IE_GENERAL_SMALL_THREADS, smem, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                                 d_status, d_aux, ws, d_info, max_expansions, small_t,
                                                                                 IE_GENERAL_SMALL_KEY, out_bias, ws.general_list, ws.general_count,
-                                                                                ws.retry_list, ws.retry_count, stride);
+                                                                                ws.retry_list, ws.retry_count, stride, 0u);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
     ie_resolve_general_kernel<false><<<ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32), IE_GENERAL_SMALL_THREADS, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
                                                                          d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH,
-                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr, 0u);
+                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr, 0u, ie_general_fcap(tcap));
+    return cudaGetLastError();
+}
+
+// Re-runs the templates on `d_list` (result indices, *d_count of them) on the full-size tier with larger bounds: the
+// host-buffer calls escalate templates that hit a DEFAULT bound (ie_capi.cu: escalate_limits).  ws.scratch must hold
+// ws.general_workers * ie_general_worker_bytes(tcap); results are appended to d_out through d_info->out_bytes.
+cudaError_t ie_launch_general_escalate(const IeTableView* d_views, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                                       uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                       const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap, uint64_t out_bias,
+                                       const uint32_t* d_list, const uint32_t* d_count, cudaStream_t stream) {
+    const uint32_t wpb = IE_GENERAL_SMALL_THREADS / 32;
+    ie_resolve_general_kernel<false><<<(ws.general_workers + wpb - 1) / wpb, IE_GENERAL_SMALL_THREADS, 0, stream>>>(
+        d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH, out_bias,
+        d_list, d_count, nullptr, nullptr, 0u, ie_general_fcap(tcap));
     return cudaGetLastError();
 }

@@ -4,6 +4,9 @@ C4: 1 Mi templates x 65 536-insert state, depth-3 nesting  -> c4_state(), c4_tem
 C5: 10 M keys `persona-<p>/field-<f>` and 64 wildcard sets   -> c5_keys(), c5_pattern_sets()
 C3: text_adventure-derived templates over cloned states     -> c3_state(), c3_templates()
 """
+import json
+import os
+
 import numpy as np
 
 from . import Arena, PackedInserts, TAG_NUMBER, TAG_STRING
@@ -167,19 +170,21 @@ def c5_pattern_sets(n_sets=64, seed=0xC5, n_persona=100000, n_field=100):
 
 
 # ---- C3: text_adventure-derived ---------------------------------------------------------------
-C3_DEFAULT_INSERTS = {  # examples/text_adventure.json5:6-13
-    "min_history_turns": 4, "max_history_turns": 18, "enable_suggestions": "false",
-    "system_prompt": "You are a creative and logical AI.\nPay attention and never make logical mistakes.",
-    "voice_path": "",
-}
-C3_TEMPLATES = [  # strings recursive_interpolate visits in the top-level tasks + README.md:37 nested keys
-    "{scenario}", "scenario", "unescape", "{history_list}", "", "\n\n", "history_text_base", "list_join",
-    "{history_text_printed}\n\n", "print", "(unset)", "output", "set", "first", "stage", "{stage}",
-    "{system_prompt}", "{scenario}\n\n{history_text_llm}", "{question-{i}}", "{persona_name}/answer-{i}",
-    "Turn {i} of {max_history_turns}: {question-{i}}", "{persona_name} says: {scenario} \\{literal\\}",
-    "{output}", "{new_user_input}", "{summary}", "> {question-{i}}\n{persona_name}: ", "{enable_suggestions}",
-    "{min_history_turns}", "cmd", "text", "{voice_path}", "history: {history_text_llm}{history_list}",
-]
+def example_batches():
+    """The reference's example programs as resolver batches: for each `examples/*.json5`, its default_state and the
+    strings recursive_interpolate sends to the resolver for every top-level task, in order.  Derived from the files by
+    oracle/gen_golden.py (load_program + the interp.rs:179-246 traversal) and committed as data/example_batches.json;
+    tests/test_oracle_golden.py re-derives it from the reference tree when that is present."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "example_batches.json")) as f:
+        return json.load(f)
+
+
+_EX = example_batches()
+C1_TEMPLATES = _EX["hello_world.json5"]["templates"]          # BASELINE.json config 1
+C2_TASKS = _EX["math.json5"]["tasks"]                         # config 2: per task, the strings of its tree walk
+C3_DEFAULT_INSERTS = _EX["text_adventure.json5"]["default_state"]["inserts"]  # text_adventure.json5:6-13
+# config 3: every string of text_adventure.json5's top-level tasks + the nested-key forms of README.md:37
+C3_TEMPLATES = _EX["text_adventure.json5"]["templates"] + ["{question-{i}}", "{persona_name}/answer-{i}"]
 
 
 def c3_state(s, rng):

@@ -392,6 +392,42 @@ def gen_maps():
     print({"maps_cases": len(cases), "errors": sum("err" in c["py"] for c in cases)})
 
 
+# ---- the example programs as resolver batches (BASELINE.json configs 1-3) ---------------------------
+# Each example is loaded through the restatement of parser.rs (add_line_numbers + load_program) and every top-level task
+# of its `order` is walked the way recursive_interpolate walks it: the strings that reach interpolate_inserts, in order.
+# The fixture holds those derived batches (not the program text); tests/test_oracle_golden.py re-derives them from
+# /root/reference when the tree is present and compares.
+EXAMPLES_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "interpolation_engine_b200", "data", "example_batches.json")
+
+
+def example_batches():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    out = {}
+    for name in sorted(os.listdir(EXAMPLES)):
+        if not name.endswith(".json5"):
+            continue
+        kind, prog = orc.call("load_program", text=open(os.path.join(EXAMPLES, name), encoding="utf-8").read())
+        assert kind == "ok", (name, prog)
+        tasks = []
+        for task in prog["order"]:
+            kind, tr = orc.call("interpolation_trace", value=task)
+            assert kind == "ok"
+            tasks.append({"cmd": task.get("cmd"), "line": task.get("line"), "templates": tr["templates"], "lookups": tr["lookups"]})
+        out[name] = {"default_state": prog["default_state"], "tasks": tasks,
+                     "templates": [t for task in tasks for t in task["templates"]]}
+    return out
+
+
+def gen_examples():
+    out = example_batches()
+    os.makedirs(os.path.dirname(EXAMPLES_OUT), exist_ok=True)
+    with open(EXAMPLES_OUT, "w") as f:
+        json.dump(out, f, ensure_ascii=True, indent=0, sort_keys=True)
+    print({k: len(v["templates"]) for k, v in out.items()})
+
+
 def resolves(twin, ins, s):
     try:
         twin.interpolate_inserts(ins, s)
@@ -401,7 +437,10 @@ def resolves(twin, ins, s):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] != "maps":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "twin"):
         main()
-    if len(sys.argv) < 2 or sys.argv[1] == "maps":
+    if which in ("all", "maps"):
         gen_maps()
+    if which in ("all", "examples"):
+        gen_examples()

@@ -83,6 +83,14 @@ Value dispatch(const Value& args) {
         out["inserts"] = Value::object(std::move(ins));
         return Value::object(std::move(out));
     }
+    if (fn == "interpolation_trace") {  // the resolver calls of recursive_interpolate(value), in order (interp.rs:179-246)
+        std::vector<std::string> t, l;
+        interpolation_trace(*field(args, "value"), t, l);
+        Object out;
+        out["templates"] = strings_value(t);
+        out["lookups"] = strings_value(l);
+        return Value::object(std::move(out));
+    }
     if (fn == "add_line_numbers") return Value::string(add_line_numbers(str_field(args, "text")));  // parser.rs:74
     if (fn == "load_program") return load_program(str_field(args, "text"));                          // parser.rs:8
     if (fn == "replace_map") {  // runtime.rs:1649

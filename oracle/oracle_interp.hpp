@@ -291,6 +291,35 @@ inline Value recursive_interpolate(const Object& inserts, const Value& value, co
     return value;
 }
 
+// The resolver calls recursive_interpolate issues for `value`, in its traversal order (interp.rs:179-246): every string
+// and every object key goes to interpolate_inserts (:186 / :199), the simple keys of a control task's `tasks` to
+// get_interpdata (:217, :224); goto_map / replace_map objects and the bodies of control tasks are not entered.
+// This is the batch a replayed program presents to the resolver (BASELINE.json configs 1-3).
+inline void interpolation_trace(const Value& value, std::vector<std::string>& templates, std::vector<std::string>& lookups) {
+    if (value.kind == Value::String) { templates.push_back(value.s); return; }
+    if (value.kind == Value::Arr) { for (auto& e : *value.a) interpolation_trace(e, templates, lookups); return; }
+    if (value.kind != Value::Obj) return;
+    const Object& obj = *value.o;
+    auto cit = obj.find("cmd");
+    if (cit != obj.end() && cit->second.kind == Value::String) {
+        const std::string& cmd = cit->second.s;
+        if (cmd == "goto_map" || cmd == "replace_map") return;
+        if (cmd == "for" || cmd == "serial" || cmd == "parallel_wait" || cmd == "parallel_race") {
+            auto tit = obj.find("tasks");
+            if (tit != obj.end()) {
+                const Value& tv = tit->second;
+                if (tv.kind == Value::String) { if (auto k = get_simple_insertkey(tv.s)) lookups.push_back(*k); }
+                else if (tv.kind == Value::Arr)
+                    for (auto& e : *tv.a)
+                        if (e.kind == Value::String)
+                            if (auto k = get_simple_insertkey(e.s)) lookups.push_back(*k);
+            }
+            return;
+        }
+    }
+    for (auto& kv : obj) { templates.push_back(kv.first); interpolation_trace(kv.second, templates, lookups); }
+}
+
 // interp.rs:273-312
 inline void extract_from_str(const std::string& s, std::vector<std::string>& keys) {
     long depth = 0;

@@ -37,7 +37,7 @@ def run(name, arena, limits=None):
     cap = int(arena.bytes.nbytes * 8) + (1 << 20)
     out = torch.empty(cap, dtype=torch.uint8, device=dev); oo = torch.empty(n, dtype=torch.int64, device=dev)
     ol = torch.empty(n, dtype=torch.int32, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev); ax = torch.empty(n, dtype=torch.int32, device=dev)
-    info = torch.zeros(32, dtype=torch.uint8, device=dev)
+    info = torch.zeros(64, dtype=torch.uint8, device=dev)
     s = torch.cuda.Stream(device=dev)
     kw = {"limits": limits} if limits else {}
     def step():

@@ -38,7 +38,7 @@ def run_one(libname):
     ol = torch.empty(n, dtype=torch.int32, device=dev)
     st = torch.empty(n, dtype=torch.int32, device=dev)
     ax = torch.empty(n, dtype=torch.int32, device=dev)
-    info = torch.zeros(32, dtype=torch.uint8, device=dev)
+    info = torch.zeros(64, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     s = torch.cuda.Stream(device=dev)
 

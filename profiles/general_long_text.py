@@ -16,7 +16,7 @@ for length, count in ((1024, 256), (1700, 256), (4096, 256), (16384, 64), (16384
     cap = arena.bytes.nbytes * 2 + (1 << 20)
     out = torch.empty(cap, dtype=torch.uint8, device=dev); oo = torch.empty(n, dtype=torch.int64, device=dev)
     ol = torch.empty(n, dtype=torch.int32, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev); ax = torch.empty(n, dtype=torch.int32, device=dev)
-    info = torch.zeros(32, dtype=torch.uint8, device=dev)
+    info = torch.zeros(64, dtype=torch.uint8, device=dev)
     s = torch.cuda.Stream(device=dev)
     def step():
         eng.resolve_batch_device(table, d_t.data_ptr(), d_o.data_ptr(), n, out.data_ptr(), cap, oo.data_ptr(), ol.data_ptr(), st.data_ptr(), ax.data_ptr(), info.data_ptr(), stream=s.cuda_stream, limits=(4096, 1 << 16, 0, 0, 0))

@@ -29,7 +29,7 @@ for frac in (0.0, 0.01, 0.1, 0.5):
     dev = torch.device("cuda", 0)
     d_t = torch.from_numpy(tmpl.bytes).to(dev); d_o = torch.from_numpy(tmpl.offs.view(np.int64)).to(dev)
     cap = int(tmpl.bytes.nbytes * 3) + (1 << 20)
-    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int64, device=dev)] + [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3)] + [torch.zeros(32, dtype=torch.uint8, device=dev)]
+    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int64, device=dev)] + [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3)] + [torch.zeros(64, dtype=torch.uint8, device=dev)]
     sdev = torch.cuda.Stream(device=dev)
     dev_ms = {}
     for rounds in (0, 2):

@@ -40,6 +40,7 @@ pub struct ie_batch_info {
     pub n: u64,
     pub out_bytes: u64,
     pub n_general: u64,
+    pub n_limit: u64,
     pub kernel_ms: f32,
 }
 

@@ -208,12 +208,35 @@ def test_recursive_interpolate_tasks(eng, oracle):
     for task in tasks:
         got, want = both(eng, oracle, "recursive_interpolate", inserts=ins, value=task)
         assert_same(got, want, task)
-    # the C1 / C2 traces (examples/hello_world.json5, examples/math.json5 after line injection)
+
+
+def test_c1_c2_example_traces_on_gpu(eng, oracle):
+    """BASELINE.json configs 1 and 2, from the batches load_program + the tree walk derive from the reference's files
+    (workloads.example_batches): hello_world's 5 templates come back unchanged; math's 14 resolver calls run as ONE
+    batch against a 2-snapshot table ({} before the math task, {result: 3} after it)."""
+    res = eng.resolve_batch(eng.pack(ie.PackedInserts.from_dict({})), workloads.C1_TEMPLATES)
+    assert [res.get(i).decode() for i in range(5)] == workloads.C1_TEMPLATES and not res.status.any()
+    t1, t2 = workloads.C2_TASKS
+    expr = t1["templates"][t1["templates"].index("input") + 1]
+    calls = t1["templates"] + [expr, expr] + t2["templates"]
+    assert len(calls) == 14
+    table = eng.pack_many([ie.PackedInserts.from_dict({}), ie.PackedInserts.from_dict({"result": 3})])
+    got = eng.resolve_batch(table, calls)
+    n = len(calls)
+    for j, t in enumerate(calls):
+        s = 0 if j < 9 else 1
+        want = oracle.call("interpolate_inserts", inserts=[{}, {"result": 3}][s], content=t)
+        assert want[0] == "ok" and got.get(s * n + j).decode() == want[1] and (got.status[s * n + j] & 0xFF) == 0, (j, t)
+    assert got.get(n + 13) == b"The result is 3!\n"
+    # the same through the tree walkers, on the task objects themselves
     c1 = {"cmd": "print", "text": "Hello, world!", "line": 8}
     assert eng.call("recursive_interpolate", inserts={}, value=c1) == ("ok", c1)
     c2b = {"cmd": "print", "text": "The result is {result}!\n", "line": 9}
     assert eng.call("recursive_interpolate", inserts={"result": 3}, value=c2b) == (
         "ok", {"cmd": "print", "text": "The result is 3!\n", "line": 9})
+    # the product's own walk of a task (ie_call_json "interpolation_trace") is the oracle's
+    for task in (c1, c2b, {"cmd": "serial", "tasks": ["{a}", "x", {"cmd": "print"}], "z": "{q}"}, {"k{i}": [{"cmd": "goto_map", "text": "{t}"}, "{u}"]}):
+        assert eng.call("interpolation_trace", value=task) == oracle.call("interpolation_trace", value=task)
 
 
 def test_escape_unescape(eng, oracle):
@@ -511,6 +534,56 @@ def test_replace_map_goto_map_on_gpu(eng, oracle):
         assert got == want, (pat, text, got, want)
     first = eng.glob_first_match(["persona-1/a", "zzz", "", "b"], ["b", "persona-*", "*"])
     assert list(first) == [1, 2, 2, 0]
+
+
+def test_limits_escalate_to_hard_caps(eng, oracle):
+    """IE_RES_LIMIT means "the reference would not finish within the hard caps", not "deeper than the first guess": the
+    host-buffer calls re-run templates that stopped at a default bound with 8x bounds.  Every case
+    below terminates in interp.rs and must equal the oracle; the runaway cases must report the limit on both sides."""
+    import time
+    big = dict(max_iterations=300000, max_bytes=1 << 28)
+
+    def same(ins, t):
+        got = eng.call("interpolate_inserts", inserts=ins, content=t, clock=CLOCK)
+        want = oracle.call("interpolate_inserts", inserts=ins, content=t, clock=CLOCK, **big)
+        assert got == want, (t[:60], str(got)[:200], str(want)[:200])
+        return got
+
+    # value chains with text left of every group: one stacked splice frame per level (24 in the first tier, about a
+    # thousand in the second, more after an escalation)
+    for depth in (5, 30, 100, 3000):
+        ins = {"A%d" % k: "x%d{A%d}" % (k, k + 1) for k in range(1, depth)}
+        ins["A%d" % depth] = "end"
+        got = same(ins, "v={A1}")
+        assert got[0] == "ok" and got[1].endswith("end") and got[1].startswith("v=x1x2")
+        got = same(ins, "." + BS + "}{A1}!")  # the same through the sentinel quirk (general path from the start)
+        assert got[0] == "ok"
+    # results beyond the default 64 KiB of text on the general path: 70 KB, 1 MB and 9 MB (two and three escalations)
+    for size in (70_000, 1_000_000, 9_000_000):
+        ins = {"big": "ab" * (size // 2), "k": "big"}
+        got = same(ins, "." + BS + "}<{big}>")
+        assert got[0] == "ok" and len(got[1]) == size + 5
+        got = same(ins, "." + BS + "}<{{k}}>")
+        assert got[0] == "ok" and len(got[1]) == size + 5
+    # more lookups than the default 4096 in one template
+    ins = {"k": "v", "e": ""}
+    got = same(ins, "." + BS + "}" + "{k}{e}" * 2600)
+    assert got[0] == "ok" and got[1].endswith("v" * 10)
+    got = same(ins, "{k}{e}" * 2600)  # and without the quirk (tile kernel / per-thread path: no bound at all)
+    assert got == ("ok", "v" * 2600)
+    # runaways: the reference never returns; both sides report the limit, and this side does so in bounded time
+    for ins, t in (({"a": "{a}"}, "x{a}"), ({"a": "y{a}"}, "x{a}"), ({"a": "{b}", "b": "-{a}-"}, "{a}!")):
+        t0 = time.time()
+        got = eng.call("interpolate_inserts", inserts=ins, content=t, clock=CLOCK)
+        want = oracle.call("interpolate_inserts", inserts=ins, content=t, clock=CLOCK, max_iterations=5000)
+        assert got[0] == "err" and got[1]["code"] == KIND_TO_CODE["limit"] and want[1]["code"] == KIND_TO_CODE["limit"], (got, want)
+        assert time.time() - t0 < 20
+    # a bound the caller sets is final: no escalation
+    table = eng.pack(ie.PackedInserts.from_dict({"k": "v", "e": ""}))
+    res = eng.resolve_batch(table, ["." + BS + "}" + "{k}{e}" * 40, "plain {k}"], limits=(16, 0, 0, 0, 0))
+    assert [int(x) & 0xFF for x in res.status] == [KIND_TO_CODE["limit"], 0]
+    res = eng.resolve_batch(table, ["." + BS + "}" + "{k}{e}" * 40, "plain {k}"])
+    assert [int(x) & 0xFF for x in res.status] == [0, 0] and res.get(0).endswith(b"v" * 40)
 
 
 def test_maps_golden_vectors_on_gpu(eng, oracle):
