@@ -134,6 +134,35 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_other_workload(args, rank, local_rank):
+    """BASELINE.json's other configs (wildcard sweep, cloned states, escape / unescape, the two tiny example traces) with
+    the contract's line shape: measured by bench_aux.py's functions on ONE GPU (rank 0; these paths shard the same way
+    C4 does - independent key / state ranges, no collective - and only C4 is run at 2/4/8 GPUs)."""
+    if rank != 0:
+        return
+    import torch
+
+    import bench_aux
+    import interpolation_engine_b200 as ie
+    from interpolation_engine_b200 import workloads
+    from tests import oracle_lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    eng = ie.Engine(local_rank)
+    fn = {"c5": bench_aux.bench_c5, "escape": bench_aux.bench_escape, "c3": bench_aux.bench_c3, "c1c2": bench_aux.bench_c1c2}[args.workload]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.time()
+    line = fn(eng, ie, workloads, torch, dev, oracle_lib.load())
+    line["clocks"] = sampler.stop(t0, time.time())
+    line.setdefault("steps", args.steps)
+    line.setdefault("warmup", max(args.warmup, 3))
+    line.setdefault("scaling", "weak")
+    line.setdefault("gpu_launches", None)
+    line["n_gpus"] = 1
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,6 +170,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--templates", type=int, default=N_TEMPLATES, help="templates per GPU (default = the BASELINE config)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "c3", "escape", "c1c2"],
+                    help="c4 (default) = the headline config; the others are BASELINE.json's remaining configs, one GPU, same line shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -157,6 +188,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "c4":
+        run_other_workload(args, rank, local_rank)
         return
 
     import torch

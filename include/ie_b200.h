@@ -118,13 +118,35 @@ ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const u
                           const char* hhmm, const char* hhmmss, ie_table** out);
 /* Many snapshots at once (the cloned states of one program, runtime.rs:700 called once per state):
  * snapshot s owns the inserts [state_offs[s], state_offs[s+1]) of the packed arrays.  One device
- * allocation and one upload; the images are built on several host threads.  A table that holds S
+ * allocation; the tables are built on the device (see ie_table_build_ms below).  A table that holds S
  * snapshots makes every ie_resolve_batch* call a cross product: all n templates are resolved against
  * every snapshot, result index = s * n + template, and every result array holds S * n entries.
  * `aux` entry indices are relative to the snapshot's first insert. */
 ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys,
                                const uint64_t* key_offs, const uint8_t* vals, const uint64_t* val_offs,
                                const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out);
+/* Snapshots of 4096 inserts and more, and every ie_table_pack_many table, are built ON THE DEVICE: the packed arrays
+ * are uploaded as they are and one thread per insert hashes its key, claims a slot, classifies and copies its value
+ * (ie_table_build.cu); the host only lays out capacities.  ie_table_build_ms = device time of those kernels (0 for a
+ * host-built table). */
+double ie_table_build_ms(const ie_table* t);
+
+/* ---- set_interpdata / delete_interpdata (interp.rs:139-145) on a packed table, in place --------------------------
+ * The reference mutates its inserts map between tasks (17 set_interpdata call sites in runtime.rs) and snapshots it
+ * per task (runtime.rs:700); with these two calls a packed table follows the map without being packed again.
+ * `state` selects the snapshot of an ie_table_pack_many table (IE_ALL_STATES: the same operations on every snapshot).
+ * Operations apply in order (a later one on the same key wins).  ie_table_set: insert or overwrite; `tags[i]` is the
+ * JSON type of value i (its text is the value_to_string rendering, as in ie_table_pack), `entries[i]` (may be NULL)
+ * what `aux` reports when a typed simple-path result is this insert.  ie_table_delete: keys that are absent are
+ * ignored, like Map::remove.  Both are synchronous and must not overlap other work on the table.
+ * IE_E_OVERFLOW: a snapshot's slot array is more than 3/4 full or the table's arena (which keeps 1/8 spare room,
+ * at least 4 KiB) is exhausted; the operations that did not fit were skipped, everything else was applied and the
+ * table is consistent - pack the snapshot again. */
+#define IE_ALL_STATES 0xFFFFFFFFu
+ie_status_t ie_table_set(ie_engine* e, ie_table* t, uint32_t state, uint64_t n, const uint8_t* keys, const uint64_t* key_offs,
+                         const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags, const uint32_t* entries);
+ie_status_t ie_table_delete(ie_engine* e, ie_table* t, uint32_t state, uint64_t n, const uint8_t* keys, const uint64_t* key_offs);
+
 /* A table must outlive the work that reads it: the host-buffer calls are synchronous, but after a *_device call on a
  * caller's stream free the table only once that stream has passed the call (stream synchronise or an event): tables
  * up to 48 MiB live in the device's stream-ordered pool and are released in the order of the ENGINE's stream, which

@@ -43,6 +43,9 @@ class _Result(ctypes.Structure):
                 ("status", ctypes.c_void_p), ("aux", ctypes.c_void_p), ("info", _BatchInfo)]
 
 
+ALL_STATES = 0xFFFFFFFF  # IE_ALL_STATES
+
+
 class _Limits(ctypes.Structure):
     _fields_ = [("max_expansions", ctypes.c_uint32), ("max_result_bytes", ctypes.c_uint32), ("avg_template_bytes", ctypes.c_uint32),
                 ("avg_template_groups", ctypes.c_uint32), ("rescan_rounds", ctypes.c_uint32)]
@@ -60,6 +63,9 @@ ABI = {
     "ie_table_pack": (_i, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "ie_table_pack_many": (_i, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "ie_table_states": (_u32, [_vp]),
+    "ie_table_build_ms": (ctypes.c_double, [_vp]),
+    "ie_table_set": (_i, [_vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ie_table_delete": (_i, [_vp, _vp, _u32, _u64, _vp, _vp]),
     "ie_table_free": (None, [_vp]),
     "ie_table_device_bytes": (_u64, [_vp]),
     "ie_resolve_batch": (_i, [_vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_Limits), ctypes.POINTER(_Result)]),
@@ -186,6 +192,29 @@ class Table:
     @property
     def device_bytes(self):
         return int(self.engine.lib.ie_table_device_bytes(self.handle))
+
+    @property
+    def build_ms(self):
+        """Device time of the build kernels (0.0 for a host-built table)."""
+        return float(self.engine.lib.ie_table_build_ms(self.handle))
+
+    def set(self, items, state=None, entries=None):
+        """set_interpdata (interp.rs:139) in place, for each (key, value) of `items` (dict or list of pairs), in order.
+        `state`: snapshot of a pack_many table (None = every snapshot)."""
+        pairs = list(items.items()) if isinstance(items, dict) else list(items)
+        k = Arena.from_strings([key for key, _ in pairs])
+        v = Arena.from_strings([render_value(val) for _, val in pairs])
+        tags = np.array([tag_of(val) for _, val in pairs], dtype=np.uint8)
+        ent = np.ascontiguousarray(entries, dtype=np.uint32) if entries is not None else None
+        self.engine._check(self.engine.lib.ie_table_set(self.engine.handle, self.handle, ALL_STATES if state is None else int(state), len(pairs),
+                                                        _ptr(k.bytes), _ptr(k.offs), _ptr(v.bytes), _ptr(v.offs), _ptr(tags),
+                                                        _ptr(ent) if ent is not None else None))
+
+    def delete(self, keys, state=None):
+        """delete_interpdata (interp.rs:143) in place."""
+        k = Arena.from_strings(list(keys))
+        self.engine._check(self.engine.lib.ie_table_delete(self.engine.handle, self.handle, ALL_STATES if state is None else int(state), k.n,
+                                                           _ptr(k.bytes), _ptr(k.offs)))
 
     def free(self):
         if self.handle:

@@ -97,6 +97,12 @@ struct ie_table {
     bool has_balanced = false;    // some value holds properly nested groups of its own: rescan rounds can do work
     bool pooled = false;          // small table: allocated from the stream-ordered pool (no cudaMalloc / cudaFree per snapshot)
     cudaEvent_t ready = nullptr;  // upload finished (calls on a caller's stream wait for it)
+    // in-place mutation (ie_table_set / ie_table_delete): the bump-allocated arena behind the slots, its header, and
+    // the per-snapshot count of non-empty slots
+    uint64_t arena_off = 0, arena_bytes = 0;
+    IeTableHeader* d_hdr = nullptr;
+    uint32_t* d_used = nullptr;
+    double build_ms = 0.0;        // device time of the build kernels (device-built tables)
 };
 
 namespace {
@@ -244,7 +250,11 @@ static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uin
     const size_t S = images.size();
     std::vector<size_t> at(S + 1, 0);
     for (size_t s = 0; s < S; ++s) at[s + 1] = at[s] + ((images[s].size() + 255) & ~size_t(255));
-    const size_t views_at = at[S], total = views_at + S * sizeof(IeTableView);
+    // behind the images: slack for values and keys that ie_table_set appends, the view array, the header, the used counts
+    size_t slack = 0;
+    if (S == 1) slack = std::max<size_t>(4096, (images[0].size() / 4 + 15) & ~size_t(15));
+    const size_t arena_at = at[S], views_at = arena_at + slack, hdr_at = views_at + S * sizeof(IeTableView);
+    const size_t used_at = hdr_at + sizeof(IeTableHeader), total = used_at + S * sizeof(uint32_t);
     CU(cudaSetDevice(e->device));
     ie_table* t = new (std::nothrow) ie_table();
     if (!t) return fail(IE_E_NOMEM, std::string(who) + ": out of host memory");
@@ -263,36 +273,55 @@ static ie_status_t upload_tables(ie_engine* e, const std::vector<std::vector<uin
     if (err != cudaSuccess) { delete t; return cuda_fail(err, who); }
     t->pooled = pooled;
     std::vector<IeTableView> views(S);
+    // trailer: views, header (nothing of the arena used yet), non-empty slots per snapshot
+    std::vector<uint8_t> trailer(total - views_at, 0);
     for (size_t s = 0; s < S; ++s) {
         views[s].base = (const uint8_t*)t->d_base + at[s];
         views[s].mask = caps[s] - 1;
         views[s].n_entries = counts[s];
+        uint32_t used = 0;
+        const IeSlot* sl = reinterpret_cast<const IeSlot*>(images[s].data());
+        for (uint32_t k = 0; k < caps[s]; ++k) used += sl[k].key_len != IE_SLOT_EMPTY;
+        std::memcpy(trailer.data() + (used_at - views_at) + s * sizeof(uint32_t), &used, sizeof used);
     }
-    if (small || S > 1) {  // images and the view array in one staged block, one copy
+    std::memcpy(trailer.data(), views.data(), S * sizeof(IeTableView));
+    if (small || S > 1) {  // images and the trailer in one staged block, one copy
         std::vector<uint8_t> all(total, 0);
         for (size_t s = 0; s < S; ++s) std::memcpy(all.data() + at[s], images[s].data(), images[s].size());
-        std::memcpy(all.data() + views_at, views.data(), S * sizeof(IeTableView));
+        std::memcpy(all.data() + views_at, trailer.data(), trailer.size());
         err = cudaMemcpyAsync(t->d_base, all.data(), all.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess && !small) err = cudaStreamSynchronize(e->stream);
     } else {               // one large snapshot: no second host copy of its image
         err = cudaMemcpyAsync(t->d_base, images[0].data(), images[0].size(), cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, views.data(), sizeof(IeTableView), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync((uint8_t*)t->d_base + views_at, trailer.data(), trailer.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess && !pooled) err = cudaStreamSynchronize(e->stream);
     }
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventRecord(t->ready, e->stream);
     if (err != cudaSuccess) { if (pooled) cudaFreeAsync(t->d_base, e->stream); else cudaFree(t->d_base); delete t; return cuda_fail(err, who); }
+    t->arena_off = arena_at;
+    t->arena_bytes = slack;
+    t->d_hdr = (IeTableHeader*)((uint8_t*)t->d_base + hdr_at);
+    t->d_used = (uint32_t*)((uint8_t*)t->d_base + used_at);
     t->view = views[0];
     t->d_views = (const IeTableView*)((uint8_t*)t->d_base + views_at);
     *out = t;
     return IE_OK;
 }
 
+static ie_status_t build_on_device(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys, const uint64_t* key_offs,
+                                   const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss,
+                                   bool compact, ie_table** out, const char* who);
+
 ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals,
                           const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss, ie_table** out) {
     if (!e || !out || (n && (!keys || !key_offs || !vals || !val_offs || !tags)))
         return fail(IE_E_INVALID, "ie_table_pack: NULL argument");
     *out = nullptr;
+    if (n >= 4096) {  // large snapshots are hashed, classified and laid out on the device (ie_table_build.cu)
+        const uint64_t so[2] = {0, n};
+        return build_on_device(e, 1, so, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, /*compact=*/false, out, "ie_table_pack");
+    }
     std::vector<std::vector<uint8_t>> images(1);
     std::vector<uint32_t> caps(1, 0), counts(1, (uint32_t)n);
     std::string why;
@@ -304,6 +333,140 @@ ie_status_t ie_table_pack(ie_engine* e, uint64_t n, const uint8_t* keys, const u
     return st;
 }
 
+// Device-side build (ie_table_build.cu): the raw packed arrays go to the device as they are, the tables of all
+// snapshots are built there by one thread per insert.  Host work is O(snapshots): capacities and the layout.
+static ie_status_t build_on_device(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys, const uint64_t* key_offs,
+                                   const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss,
+                                   bool compact, ie_table** out, const char* who) {
+    const uint64_t n = state_offs[n_states];
+    if (n > 0x3FFFFFFFull) return fail(IE_E_INVALID, std::string(who) + ": too many inserts (max 2^30 - 1)");
+    const size_t hm = hhmm ? std::strlen(hhmm) : 0, hs = hhmmss ? std::strlen(hhmmss) : 0;
+    if (hm > 64 || hs > 64) return fail(IE_E_INVALID, std::string(who) + ": clock rendering longer than 64 bytes");
+    const uint64_t kbytes = n ? key_offs[n] : 0, vbytes = n ? val_offs[n] : 0;
+    // layout: slot arrays (load factor <= 0.5 for packed-side-by-side snapshots, <= 0.25 for a single one), then the arena
+    std::vector<uint64_t> slot_base(n_states);
+    std::vector<uint32_t> slot_cap(n_states);
+    uint64_t slots = 0;
+    for (uint64_t s = 0; s < n_states; ++s) {
+        if (state_offs[s + 1] < state_offs[s]) return fail(IE_E_INVALID, std::string(who) + ": state offsets not monotone");
+        const uint64_t cnt = state_offs[s + 1] - state_offs[s] + 2;
+        const uint64_t want = (!compact && cnt <= (1ull << 22)) ? cnt * 4 : cnt * 2;
+        uint64_t cap = 16;
+        while (cap < want) cap <<= 1;
+        if (cap > (1ull << 31)) return fail(IE_E_INVALID, std::string(who) + ": table too large");
+        slot_base[s] = slots;
+        slot_cap[s] = (uint32_t)cap;
+        slots += cap;
+    }
+    const uint64_t items = n + 2 * n_states;
+    // every item longer than 16 bytes takes its length rounded up to 16 from the arena; + slack for later ie_table_set calls
+    const uint64_t arena_need = kbytes + vbytes + 15 * items + 2 * 64 * n_states;
+    const uint64_t arena_bytes = ((arena_need + std::max<uint64_t>(64u << 10, arena_need / 8)) + 15) & ~uint64_t(15);
+    const uint64_t slots_bytes = slots * sizeof(IeSlot);
+    const uint64_t views_at = slots_bytes + arena_bytes, hdr_at = views_at + n_states * sizeof(IeTableView);
+    const uint64_t used_at = hdr_at + sizeof(IeTableHeader), total = used_at + n_states * sizeof(uint32_t);
+    if ((total >> 4) > 0xFFFFFFFFull) return fail(IE_E_INVALID, std::string(who) + ": table exceeds 64 GiB");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    ie_table* t = new (std::nothrow) ie_table();
+    if (!t) return fail(IE_E_NOMEM, std::string(who) + ": out of host memory");
+    t->e = e;
+    t->bytes = total;
+    t->n_states = (uint32_t)n_states;
+    t->pooled = total <= (48u << 20);
+    cudaError_t err = t->pooled ? cudaMallocAsync(&t->d_base, total, s) : cudaMalloc(&t->d_base, total);
+    if (err != cudaSuccess) { delete t; return cuda_fail(err, who); }
+    // staging area of the inputs (stream-ordered pool; released behind the build kernels)
+    auto up16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
+    const uint64_t o_so = 0, o_sb = o_so + up16((n_states + 1) * 8), o_sc = o_sb + up16(n_states * 8), o_ko = o_sc + up16(n_states * 4);
+    const uint64_t o_vo = o_ko + up16((n + 1) * 8), o_tg = o_vo + up16((n + 1) * 8), o_ck = o_tg + up16(n), o_k = o_ck + 160;
+    const uint64_t o_v = o_k + up16(kbytes), o_sl = o_v + up16(vbytes), stage_total = o_sl + up16(items * 4);
+    uint8_t* d_stage = nullptr;
+    err = cudaMallocAsync((void**)&d_stage, stage_total, s);
+    auto bail = [&](cudaError_t ce) {
+        if (d_stage) cudaFreeAsync(d_stage, s);
+        if (t->pooled) cudaFreeAsync(t->d_base, s); else cudaFree(t->d_base);
+        delete t;
+        return cuda_fail(ce, who);
+    };
+    if (err != cudaSuccess) { d_stage = nullptr; return bail(err); }
+    uint8_t clock[160] = {0};
+    std::memcpy(clock, "HH:MM", 5);
+    std::memcpy(clock + 8, "HH:MM:SS", 8);
+    if (hhmm) std::memcpy(clock + 16, hhmm, hm);
+    if (hhmmss) std::memcpy(clock + 80, hhmmss, hs);
+    const uint64_t zero_off[1] = {0};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEventCreate(&ev_a);
+    cudaEventCreate(&ev_b);
+#define UP(dst_off, src, bytes) if (err == cudaSuccess && (bytes)) err = cudaMemcpyAsync(d_stage + (dst_off), (src), (bytes), cudaMemcpyHostToDevice, s)
+    UP(o_so, state_offs, (n_states + 1) * 8);
+    UP(o_sb, slot_base.data(), n_states * 8);
+    UP(o_sc, slot_cap.data(), n_states * 4);
+    UP(o_ko, n ? key_offs : zero_off, (n + 1) * 8);
+    UP(o_vo, n ? val_offs : zero_off, (n + 1) * 8);
+    UP(o_tg, tags, n);
+    UP(o_ck, clock, sizeof clock);
+    UP(o_k, keys, kbytes);
+    UP(o_v, vals, vbytes);
+#undef UP
+    // empty slots are all-ones (key_len = IE_SLOT_EMPTY, claim word = none); header and used counts start at zero
+    if (err == cudaSuccess) err = cudaMemsetAsync(t->d_base, 0xFF, slots_bytes, s);
+    if (err == cudaSuccess) err = cudaMemsetAsync((uint8_t*)t->d_base + hdr_at, 0, total - hdr_at, s);
+    IeBuildArgs a{};
+    a.base = (uint8_t*)t->d_base;
+    a.arena_off = slots_bytes;
+    a.arena_bytes = arena_bytes;
+    a.hdr = (IeTableHeader*)((uint8_t*)t->d_base + hdr_at);
+    a.used = (uint32_t*)((uint8_t*)t->d_base + used_at);
+    a.state_offs = (const uint64_t*)(d_stage + o_so);
+    a.slot_base = (const uint64_t*)(d_stage + o_sb);
+    a.slot_cap = (const uint32_t*)(d_stage + o_sc);
+    a.slot_of = (uint32_t*)(d_stage + o_sl);
+    a.keys = d_stage + o_k; a.key_offs = (const uint64_t*)(d_stage + o_ko);
+    a.vals = d_stage + o_v; a.val_offs = (const uint64_t*)(d_stage + o_vo);
+    a.tags = d_stage + o_tg;
+    a.clock = d_stage + o_ck;
+    a.hhmm_len = (uint32_t)hm; a.hhmmss_len = (uint32_t)hs;
+    a.n = n;
+    a.n_states = (uint32_t)n_states;
+    a.with_clock = (hhmm ? 1u : 0u) | (hhmmss ? 2u : 0u);
+    if (err == cudaSuccess) err = cudaEventRecord(ev_a, s);
+    if (err == cudaSuccess) err = ie_launch_table_build(a, (IeTableView*)((uint8_t*)t->d_base + views_at), s);
+    if (err == cudaSuccess) err = cudaEventRecord(ev_b, s);
+    IeTableHeader hdr{};
+    IeTableView v0{};
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&hdr, a.hdr, sizeof hdr, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&v0, (uint8_t*)t->d_base + views_at, sizeof v0, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    if (err == cudaSuccess) cudaEventElapsedTime(&ms, ev_a, ev_b);
+    cudaEventDestroy(ev_a);
+    cudaEventDestroy(ev_b);
+    if (err != cudaSuccess) return bail(err);
+    cudaFreeAsync(d_stage, s);
+    d_stage = nullptr;
+    if (hdr.error) {
+        const uint32_t code = hdr.error;
+        bail(cudaSuccess);
+        return fail(IE_E_INVALID, std::string(who) + ((code & 1) ? ": offsets not monotone, key longer than 4 GiB, value longer than 32 MiB or bad tag"
+                                                                   : ": internal error while building the table (code " + std::to_string(code) + ")"));
+    }
+    err = cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(t->ready, s);
+    if (err != cudaSuccess) return bail(err);
+    t->view = v0;
+    t->d_views = (const IeTableView*)((uint8_t*)t->d_base + views_at);
+    t->has_balanced = (hdr.flags & 1u) != 0;
+    t->arena_off = slots_bytes;
+    t->arena_bytes = arena_bytes;
+    t->d_hdr = a.hdr;
+    t->d_used = a.used;
+    t->build_ms = ms;
+    *out = t;
+    return IE_OK;
+}
+
 ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* state_offs, const uint8_t* keys, const uint64_t* key_offs,
                                const uint8_t* vals, const uint64_t* val_offs, const uint8_t* tags, const char* hhmm, const char* hhmmss,
                                ie_table** out) {
@@ -311,33 +474,94 @@ ie_status_t ie_table_pack_many(ie_engine* e, uint64_t n_states, const uint64_t* 
     if (n_states > 0x7FFFFFFFull) return fail(IE_E_INVALID, "ie_table_pack_many: too many snapshots");
     if (state_offs[n_states] && (!keys || !key_offs || !vals || !val_offs || !tags)) return fail(IE_E_INVALID, "ie_table_pack_many: NULL argument");
     *out = nullptr;
-    std::vector<std::vector<uint8_t>> images(n_states);
-    std::vector<uint32_t> caps(n_states, 0), counts(n_states, 0);
-    std::vector<std::string> whys(n_states);
-    std::atomic<uint64_t> next{0};
-    std::atomic<int> bad{0};
-    auto work = [&]() {
-        for (;;) {
-            const uint64_t s = next.fetch_add(1);
-            if (s >= n_states) return;
-            const uint64_t lo = state_offs[s], hi = state_offs[s + 1];
-            if (hi < lo) { whys[s] = "state offsets not monotone"; bad = 1; continue; }
-            counts[s] = (uint32_t)(hi - lo);
-            if (!ie_host::build_table_image(hi - lo, keys, key_offs + lo, vals, val_offs + lo, tags + lo, hhmm, hhmmss, &images[s], &caps[s],
-                                            &whys[s], /*compact=*/true))
-                bad = 1;
-        }
-    };
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    const unsigned nthreads = n_states >= 256 ? hw : 1;
-    std::vector<std::thread> pool;
-    for (unsigned k = 1; k < nthreads; ++k) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
-    if (bad)
-        for (uint64_t s = 0; s < n_states; ++s)
-            if (!whys[s].empty()) return fail(IE_E_INVALID, "ie_table_pack_many: snapshot " + std::to_string(s) + ": " + whys[s]);
-    return upload_tables(e, images, caps, counts, out, "ie_table_pack_many");
+    return build_on_device(e, n_states, state_offs, keys, key_offs, vals, val_offs, tags, hhmm, hhmmss, /*compact=*/true, out, "ie_table_pack_many");
+}
+
+double ie_table_build_ms(const ie_table* t) { return t ? t->build_ms : 0.0; }
+
+// set_interpdata / delete_interpdata (interp.rs:139-145) on the device table, in place.
+static ie_status_t mutate(ie_engine* e, ie_table* t, uint32_t state, uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals,
+                          const uint64_t* val_offs, const uint8_t* tags, const uint32_t* entries, const char* who) {
+    if (!e || !t || (n && (!keys && key_offs && key_offs[n]))) return fail(IE_E_INVALID, std::string(who) + ": NULL argument");
+    if (n && !key_offs) return fail(IE_E_INVALID, std::string(who) + ": NULL argument");
+    if (t->e != e) return fail(IE_E_INVALID, std::string(who) + ": the table belongs to another engine");
+    if (state != IE_ALL_STATES && state >= t->n_states) return fail(IE_E_INVALID, std::string(who) + ": snapshot index out of range");
+    if (n > 0xFFFFFFFFull) return fail(IE_E_INVALID, std::string(who) + ": too many operations");
+    if (!n) return IE_OK;
+    const bool is_set = vals != nullptr || val_offs != nullptr;
+    if (is_set && (!val_offs || !tags)) return fail(IE_E_INVALID, std::string(who) + ": NULL argument");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint64_t kbytes = key_offs[n], vbytes = is_set ? val_offs[n] : 0;
+    std::vector<uint8_t> flags(is_set ? n : 0);
+    bool balanced = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (key_offs[i + 1] < key_offs[i] || key_offs[i + 1] - key_offs[i] >= IE_SLOT_TOMB) return fail(IE_E_INVALID, std::string(who) + ": bad key offsets");
+        if (!is_set) continue;
+        if (val_offs[i + 1] < val_offs[i] || val_offs[i + 1] - val_offs[i] > IE_VLEN_MAX || tags[i] > IE_TAG_OBJECT)
+            return fail(IE_E_INVALID, std::string(who) + ": bad value offsets, value longer than 32 MiB or bad tag");
+        flags[i] = (uint8_t)ie_classify_value(vals + val_offs[i], val_offs[i + 1] - val_offs[i]);
+        balanced |= (flags[i] & IE_VF_BALANCED) != 0;
+    }
+    auto up16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
+    const uint64_t o_ko = 0, o_vo = o_ko + up16((n + 1) * 8), o_tg = o_vo + up16((n + 1) * 8), o_fl = o_tg + up16(n), o_en = o_fl + up16(n);
+    const uint64_t o_k = o_en + up16(n * 4), o_v = o_k + up16(kbytes), stage_total = o_v + up16(vbytes) + 16;
+    // one staged block, one copy
+    std::vector<uint8_t> blk(stage_total, 0);
+    std::memcpy(blk.data() + o_ko, key_offs, (n + 1) * 8);
+    if (kbytes) std::memcpy(blk.data() + o_k, keys, kbytes);
+    if (is_set) {
+        std::memcpy(blk.data() + o_vo, val_offs, (n + 1) * 8);
+        std::memcpy(blk.data() + o_tg, tags, n);
+        std::memcpy(blk.data() + o_fl, flags.data(), n);
+        if (entries) std::memcpy(blk.data() + o_en, entries, n * 4);
+        if (vbytes) std::memcpy(blk.data() + o_v, vals, vbytes);
+    }
+    uint8_t* d_stage = nullptr;
+    CU(cudaMallocAsync((void**)&d_stage, stage_total, s));
+    cudaError_t err = cudaMemcpyAsync(d_stage, blk.data(), stage_total, cudaMemcpyHostToDevice, s);
+    IeMutateArgs m{};
+    m.base = (uint8_t*)t->d_base;
+    m.arena_off = t->arena_off;
+    m.arena_bytes = t->arena_bytes;
+    m.hdr = t->d_hdr;
+    m.views = t->d_views;
+    m.used_slots = t->d_used;
+    m.state = state == IE_ALL_STATES ? 0u : state;
+    m.all_states = state == IE_ALL_STATES ? 1u : 0u;
+    m.n_ops = (uint32_t)n;
+    m.keys = d_stage + o_k; m.key_offs = (const uint64_t*)(d_stage + o_ko);
+    m.vals = is_set ? d_stage + o_v : nullptr; m.val_offs = (const uint64_t*)(d_stage + o_vo);
+    m.tags = d_stage + o_tg; m.flags = d_stage + o_fl;
+    m.entries = (is_set && entries) ? (const uint32_t*)(d_stage + o_en) : nullptr;
+    if (err == cudaSuccess) err = ie_launch_table_mutate(m, t->n_states, s);
+    IeTableHeader hdr{};
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&hdr, t->d_hdr, sizeof hdr, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess && hdr.error) {}  // (read below, after the synchronisation)
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    cudaFreeAsync(d_stage, s);
+    if (err != cudaSuccess) return cuda_fail(err, who);
+    if (balanced) t->has_balanced = true;
+    if (hdr.error) {
+        const uint32_t zero = 0;  // the table stays usable: clear the flag, report which room ran out
+        cudaMemcpyAsync(&t->d_hdr->error, &zero, sizeof zero, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);
+        return fail(IE_E_OVERFLOW, std::string(who) + ((hdr.error & 8) ? ": the snapshot's slot array is more than three quarters full"
+                                                                       : ": the table's arena is full") +
+                                       " - the operations that did not fit were skipped; pack the snapshot again");
+    }
+    return IE_OK;
+}
+
+ie_status_t ie_table_set(ie_engine* e, ie_table* t, uint32_t state, uint64_t n, const uint8_t* keys, const uint64_t* key_offs, const uint8_t* vals,
+                         const uint64_t* val_offs, const uint8_t* tags, const uint32_t* entries) {
+    static const uint8_t none = 0;
+    if (n && !val_offs) return fail(IE_E_INVALID, "ie_table_set: NULL argument");
+    return mutate(e, t, state, n, keys, key_offs, vals ? vals : &none, val_offs, tags, entries, "ie_table_set");
+}
+
+ie_status_t ie_table_delete(ie_engine* e, ie_table* t, uint32_t state, uint64_t n, const uint8_t* keys, const uint64_t* key_offs) {
+    return mutate(e, t, state, n, keys, key_offs, nullptr, nullptr, nullptr, nullptr, "ie_table_delete");
 }
 
 uint32_t ie_table_states(const ie_table* t) { return t ? t->n_states : 0; }

@@ -89,3 +89,30 @@ IE_HD uint32_t ie_hash_bytes(const uint8_t* p, uint32_t len) {
     }
     return ie_fmix32(h ^ len);
 }
+
+// Value flags (IE_VF_*), computed once per insert when a table is built or patched: what makes the fast path hand a
+// template to the general path when this value is spliced into text (interp.rs:81-83 rescans the spliced value;
+// interp.rs:40-43's sentinels collide).  Host (ie_table.cpp) and device (ie_table_build.cu) share this definition.
+IE_HD uint32_t ie_classify_value(const uint8_t* v, uint64_t n) {
+    uint32_t f = 0;
+    int64_t depth = 0;
+    bool nested_ok = true;
+    if (n && v[n - 1] == '\\') f |= IE_VF_TRAIL_BS;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t c = v[i];
+        if (c == '{' || c == '}') {
+            const bool esc = i > 0 && v[i - 1] == '\\';
+            if (!esc) {
+                f |= IE_VF_BRACE;
+                depth += c == '{' ? 1 : -1;
+                if (depth < 0) nested_ok = false;
+            }
+            else if (c == '}' && (i == 1 || v[i - 2] == '.' || v[i - 2] == '}')) f |= IE_VF_QUIRK;
+        } else if (c == 0xA0 && i >= 2 && v[i - 1] == 0x80 && v[i - 2] == 0xE3) f |= IE_VF_QUIRK;
+    }
+    if (f == IE_VF_BRACE && nested_ok && depth == 0) f |= IE_VF_BALANCED;
+    return f;
+}
+
+// A deleted slot (ie_table_delete): not empty, so probe chains run through it, and its key length matches no key.
+#define IE_SLOT_TOMB 0xFFFFFFFEu

@@ -162,3 +162,42 @@ cudaError_t ie_launch_glob_first_long(const uint8_t* d_keys, const uint64_t* d_k
                                       const uint64_t* d_pat_offs, uint32_t n_pat, uint32_t* d_first, cudaStream_t stream);
 cudaError_t ie_launch_glob(const uint8_t* d_keys, const uint64_t* d_key_offs, uint64_t n, const IeGlobPatterns& pats,
                            uint32_t* d_mask, uint64_t* d_n_deleted, uint32_t* d_first, cudaStream_t stream);
+
+// ---- device-side table build and in-place mutation (ie_table_build.cu) ------------------------------------------------
+struct IeTableHeader {     // lives behind the view array of a table
+    uint64_t arena_used;   // bytes of the arena handed out so far (bump allocator)
+    uint32_t flags;        // bit 0: some value holds properly nested groups of its own (rescan rounds can do work)
+    uint32_t error;        // 1 bad input arrays, 2 probe chain exhausted, 4 arena full, 8 slot array too full for an insert
+};
+struct IeBuildArgs {
+    uint8_t* base;               // the table allocation
+    uint64_t arena_off, arena_bytes;
+    IeTableHeader* hdr;
+    uint32_t* used;              // [n_states] non-empty slots per snapshot
+    const uint64_t* state_offs;  // [n_states + 1] (device copies of the caller's arrays from here on)
+    const uint64_t* slot_base;   // [n_states] first slot of each snapshot, in slots from `base`
+    const uint32_t* slot_cap;    // [n_states] power of two
+    uint32_t* slot_of;           // [items] scratch: the slot each item probed to
+    const uint8_t* keys; const uint64_t* key_offs;
+    const uint8_t* vals; const uint64_t* val_offs;
+    const uint8_t* tags;
+    const uint8_t* clock;        // "HH:MM" at 0, "HH:MM:SS" at 8, their renderings at 16 and 80 (<= 64 bytes each)
+    uint32_t hhmm_len, hhmmss_len;
+    uint64_t n;                  // caller inserts (all snapshots)
+    uint32_t n_states;
+    uint32_t with_clock;         // bit 0: "HH:MM" given, bit 1: "HH:MM:SS" given
+};
+struct IeMutateArgs {
+    uint8_t* base;
+    uint64_t arena_off, arena_bytes;
+    IeTableHeader* hdr;
+    const IeTableView* views;
+    uint32_t* used_slots;        // [n_states] non-empty slots (live + tombstones)
+    uint32_t state, all_states, n_ops;
+    const uint8_t* keys; const uint64_t* key_offs;
+    const uint8_t* vals; const uint64_t* val_offs;  // vals == nullptr: delete
+    const uint8_t* tags; const uint8_t* flags;      // per op: JSON type, IE_VF_* of the value (classified by the host)
+    const uint32_t* entries;                        // per op: what a typed result reports in aux (nullptr: IE_AUX_NONE)
+};
+cudaError_t ie_launch_table_build(const IeBuildArgs& a, IeTableView* d_views, cudaStream_t stream);
+cudaError_t ie_launch_table_mutate(const IeMutateArgs& m, uint32_t n_states, cudaStream_t stream);

@@ -11,29 +11,6 @@ namespace ie_host {
 
 namespace {
 
-// Flags that make the fast path hand a template to the general path when this value is spliced
-// into text (interp.rs:81-83 rescans the spliced value; interp.rs:40-43's sentinels collide).
-uint32_t classify_value(const uint8_t* v, uint64_t n) {
-    uint32_t f = 0;
-    int64_t depth = 0;
-    bool nested_ok = true;
-    if (n && v[n - 1] == '\\') f |= IE_VF_TRAIL_BS;
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint8_t c = v[i];
-        if (c == '{' || c == '}') {
-            const bool esc = i > 0 && v[i - 1] == '\\';
-            if (!esc) {
-                f |= IE_VF_BRACE;
-                depth += c == '{' ? 1 : -1;
-                if (depth < 0) nested_ok = false;
-            }
-            else if (c == '}' && (i == 1 || v[i - 2] == '.' || v[i - 2] == '}')) f |= IE_VF_QUIRK;
-        } else if (c == 0xA0 && i >= 2 && v[i - 1] == 0x80 && v[i - 2] == 0xE3) f |= IE_VF_QUIRK;
-    }
-    if (f == IE_VF_BRACE && nested_ok && depth == 0) f |= IE_VF_BALANCED;
-    return f;
-}
-
 struct Entry {
     const uint8_t* key; uint64_t key_len;
     const uint8_t* val; uint64_t val_len;
@@ -108,7 +85,7 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
                 kcur += pad16(en.key_len);
             }
         }
-        const uint32_t vflags = classify_value(en.val, en.val_len);
+        const uint32_t vflags = ie_classify_value(en.val, en.val_len);
         if (any_balanced && (vflags & IE_VF_BALANCED)) *any_balanced = true;
         s->vl_tf = (uint32_t)en.val_len | (en.tag << 25) | (vflags << 28);
         s->entry = en.index;

@@ -173,8 +173,8 @@ def c5_pattern_sets(n_sets=64, seed=0xC5, n_persona=100000, n_field=100):
 def example_batches():
     """The reference's example programs as resolver batches: for each `examples/*.json5`, its default_state and the
     strings recursive_interpolate sends to the resolver for every top-level task, in order.  Derived from the files by
-    oracle/gen_golden.py (load_program + the interp.rs:179-246 traversal) and committed as data/example_batches.json;
-    tests/test_oracle_golden.py re-derives it from the reference tree when that is present."""
+    the test tooling's `gen_golden.py examples` (load_program + the interp.rs:179-246 traversal) and committed as
+    data/example_batches.json; the CPU test suite re-derives it from the reference tree when that is present."""
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "example_batches.json")) as f:
         return json.load(f)
 

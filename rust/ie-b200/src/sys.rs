@@ -70,6 +70,10 @@ extern "C" {
     pub fn ie_table_free(t: *mut ie_table);
     pub fn ie_table_device_bytes(t: *const ie_table) -> u64;
     pub fn ie_table_states(t: *const ie_table) -> u32;
+    pub fn ie_table_build_ms(t: *const ie_table) -> f64;
+    pub fn ie_table_set(e: *mut ie_engine, t: *mut ie_table, state: u32, n: u64, keys: *const u8, key_offs: *const u64,
+                        vals: *const u8, val_offs: *const u64, tags: *const u8, entries: *const u32) -> ie_status_t;
+    pub fn ie_table_delete(e: *mut ie_engine, t: *mut ie_table, state: u32, n: u64, keys: *const u8, key_offs: *const u64) -> ie_status_t;
 
     pub fn ie_resolve_batch(e: *mut ie_engine, t: *const ie_table, tmpl: *const u8, tmpl_offs: *const u64, n: u64,
                             limits: *const ie_limits, res: *mut ie_result) -> c_int;

@@ -536,6 +536,138 @@ def test_replace_map_goto_map_on_gpu(eng, oracle):
     assert list(first) == [1, 2, 2, 0]
 
 
+# ---- device-built tables and in-place mutation (interp.rs:139-145; VERDICT r01 missing #1) -----------------------------
+def _oracle_batch(oracle, inserts, templates):
+    arena = ie.Arena.from_strings(templates)
+    return oracle.build_table(ie.PackedInserts.from_dict(inserts)).resolve_batch(arena.bytes, arena.offs)
+
+
+def _assert_batch_equals_oracle(oracle, got, base, inserts, templates, ctx):
+    out, offs, status, _ = _oracle_batch(oracle, inserts, templates)
+    n = len(templates)
+    assert np.array_equal(got.status[base:base + n], status), (ctx, got.status[base:base + n], status)
+    for j in range(n):
+        assert got.get(base + j) == out[int(offs[j]):int(offs[j + 1])].tobytes(), (ctx, templates[j])
+
+
+def test_device_built_tables(eng, oracle):
+    """ie_table_pack_many (and ie_table_pack from 4096 inserts) build their tables on the device: one thread per insert
+    hashes, claims a slot, classifies and copies.  Same results as the host-built table of every snapshot and as the
+    oracle: duplicate keys (the later insert wins), keys / values around the 16-byte inline limit, empty snapshots,
+    clock keys shadowing inserts, values with every flag."""
+    rng = random.Random(0xB17D)
+    words = ["", "v", "x" * 15, "y" * 16, "z" * 17, "long value " * 9, "{a}", "a{b}c", BS + "{q" + BS + "}", "." + BS + "}", "t" + BS, "}", "\u3020", "{a"]
+    keyset = ["a", "b", "k" * 16, "K" * 17, "key with spaces and more than sixteen bytes", "HH:MM", "HH:MM:SS", "ARG1", "n", "", "é"]
+    states, packs = [], []
+    for s in range(300):
+        st = {}
+        for k in rng.sample(keyset, rng.randint(0, len(keyset))):
+            st[k] = rng.choice(words + [7, -12, True, None, ["p", 1], {"o": 1}])
+        states.append(st)
+        packs.append(ie.PackedInserts.from_dict(st))
+    # a snapshot whose packed arrays hold the same key three times: Map::insert semantics, the last one wins
+    dup = ie.PackedInserts(np.frombuffer(b"aab" + b"a", np.uint8), np.array([0, 1, 2, 3, 4], np.uint64), np.frombuffer(b"1" + b"22" + b"B" + b"333", np.uint8),
+                           np.array([0, 1, 3, 4, 7], np.uint64), np.array([3, 3, 3, 2], np.uint8))
+    states.append({"a": 333, "b": "B"})
+    packs.append(dup)
+    templates = ["{a}", "<{a}|{b}>", "{%s}" % ("k" * 16), "x{%s}" % ("K" * 17), "{key with spaces and more than sixteen bytes}", "t={HH:MM} {HH:MM:SS}", "{ARG1}",
+                 "{n}", "n={n}", "{}", "{é}", "{missing}", "plain", "{{a}}", "q{{a}}"]
+    table = eng.pack_many(packs, hhmm="12:34", hhmmss="12:34:56")
+    assert table.build_ms > 0
+    got = eng.resolve_batch(table, templates)
+    n = len(templates)
+    arena = ie.Arena.from_strings(templates)
+    for s, pk in enumerate(packs):
+        out, offs, status, _ = oracle.build_table(pk).resolve_batch(arena.bytes, arena.offs, hhmm="12:34", hhmmss="12:34:56")
+        assert np.array_equal(got.status[s * n:(s + 1) * n], status), (s, states[s])
+        for j in range(n):
+            assert got.get(s * n + j) == out[int(offs[j]):int(offs[j + 1])].tobytes(), (s, templates[j], states[s])
+        if s % 29 == 0:  # and identical to the host-built table of the same snapshot, typed-result entries included
+            one = eng.resolve_batch(eng.pack(pk, hhmm="12:34", hhmmss="12:34:56"), templates)
+            assert np.array_equal(one.status_raw, got.status_raw[s * n:(s + 1) * n])
+            typed = (one.status_raw & 0xFF) == ie.RES_TYPED
+            assert np.array_equal(one.aux[typed], got.aux[s * n:(s + 1) * n][typed]), s
+    assert got.get((len(packs) - 1) * n) == b"333" and got.aux[(len(packs) - 1) * n] == 3  # the third "a" of the duplicate snapshot
+    # one large snapshot (>= 4096 inserts): device-built too; against the oracle
+    big = {"key-%d" % k: ("value %d " % k) * (k % 5) for k in range(6000)}
+    big.update({"i": 17, "deep": "{key-{i}}"})
+    tb = eng.pack(ie.PackedInserts.from_dict(big))
+    assert tb.build_ms > 0
+    tpl = ["{key-%d}|{key-{i}}" % k for k in range(0, 6000, 7)] + ["{deep}", "x{deep}", "{key-6000}"]
+    _assert_batch_equals_oracle(oracle, eng.resolve_batch(tb, tpl), 0, big, tpl, "big")
+    # bad packed arrays are refused, not built
+    bad = ie.PackedInserts(np.frombuffer(b"ab", np.uint8), np.array([0, 1, 2], np.uint64), np.frombuffer(b"xy", np.uint8), np.array([0, 1, 2], np.uint64),
+                           np.array([3, 9], np.uint8))
+    with pytest.raises(ie.EngineError, match="bad tag"):
+        eng.pack_many([bad, bad])
+
+
+def test_table_set_delete_in_place(eng, oracle):
+    """set_interpdata / delete_interpdata on the device table (ie_table_set / ie_table_delete) interleaved with resolves,
+    against the oracle on a dict that follows the same operations: overwrite (shorter, longer, across the inline limit),
+    new keys, delete and re-insert through tombstones, per-snapshot and all-snapshot operations, overflow reporting."""
+    rng = random.Random(0x5E7)
+    values = ["", "v", "x" * 15, "y" * 16, "z" * 17, "long value " * 9, "another long value " * 20, "{a}", "a{b}c", "." + BS + "}", 3, -5, ["l", 2], True]
+    keys = ["a", "b", "c", "k" * 16, "K" * 17, "a key that is clearly longer than sixteen bytes", "i", "q-1", "q-2", "q-3"]
+    templates = ["{a}", "<{a}|{b}|{c}>", "{%s}" % ("k" * 16), "x{%s}" % ("K" * 17), "{a key that is clearly longer than sixteen bytes}!", "{q-{i}}", "{i}", "{missing}",
+                 "{{b}}"]
+    # (1) one snapshot, host-built (small) and device-built (large) tables
+    for size in (0, 5000):
+        cur = {"pad-%d" % k: "p%d" % k for k in range(size)}
+        cur.update({"a": "A", "i": 1, "q-1": "first"})
+        table = eng.pack(ie.PackedInserts.from_dict(cur))
+        for step in range(60):
+            if rng.random() < 0.7:
+                ops = [(rng.choice(keys), rng.choice(values)) for _ in range(rng.randint(1, 4))]
+                # values with groups of their own only under "c", which no value refers to: no reference cycles (those
+                # are test_limits_escalate_to_hard_caps' subject and take a second each)
+                ops = [(k, v) if not (isinstance(v, str) and "{" in v) else ("c", v) for k, v in ops]
+                table.set(ops)
+                for k, v in ops:
+                    cur[k] = v
+            else:
+                ks = [rng.choice(keys + ["never-there"]) for _ in range(rng.randint(1, 3))]
+                table.delete(ks)
+                for k in ks:
+                    cur.pop(k, None)
+            _assert_batch_equals_oracle(oracle, eng.resolve_batch(table, templates), 0, cur, templates, (size, step))
+    # typed results report the entry the caller attached to the insert
+    table = eng.pack(ie.PackedInserts.from_dict({"a": 1}))
+    table.set([("b", ["x", "y"]), ("a", {"o": 2})], entries=[41, 42])
+    res = eng.resolve_batch(table, ["{b}", "{a}"])
+    assert [int(x) for x in res.aux] == [41, 42] and [int(x) >> 8 for x in res.status_raw] == [ie.TAG_ARRAY, ie.TAG_OBJECT]
+    # (2) many snapshots: operations on one snapshot and on all of them
+    states = [{"a": "s%d" % s, "i": s % 3 + 1, "q-1": "one", "q-2": "two", "q-3": "three"} for s in range(200)]
+    table = eng.pack_many([ie.PackedInserts.from_dict(st) for st in states])
+    table.set({"b": "everywhere", "c": "long shared value " * 5})
+    for st in states:
+        st.update({"b": "everywhere", "c": "long shared value " * 5})
+    for s in (0, 7, 199):
+        table.set({"a": "patched %d " % s * 3, "new-%d" % s: s}, state=s)
+        states[s].update({"a": "patched %d " % s * 3, "new-%d" % s: s})
+        table.delete(["q-2"], state=s)
+        states[s].pop("q-2")
+    table.delete(["q-3", "c"])
+    for st in states:
+        st.pop("q-3", None), st.pop("c", None)
+    tpl = templates + ["{new-7}", "{new-0}{new-199}"]
+    got = eng.resolve_batch(table, tpl)
+    for s in (0, 1, 2, 7, 8, 100, 199):
+        _assert_batch_equals_oracle(oracle, got, s * len(tpl), states[s], tpl, ("many", s))
+    # (3) a table has finite spare room: running out is reported, the table stays consistent, a fresh pack takes over
+    cur = {"a": "A"}
+    table = eng.pack(ie.PackedInserts.from_dict(cur))
+    with pytest.raises(ie.EngineError, match="pack the snapshot again"):
+        for k in range(100000):
+            table.set({"grow-%d" % k: "a value that needs arena space %d" % k})
+            cur["grow-%d" % k] = "a value that needs arena space %d" % k
+    assert k > 4
+    cur.pop("grow-%d" % k, None)  # the operation that did not fit was skipped
+    tpl = ["{a}", "{grow-0}", "{grow-%d}" % (k - 1), "{grow-%d}" % k]
+    _assert_batch_equals_oracle(oracle, eng.resolve_batch(table, tpl), 0, cur, tpl, "overflow")
+    _assert_batch_equals_oracle(oracle, eng.resolve_batch(eng.pack(ie.PackedInserts.from_dict(cur)), tpl), 0, cur, tpl, "repacked")
+
+
 def test_limits_escalate_to_hard_caps(eng, oracle):
     """IE_RES_LIMIT means "the reference would not finish within the hard caps", not "deeper than the first guess": the
     host-buffer calls re-run templates that stopped at a default bound with 8x bounds.  Every case
