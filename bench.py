@@ -302,6 +302,57 @@ def main():
         lib.ie_host_free(h_t)
         lib.ie_host_free(h_o)
 
+    # ---- e2e, single process: ONE host batch of world * n templates sharded over all GPUs by ie_resolve_batch_multi
+    # (one host thread + stream set per device inside the call), then the host gather.  Rank 0 drives every GPU of the
+    # box while the other ranks wait at the barrier with their devices idle.
+    multi = None
+    if world > 1 and not args.no_e2e:
+        barrier()
+        if rank == 0:
+            lib = eng.lib
+            engines = [eng] + [ie.Engine(d) for d in range(1, world)]
+            tables = [table] + [e2.pack(state) for e2 in engines[1:]]
+            big = workloads.c4_templates(world * n)
+            p_t, p_o = ctypes.c_void_p(), ctypes.c_void_p()
+            eng._check(lib.ie_host_alloc(big.bytes.nbytes, ctypes.byref(p_t)))
+            eng._check(lib.ie_host_alloc(big.offs.nbytes, ctypes.byref(p_o)))
+            ctypes.memmove(p_t.value, big.bytes.ctypes.data, big.bytes.nbytes)
+            ctypes.memmove(p_o.value, big.offs.ctypes.data, big.offs.nbytes)
+            eh = (ctypes.c_void_p * world)(*[e2.handle for e2 in engines])
+            th = (ctypes.c_void_p * world)(*[t2.handle for t2 in tables])
+            shards = (ie._ShardResult * world)()
+
+            def call():
+                eng._check(lib.ie_resolve_batch_multi(eh, th, world, p_t, p_o, world * n, None, shards))
+            for _ in range(2):
+                call()
+            m_steps = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(m_steps):
+                call()
+            m_s = (time.perf_counter() - t0) / m_steps
+            # the host gather (concatenation in template order), timed by itself
+            total = sum(int(np.frombuffer((ctypes.c_char * (int(sh.n) * 4)).from_address(sh.res.out_lens), dtype=np.uint32).sum(dtype=np.uint64)) for sh in shards)
+            g_out = np.empty(total, dtype=np.uint8)
+            g_offs = np.empty(world * n + 1, dtype=np.uint64)
+            g_st = np.empty(world * n, dtype=np.int32)
+            g_ax = np.empty(world * n, dtype=np.uint32)
+            ob = ctypes.c_uint64(0)
+            t0 = time.perf_counter()
+            eng._check(lib.ie_shards_gather(shards, world, g_out.ctypes.data, total, g_offs.ctypes.data, g_st.ctypes.data, g_ax.ctypes.data, ctypes.byref(ob)))
+            gather_s = time.perf_counter() - t0
+            multi = {"value": world * n / m_s, "unit": "strings/s", "ms_per_step": m_s * 1e3, "host_gather_ms": gather_s * 1e3,
+                     "with_host_gather": world * n / (m_s + gather_s), "steps": m_steps,
+                     "what": "ie_resolve_batch_multi: one process, one host batch of %d templates, contiguous shards over %d GPUs, one host thread per device; "
+                             "ie_shards_gather concatenates %d result bytes in template order" % (world * n, world, total)}
+            for t2 in tables[1:]:
+                t2.free()
+            for e2 in engines[1:]:
+                e2.close()
+            lib.ie_host_free(p_t)
+            lib.ie_host_free(p_o)
+        barrier()
+
     # ---- reduce over ranks: max time, summed work ----
     from interpolation_engine_b200 import sharding
     total_ms_max, _ = sharding.reduce_timing(dist if world > 1 else None, total_ms, n * args.steps)
@@ -333,6 +384,8 @@ def main():
         if e2e:
             line["e2e"] = {"value": world * n / e2e_s_max, "unit": "strings/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "ms_per_step": e2e_s_max * 1e3, "kernel_ms_inside": e2e["kernel_ms"], "timing": "wall clock around ie_resolve_batch (synchronous), pinned host arenas"}
+            if multi:
+                line["e2e"]["single_process"] = multi
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = n

@@ -168,8 +168,27 @@ typedef struct {
     const uint32_t* aux;      /* [n] insert entry index for IE_RES_TYPED */
     ie_batch_info info;
 } ie_result;
+/* tmpl_offs[0] need not be 0: (tmpl, tmpl_offs + k) is a shard of a larger arena, only its bytes are copied. */
 ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmpl, const uint64_t* tmpl_offs,
                              uint64_t n, const ie_limits* limits, ie_result* res);
+
+/* Several GPUs of one box, one process (SURVEY.md §8 e): templates are independent given an immutable snapshot, so
+ * ONE host batch is cut into contiguous shards of ceil(n / n_engines) templates, shard g goes through engines[g] (one
+ * host thread and one set of streams per device; tables[g] = the snapshot packed on that engine) and there is no
+ * device-to-device traffic.  shards[g] describes shard g: templates [first, first + n), results in res (owned by
+ * engines[g] until its next call, like ie_resolve_batch's).  ie_shards_gather is the host gather: it concatenates the
+ * shards' results in template order into caller arrays (out_offs gets n + 1 entries, contiguous). */
+typedef struct {
+    uint64_t first, n;   /* the shard's templates */
+    ie_result res;       /* indices relative to `first` */
+    ie_status_t status;  /* of this shard's call */
+    char error[160];
+} ie_shard_result;
+ie_status_t ie_resolve_batch_multi(ie_engine* const* engines, const ie_table* const* tables, uint32_t n_engines,
+                                   const uint8_t* tmpl, const uint64_t* tmpl_offs, uint64_t n, const ie_limits* limits,
+                                   ie_shard_result* shards);
+ie_status_t ie_shards_gather(const ie_shard_result* shards, uint32_t n_shards, uint8_t* out, uint64_t out_capacity,
+                             uint64_t* out_offs, int32_t* status, uint32_t* aux, uint64_t* out_bytes);
 
 /* Device-buffer form (inputs and outputs already resident in HBM; asynchronous on `stream`,
  * which may be NULL for the engine's own stream).  `d_info` is a device ie_batch_info. */
@@ -226,6 +245,9 @@ void ie_device_free(ie_engine* e, void* d_ptr);
 ie_status_t ie_copy_to_device(ie_engine* e, void* d_dst, const void* h_src, uint64_t bytes);
 ie_status_t ie_copy_to_host(ie_engine* e, void* h_dst, const void* d_src, uint64_t bytes);
 ie_status_t ie_host_alloc(uint64_t bytes, void** h_ptr); /* page-locked host memory for the host-buffer calls */
+/* write-combined page-locked memory: for INPUT arenas the host only writes (reads from it are slow); the device reads
+ * it without snooping the CPU caches */
+ie_status_t ie_host_alloc_wc(uint64_t bytes, void** h_ptr);
 void ie_host_free(void* h_ptr);
 
 /* ---- JSON-level mirror of the interp.rs public functions (host logic above the batch ABI) ----

@@ -16,7 +16,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Engine", "Table", "PackedInserts", "Arena", "EngineError", "load_library", "LIB_PATH",
+__all__ = ["Engine", "Table", "PackedInserts", "Arena", "EngineError", "load_library", "LIB_PATH", "resolve_batch_multi",
            "RES_STRING", "RES_TYPED", "RES_UNEVEN", "RES_UNSUPPORTED", "RES_EMPTY_KEY", "RES_ARG_MISSING",
            "RES_NOT_FOUND", "RES_PANIC", "RES_LIMIT", "STATUS_NAMES"]
 
@@ -46,6 +46,10 @@ class _Result(ctypes.Structure):
 ALL_STATES = 0xFFFFFFFF  # IE_ALL_STATES
 
 
+class _ShardResult(ctypes.Structure):
+    _fields_ = [("first", ctypes.c_uint64), ("n", ctypes.c_uint64), ("res", _Result), ("status", ctypes.c_int), ("error", ctypes.c_char * 160)]
+
+
 class _Limits(ctypes.Structure):
     _fields_ = [("max_expansions", ctypes.c_uint32), ("max_result_bytes", ctypes.c_uint32), ("avg_template_bytes", ctypes.c_uint32),
                 ("avg_template_groups", ctypes.c_uint32), ("rescan_rounds", ctypes.c_uint32)]
@@ -69,6 +73,8 @@ ABI = {
     "ie_table_free": (None, [_vp]),
     "ie_table_device_bytes": (_u64, [_vp]),
     "ie_resolve_batch": (_i, [_vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_Limits), ctypes.POINTER(_Result)]),
+    "ie_resolve_batch_multi": (_i, [_vp, _vp, _u32, _vp, _vp, _u64, ctypes.POINTER(_Limits), _vp]),
+    "ie_shards_gather": (_i, [_vp, _u32, _vp, _u64, _vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "ie_resolve_batch_device": (_i, [_vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_Limits), _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ie_lookup_batch": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "ie_escape_batch": (_i, [_vp, _i, _vp, _vp, _u64, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
@@ -81,6 +87,7 @@ ABI = {
     "ie_copy_to_device": (_i, [_vp, _vp, _vp, _u64]),
     "ie_copy_to_host": (_i, [_vp, _vp, _vp, _u64]),
     "ie_host_alloc": (_i, [_u64, ctypes.POINTER(_vp)]),
+    "ie_host_alloc_wc": (_i, [_u64, ctypes.POINTER(_vp)]),
     "ie_host_free": (None, [_vp]),
     "ie_call_json": (_i, [_vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t)]),
     "ie_free": (None, [_vp]),
@@ -240,6 +247,42 @@ class BatchResult:
     def get(self, i):
         o = int(self.offs[i])
         return self.out[o:o + int(self.lens[i])].tobytes()
+
+
+def resolve_batch_multi(engines, tables, templates, limits=None, gather=True):
+    """ie_resolve_batch_multi: ONE host batch cut into contiguous shards, shard g through engines[g] / tables[g] (one
+    host thread per engine inside the C call).  Returns (shards, gathered): the per-shard BatchResults and, with
+    gather=True, the host gather of ie_shards_gather as (out, offs[n+1], status, aux)."""
+    arena = templates if isinstance(templates, Arena) else Arena.from_strings(templates)
+    lib = engines[0].lib
+    G = len(engines)
+    eh = (ctypes.c_void_p * G)(*[e.handle for e in engines])
+    th = (ctypes.c_void_p * G)(*[t.handle for t in tables])
+    shards = (_ShardResult * G)()
+    lim = _Limits(*limits) if limits else None
+    engines[0]._check(lib.ie_resolve_batch_multi(eh, th, G, _ptr(arena.bytes), _ptr(arena.offs), arena.n, ctypes.byref(lim) if lim else None, shards))
+
+    def view(p, dtype, count):
+        if not count:
+            return np.zeros(0, dtype=dtype)
+        return np.frombuffer((ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(p), dtype=dtype, count=count).copy()
+    per = []
+    for sh in shards:
+        n, ob = int(sh.n), int(sh.res.info.out_bytes)
+        per.append((int(sh.first), BatchResult(view(sh.res.out, np.uint8, ob), view(sh.res.out_offs, np.uint64, n), view(sh.res.out_lens, np.uint32, n),
+                                               view(sh.res.status, np.int32, n), view(sh.res.aux, np.uint32, n),
+                                               (ob, int(sh.res.info.n_general), float(sh.res.info.kernel_ms)))))
+    gathered = None
+    if gather:
+        total = ctypes.c_uint64(0)
+        offs = np.zeros(arena.n + 1, dtype=np.uint64)
+        status = np.zeros(max(arena.n, 1), dtype=np.int32)
+        aux = np.zeros(max(arena.n, 1), dtype=np.uint32)
+        cap = sum(int(b.lens.sum()) for _, b in per)
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        engines[0]._check(lib.ie_shards_gather(shards, G, _ptr(out), cap, _ptr(offs), _ptr(status), _ptr(aux), ctypes.byref(total)))
+        gathered = (out[:int(total.value)], offs, status[:arena.n], aux[:arena.n])
+    return per, gathered
 
 
 class DeviceBuffer:

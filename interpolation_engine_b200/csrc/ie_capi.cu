@@ -75,6 +75,7 @@ struct ie_engine {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy engines of the pipelined host-buffer path
     std::vector<cudaEvent_t> ev_in, ev_done;
     double expand = 2.0;  // output bytes per input byte the pipelined path provisions (adapts upward)
+    uint64_t in_bias = 0; // tmpl_offs[0] of the batch in d_in: the arena may be a shard of a larger one, d_in holds bytes [offs[0], offs[n])
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // workspace
     DevBuf ws_zero, ws_list, ws_scratch;
@@ -639,7 +640,8 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         if (cut.back() + step < n) cut.push_back(cut.back() + step);
     while (cut.back() < n) cut.push_back(std::min(n, cut.back() + kPipeChunk));
     const uint64_t K = cut.size() - 1;
-    const uint64_t in_bytes = tmpl_offs[n];
+    const uint64_t base0 = tmpl_offs[0], in_bytes = tmpl_offs[n] - base0;
+    e->in_bias = base0;
     cudaStream_t sc = e->stream;
     while (e->ev_in.size() < K) {
         cudaEvent_t a, b;
@@ -676,7 +678,7 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
         ie_status_t st = prepare_workspace(e, kPipeChunk, tcap, true, &ws, 0, true);
         if (st != IE_OK) return st;
     }
-    const uint64_t groups_x16 = sample_groups_x16(tmpl, in_bytes, n);
+    const uint64_t groups_x16 = sample_groups_x16(tmpl + base0, in_bytes, n);
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
     ie_batch_info* hinfo_dev = nullptr;  // the same pinned block as the device sees it
     CU(cudaHostGetDevicePointer((void**)&hinfo_dev, hinfo, 0));
@@ -685,10 +687,10 @@ static ie_status_t resolve_pipelined(ie_engine* e, const ie_table* t, const uint
     for (uint64_t k = 0; k < K; ++k) {
         const uint64_t lo = cut[k], hi = cut[k + 1];
         const uint64_t b0 = tmpl_offs[lo], b1 = tmpl_offs[hi];
-        if (b1 > b0) CU(cudaMemcpyAsync((uint8_t*)e->d_in.p + b0, tmpl + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in));
+        if (b1 > b0) CU(cudaMemcpyAsync((uint8_t*)e->d_in.p + (b0 - base0), tmpl + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in));
         CU(cudaEventRecord(e->ev_in[k], e->s_in));
         CU(cudaStreamWaitEvent(sc, e->ev_in[k], 0));
-        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
+        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p - base0, (const uint64_t*)e->d_in_offs.p + lo, hi - lo, limits,
                                         (uint8_t*)e->d_out.p + base[k], base[k + 1] - base[k], (uint64_t*)e->d_out_offs.p + lo,
                                         (uint32_t*)e->d_out_lens.p + lo, (int32_t*)e->d_status.p + lo, (uint32_t*)e->d_aux.p + lo,
                                         (ie_batch_info*)e->d_info.p + k, base[k], sc, in_bytes / n, host_rounds(limits), groups_x16);
@@ -751,7 +753,7 @@ static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t*
                                  const ie_limits* limits, ie_result* res, bool* done) {
     *done = false;
     cudaStream_t s = e->stream;
-    const uint64_t in_bytes = tmpl_offs[n], nr = n * t->n_states;
+    const uint64_t base0 = tmpl_offs[0], in_bytes = tmpl_offs[n] - base0, nr = n * t->n_states;
     const size_t offs_bytes = (n + 1) * 8, in_total = offs_bytes + in_bytes;
     const size_t a_info = 0, a_offs = 64, a_lens = a_offs + nr * 8, a_stat = a_lens + nr * 4, a_aux = a_stat + nr * 4;
     const size_t a_arena = (a_aux + nr * 4 + 15) & ~size_t(15), res_total = a_arena + kSmallArena;
@@ -761,14 +763,14 @@ static ie_status_t resolve_small(ie_engine* e, const ie_table* t, const uint8_t*
     CU(e->h_small_res.ensure(res_total + 64));
     uint8_t* hin = (uint8_t*)e->h_small_in.p;
     std::memcpy(hin, tmpl_offs, offs_bytes);
-    if (in_bytes) std::memcpy(hin + offs_bytes, tmpl, in_bytes);
+    if (in_bytes) std::memcpy(hin + offs_bytes, tmpl + base0, in_bytes);
     CU(cudaMemcpyAsync(e->d_small_in.p, hin, in_total, cudaMemcpyHostToDevice, s));
     uint8_t* dres = (uint8_t*)e->d_small_res.p;
     CU(cudaEventRecord(e->ev0, s));
-    ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_small_in.p + offs_bytes, (const uint64_t*)e->d_small_in.p, n, limits,
+    ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_small_in.p + offs_bytes - base0, (const uint64_t*)e->d_small_in.p, n, limits,
                                     dres + a_arena, kSmallArena, (uint64_t*)(dres + a_offs), (uint32_t*)(dres + a_lens), (int32_t*)(dres + a_stat),
                                     (uint32_t*)(dres + a_aux), (ie_batch_info*)(dres + a_info), 0, s, n ? in_bytes / n : 0, host_rounds(limits),
-                                    sample_groups_x16(tmpl, in_bytes, n));
+                                    sample_groups_x16(tmpl + base0, in_bytes, n));
     if (st != IE_OK) return st;
     CU(cudaEventRecord(e->ev1, s));
     // results + the first part of the arena in one copy; the rest of the arena only if the batch produced more
@@ -839,7 +841,7 @@ static ie_status_t escalate_limits(ie_engine* e, const ie_table* t, uint64_t n, 
         ie_batch_info info2{};
         for (int attempt = 0;; ++attempt) {
             CU(cudaMemsetAsync(d_info2, 0, sizeof(ie_batch_info), s));
-            CU(ie_launch_general_escalate(t->d_views, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, (uint8_t*)e->d_out.p, cap,
+            CU(ie_launch_general_escalate(t->d_views, (const uint8_t*)e->d_in.p - e->in_bias, (const uint64_t*)e->d_in_offs.p, n, (uint8_t*)e->d_out.p, cap,
                                           (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p, (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, ws,
                                           d_info2, max_exp, tcap, *host_bytes, d_list, d_count, s));
             CU(cudaMemcpyAsync(&info2, d_info2, sizeof info2, cudaMemcpyDeviceToHost, s));
@@ -882,7 +884,9 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     if (!e || !t || !res || (n && (!tmpl_offs))) return fail(IE_E_INVALID, "ie_resolve_batch: NULL argument");
     std::memset(res, 0, sizeof *res);
     CU(cudaSetDevice(e->device));
-    const uint64_t in_bytes = n ? tmpl_offs[n] : 0;
+    const uint64_t base0 = n ? tmpl_offs[0] : 0;  // not 0 when the batch is a shard of a larger arena
+    if (n && tmpl_offs[n] < base0) return fail(IE_E_INVALID, "ie_resolve_batch: offsets not monotone");
+    const uint64_t in_bytes = n ? tmpl_offs[n] - base0 : 0;
     if (in_bytes && !tmpl) return fail(IE_E_INVALID, "ie_resolve_batch: NULL template arena");
     cudaStream_t s = e->stream;
     const uint64_t S = t->n_states, nr = n * S;  // every snapshot resolves all n templates: nr results, index = snapshot * n + template
@@ -905,8 +909,9 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     CU(e->d_info.ensure(sizeof(ie_batch_info), s));
     CU(e->h_info.ensure(sizeof(ie_batch_info)));
     CU(e->d_out.ensure(std::max<uint64_t>(in_bytes * 2 * S + (1u << 16), 1u << 20), s));
-    if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, tmpl, in_bytes, cudaMemcpyHostToDevice, s));
+    if (in_bytes) CU(cudaMemcpyAsync(e->d_in.p, tmpl + base0, in_bytes, cudaMemcpyHostToDevice, s));
     if (n) CU(cudaMemcpyAsync(e->d_in_offs.p, tmpl_offs, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    e->in_bias = base0;
     ie_batch_info* hinfo = (ie_batch_info*)e->h_info.p;
     float kernel_ms = 0.f;
     // An overflowing run skips the stages behind the one that overflowed (a rescan round whose gather did not fit
@@ -915,10 +920,10 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     const int max_attempts = 8;
     for (int attempt = 0;; ++attempt) {
         CU(cudaEventRecord(e->ev0, s));
-        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p, (const uint64_t*)e->d_in_offs.p, n, limits,
+        ie_status_t st = resolve_device(e, t, (const uint8_t*)e->d_in.p - base0, (const uint64_t*)e->d_in_offs.p, n, limits,
                                         (uint8_t*)e->d_out.p, e->d_out.cap, (uint64_t*)e->d_out_offs.p, (uint32_t*)e->d_out_lens.p,
                                         (int32_t*)e->d_status.p, (uint32_t*)e->d_aux.p, (ie_batch_info*)e->d_info.p, 0, s,
-                                        n ? in_bytes / n : 0, host_rounds(limits), sample_groups_x16(tmpl, in_bytes, n));
+                                        n ? in_bytes / n : 0, host_rounds(limits), sample_groups_x16(tmpl + base0, in_bytes, n));
         if (st != IE_OK) return st;
         CU(cudaEventRecord(e->ev1, s));
         CU(cudaMemcpyAsync(hinfo, e->d_info.p, sizeof(ie_batch_info), cudaMemcpyDeviceToHost, s));
@@ -958,6 +963,77 @@ ie_status_t ie_resolve_batch(ie_engine* e, const ie_table* t, const uint8_t* tmp
     res->info = info;
     res->info.n = nr;
     res->info.kernel_ms = kernel_ms;
+    return IE_OK;
+}
+
+// One host thread per engine: contiguous shards of ONE host batch, each through its own engine's pipelined path.
+ie_status_t ie_resolve_batch_multi(ie_engine* const* engines, const ie_table* const* tables, uint32_t n_engines, const uint8_t* tmpl,
+                                   const uint64_t* tmpl_offs, uint64_t n, const ie_limits* limits, ie_shard_result* shards) {
+    if (!engines || !tables || !n_engines || !shards || (n && !tmpl_offs)) return fail(IE_E_INVALID, "ie_resolve_batch_multi: NULL argument");
+    for (uint32_t g = 0; g < n_engines; ++g) {
+        if (!engines[g] || !tables[g]) return fail(IE_E_INVALID, "ie_resolve_batch_multi: NULL engine or table");
+        if (tables[g]->e != engines[g]) return fail(IE_E_INVALID, "ie_resolve_batch_multi: table " + std::to_string(g) + " belongs to another engine");
+        if (tables[g]->n_states != 1) return fail(IE_E_INVALID, "ie_resolve_batch_multi: one snapshot per table");
+        for (uint32_t h = 0; h < g; ++h)
+            if (engines[h] == engines[g]) return fail(IE_E_INVALID, "ie_resolve_batch_multi: the same engine twice");
+    }
+    const uint64_t per = (n + n_engines - 1) / n_engines;  // ceil(n / G) templates per shard, the last ones may be short or empty
+    auto work = [&](uint32_t g) {
+        ie_shard_result& sh = shards[g];
+        std::memset(&sh, 0, sizeof sh);
+        sh.first = std::min<uint64_t>(n, (uint64_t)g * per);
+        sh.n = std::min<uint64_t>(n, (uint64_t)(g + 1) * per) - sh.first;
+        sh.status = ie_resolve_batch(engines[g], tables[g], tmpl, tmpl_offs ? tmpl_offs + sh.first : nullptr, sh.n, limits, &sh.res);
+        if (sh.status != IE_OK) std::snprintf(sh.error, sizeof sh.error, "%s", ie_last_error());
+    };
+    std::vector<std::thread> th;
+    for (uint32_t g = 1; g < n_engines; ++g) th.emplace_back(work, g);
+    work(0);
+    for (auto& x : th) x.join();
+    for (uint32_t g = 0; g < n_engines; ++g)
+        if (shards[g].status != IE_OK) return fail(shards[g].status, "ie_resolve_batch_multi: shard " + std::to_string(g) + ": " + shards[g].error);
+    return IE_OK;
+}
+
+// The host gather of SURVEY.md §8(e): the shards' results concatenated in template order into the caller's arrays.
+ie_status_t ie_shards_gather(const ie_shard_result* shards, uint32_t n_shards, uint8_t* out, uint64_t out_capacity, uint64_t* out_offs,
+                             int32_t* status, uint32_t* aux, uint64_t* out_bytes) {
+    if (!shards || !n_shards || !out_offs || !status || !aux) return fail(IE_E_INVALID, "ie_shards_gather: NULL argument");
+    // shard bases by a prefix over the shards' exact result bytes, then every shard is copied by its own thread
+    std::vector<uint64_t> base(n_shards + 1, 0);
+    std::vector<uint64_t> bytes(n_shards, 0);
+    auto count = [&](uint32_t g) {
+        uint64_t b = 0;
+        for (uint64_t i = 0; i < shards[g].n; ++i) b += shards[g].res.out_lens[i];
+        bytes[g] = b;
+    };
+    {
+        std::vector<std::thread> th;
+        for (uint32_t g = 1; g < n_shards; ++g) th.emplace_back(count, g);
+        count(0);
+        for (auto& x : th) x.join();
+    }
+    for (uint32_t g = 0; g < n_shards; ++g) base[g + 1] = base[g] + bytes[g];
+    if (out_bytes) *out_bytes = base[n_shards];
+    if (base[n_shards] > out_capacity || (base[n_shards] && !out)) return fail(IE_E_OVERFLOW, "ie_shards_gather: output arena too small (see out_bytes)");
+    auto copy = [&](uint32_t g) {
+        const ie_shard_result& sh = shards[g];
+        uint64_t at = base[g];
+        for (uint64_t i = 0; i < sh.n; ++i) {
+            const uint32_t len = sh.res.out_lens[i];
+            out_offs[sh.first + i] = at;
+            if (len) std::memcpy(out + at, sh.res.out + sh.res.out_offs[i], len);
+            at += len;
+            status[sh.first + i] = sh.res.status[i];
+            aux[sh.first + i] = sh.res.aux[i];
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t g = 1; g < n_shards; ++g) th.emplace_back(copy, g);
+    copy(0);
+    for (auto& x : th) x.join();
+    const ie_shard_result& last = shards[n_shards - 1];
+    out_offs[last.first + last.n] = base[n_shards];
     return IE_OK;
 }
 
@@ -1150,6 +1226,11 @@ ie_status_t ie_copy_to_host(ie_engine* e, void* h_dst, const void* d_src, uint64
 ie_status_t ie_host_alloc(uint64_t bytes, void** h_ptr) {
     if (!h_ptr) return fail(IE_E_INVALID, "ie_host_alloc: NULL argument");
     CU(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return IE_OK;
+}
+ie_status_t ie_host_alloc_wc(uint64_t bytes, void** h_ptr) {
+    if (!h_ptr) return fail(IE_E_INVALID, "ie_host_alloc_wc: NULL argument");
+    CU(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
     return IE_OK;
 }
 void ie_host_free(void* h_ptr) { if (h_ptr) cudaFreeHost(h_ptr); }

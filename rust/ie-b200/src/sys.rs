@@ -54,6 +54,17 @@ pub struct ie_result {
     pub info: ie_batch_info,
 }
 
+pub type ie_status_t = c_int;
+
+#[repr(C)]
+pub struct ie_shard_result {
+    pub first: u64,
+    pub n: u64,
+    pub res: ie_result,
+    pub status: ie_status_t,
+    pub error: [c_char; 160],
+}
+
 extern "C" {
     pub fn ie_last_error() -> *const c_char;
     pub fn ie_device_count() -> c_int;
@@ -77,6 +88,10 @@ extern "C" {
 
     pub fn ie_resolve_batch(e: *mut ie_engine, t: *const ie_table, tmpl: *const u8, tmpl_offs: *const u64, n: u64,
                             limits: *const ie_limits, res: *mut ie_result) -> c_int;
+    pub fn ie_resolve_batch_multi(engines: *const *mut ie_engine, tables: *const *const ie_table, n_engines: u32, tmpl: *const u8,
+                                  tmpl_offs: *const u64, n: u64, limits: *const ie_limits, shards: *mut ie_shard_result) -> ie_status_t;
+    pub fn ie_shards_gather(shards: *const ie_shard_result, n_shards: u32, out: *mut u8, out_capacity: u64, out_offs: *mut u64,
+                            status: *mut i32, aux: *mut u32, out_bytes: *mut u64) -> ie_status_t;
     pub fn ie_resolve_batch_device(e: *mut ie_engine, t: *const ie_table, d_tmpl: *const u8, d_tmpl_offs: *const u64, n: u64,
                                    limits: *const ie_limits, d_out: *mut u8, out_capacity: u64, d_out_offs: *mut u64,
                                    d_out_lens: *mut u32, d_status: *mut i32, d_aux: *mut u32, d_info: *mut ie_batch_info,
@@ -103,6 +118,7 @@ extern "C" {
     pub fn ie_copy_to_device(e: *mut ie_engine, d_dst: *mut c_void, h_src: *const c_void, bytes: u64) -> c_int;
     pub fn ie_copy_to_host(e: *mut ie_engine, h_dst: *mut c_void, d_src: *const c_void, bytes: u64) -> c_int;
     pub fn ie_host_alloc(bytes: u64, h_ptr: *mut *mut c_void) -> c_int;
+    pub fn ie_host_alloc_wc(bytes: u64, h_ptr: *mut *mut c_void) -> ie_status_t;
     pub fn ie_host_free(h_ptr: *mut c_void);
 
     pub fn ie_call_json(e: *mut ie_engine, args_json: *const c_char, len: usize, out_json: *mut *mut c_char, out_len: *mut usize) -> c_int;

@@ -3,6 +3,7 @@
 Bar: bit-exact — result bytes, status codes, typed-result tags and error texts identical to the
 oracle's restatement of rust-project/src/interp.rs and runtime.rs:1198-1239, 1633-1647.
 """
+import ctypes
 import json
 import os
 import random
@@ -666,6 +667,46 @@ def test_table_set_delete_in_place(eng, oracle):
     tpl = ["{a}", "{grow-0}", "{grow-%d}" % (k - 1), "{grow-%d}" % k]
     _assert_batch_equals_oracle(oracle, eng.resolve_batch(table, tpl), 0, cur, tpl, "overflow")
     _assert_batch_equals_oracle(oracle, eng.resolve_batch(eng.pack(ie.PackedInserts.from_dict(cur)), tpl), 0, cur, tpl, "repacked")
+
+
+def test_resolve_batch_multi_and_gather(eng, oracle):
+    """ie_resolve_batch_multi: contiguous shards of one host batch through several engines (one per GPU when the box has
+    them, otherwise several engines on the one device), then the host gather.  Shards and gather equal the single-engine
+    result and the oracle; shard arithmetic at the edges (more engines than templates, empty batch)."""
+    n_dev = int(eng.lib.ie_device_count())
+    state = workloads.c4_state()
+    for G, n in ((2, 100_003), (3, 5), (4, 2), (2, 0), (min(8, max(2, n_dev)), 300_000)):
+        engines = [ie.Engine(g % n_dev) for g in range(G)]
+        tables = [e.pack(state) for e in engines]
+        tmpl = workloads.c4_templates(max(n, 1), start=77)
+        arena = ie.Arena(tmpl.bytes[:int(tmpl.offs[n])], tmpl.offs[:n + 1])
+        per, (out, offs, status, aux) = ie.resolve_batch_multi(engines, tables, arena)
+        assert [first for first, _ in per] == [min(n, g * -(-n // G)) for g in range(G)] and sum(len(b.lens) for _, b in per) == n
+        w_out, w_offs, w_status, _ = oracle.build_table(state).resolve_batch(arena.bytes, arena.offs, threads=8)
+        assert np.array_equal(status & 0xFF, w_status) and np.array_equal(offs, w_offs) and np.array_equal(out, w_out)
+        for first, b in per:  # every shard by itself too
+            for i in range(0, len(b.lens), max(1, len(b.lens) // 50)):
+                assert b.get(i) == w_out[int(w_offs[first + i]):int(w_offs[first + i + 1])].tobytes()
+        for t in tables:
+            t.free()
+        for e in engines:
+            e.close()
+    # a shard of a larger arena through the plain call: offsets that do not start at 0
+    tmpl = workloads.c4_templates(70_000)
+    table = eng.pack(state)
+    res = ie._Result()
+    lo = 1234
+    sub_offs = np.ascontiguousarray(tmpl.offs[lo:])
+    eng._check(eng.lib.ie_resolve_batch(eng.handle, table.handle, tmpl.bytes.ctypes.data, sub_offs.ctypes.data, tmpl.n - lo, None, ctypes.byref(res)))
+    m = tmpl.n - lo
+    # (copies: the engine owns these buffers until its next call)
+    lens = np.frombuffer((ctypes.c_char * (m * 4)).from_address(res.out_lens), dtype=np.uint32).copy()
+    o = np.frombuffer((ctypes.c_char * (m * 8)).from_address(res.out_offs), dtype=np.uint64).copy()
+    ob = np.frombuffer((ctypes.c_char * int(res.info.out_bytes)).from_address(res.out), dtype=np.uint8).copy()
+    full = eng.resolve_batch(table, tmpl)
+    assert np.array_equal(lens, full.lens[lo:])
+    for i in range(0, m, 997):
+        assert ob[int(o[i]):int(o[i]) + int(lens[i])].tobytes() == full.get(lo + i)
 
 
 def test_limits_escalate_to_hard_caps(eng, oracle):
