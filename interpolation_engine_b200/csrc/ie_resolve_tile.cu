@@ -118,6 +118,7 @@ struct Smem {
     uint4 lowmask[17];         // lowmask[k] = the low k bytes of a 16-byte quantity set (load16_range)
     uint32_t warp_scan[NW];
     uint32_t q_n[1];
+    uint32_t q_lvl[3];         // P3: groups appended per level (rotating)
     uint32_t ev_n;             // events allocated
     uint32_t overflow;
 };
@@ -353,10 +354,11 @@ struct PieceEmit {
         off += len;
     }
 };
-struct PieceCopy {  // per-thread byte copy (segment-table overflow fallback)
+struct PieceCopy {  // warp-wide byte copy (segment-table overflow fallback): all 32 lanes walk the same template
     uint8_t* dst;
+    uint32_t lane;
     __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
-        for (uint32_t k = 0; k < len; ++k) dst[k] = __ldg(src + k);
+        for (uint32_t k = lane; k < len; k += 32) dst[k] = __ldg(src + k);
         dst += len;
     }
 };
@@ -410,8 +412,13 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
 
 // Resolves group g and then, while g was the last unresolved child of its parent, the parent too
 // (a `{q-{idx-{slot-A}}}` chain is one thread's work instead of one queue round per level).
+// IE_P3_LEVELS (experiment switch, profiles/r02_kernel_experiments.md): instead of carrying on with the parent itself the
+// thread returns the parent that became ready (NONE16: none) and the caller queues it for the next level, so that a
+// chain hop runs on a compacted queue at full lanes.  Measured on C4: 8 % fewer warp instructions (223 M vs 242 M,
+// 27 instead of 25 active lanes) but 6 % MORE time (0.366 vs 0.343 ms): the later levels hold half as many groups as
+// the CTA has threads, and the barrier per level costs more than the idle lanes of a chain.
 template <bool ROUNDS>
-__device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
+__device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
   uint32_t carry_e = NONE16;
   uint4 carry_v = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
   for (;;) {
@@ -478,26 +485,29 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
             // interp.rs:81-83 rescans the spliced value.  Properly nested groups in it resolve in place: the value's
             // text takes the group's place and the template goes another round; anything else is the general path's.
             if (ROUNDS && IE_SLOT_FLAGS(vl_tf) == (IE_VF_BRACE | IE_VF_BALANCED)) splice = true;
-            else { atomicOr(&sm.t_flags[t], TF_PUNT); return; }
+            else { atomicOr(&sm.t_flags[t], TF_PUNT); return NONE16; }
         }
     }
-    if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return; }
+    if (err) { atomicMax(&sm.t_err[t], (g << 8) | err); return NONE16; }
     sm.ev_a[EI(g)] = val_off16;
     sm.ev_a[EI(c)] = IE_SLOT_VLEN(vl_tf);
     if (ROUNDS) sm.ev_pos[EI(g)] |= EV_DONE;
     if (ROUNDS && splice) {  // the groups enclosing g cannot be looked up yet: they stay text for the next round
         atomicMax(&sm.t_splice[t], g + 1u);
         atomicOr(&sm.t_flags[t], TF_AGAIN);
-        return;
+        return NONE16;
     }
     const uint32_t parent = sm.ev_c[EI(g)];
     if (parent == NONE16) {
         if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
-        return;
+        return NONE16;
     }
-    // one child of `parent` resolved; whoever resolves the last one carries on with the parent
+    // one child of `parent` resolved; whoever resolves the last one carries on with the parent / hands it to the next level
     __threadfence_block();
-    if (atomicSub(&sm.ev_a[EI(parent)], 1u) != 1u) return;
+    if (atomicSub(&sm.ev_a[EI(parent)], 1u) != 1u) return NONE16;
+#ifdef IE_P3_LEVELS
+    return parent;  // (the level barrier orders the siblings' results before the parent's lookup)
+#endif
     __threadfence_block();  // the siblings' results (written before their decrements) are visible from here on
     // short-key hits leave the slot's inline value in q3 (valid when the value is inline)
     carry_e = (klen <= 16 && IE_SLOT_VLEN(vl_tf) <= IE_INLINE_BYTES) ? g : NONE16;
@@ -509,14 +519,23 @@ __device__ __forceinline__ void resolve_group(Smem& sm, const IeTableView& tv, c
 // The cold blocks of the tile body, out of line (arguments by value: taking the address of a kernel-level struct would
 // move it to local memory for the hot path too).  Measured: 0.379 -> 0.374 ms on C4 (the hot instructions are a
 // sixth of the kernel's code and were spread over all of it).
+// Segment-table overflow (a tile with more copy segments than S_CAP - one template with hundreds of groups is enough):
+// the templates are copied one per WARP, every lane walking the same pieces and taking every 32nd byte.  (One thread
+// per template took 11 ms for a single 16 KB template with 600 groups.)  The per-template parameters come from the
+// dead segment table: five words per template.
 template <bool ROUNDS>
-__device__ __noinline__ void copy_own_pieces(Smem* smp, IeTableView tv, const uint8_t* __restrict__ tp, uint32_t tid, uint32_t mode, uint32_t err_g,
-                                             uint8_t* dst, uint32_t olen) {
+__device__ __noinline__ void copy_own_pieces(Smem* smp, IeTableView tv, const uint8_t* __restrict__ tp, uint32_t nt, uint8_t* out) {
     Smem& sm = *smp;
-    PieceCopy cp{dst};
-    if (mode == 1) cp(tp + sm.t_start[tid], olen);
-    else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, cp);
-    else if (mode == 3) walk_output_pieces<ROUNDS>(sm, tv, tp, tid, cp);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t t = warp; t < nt; t += NW) {
+        const uint32_t* par = &sm.u.seg.out[5 * t];
+        const uint32_t mode = par[0], err_g = par[1], olen = par[4];
+        if (!olen) continue;
+        PieceCopy cp{out + (((uint64_t)par[3] << 32) | par[2]), lane};
+        if (mode == 1) cp(tp + sm.t_start[t], olen);
+        else if (mode == 2) walk_key_pieces(sm, tv, tp, err_g, cp);
+        else if (mode == 3) walk_output_pieces<ROUNDS>(sm, tv, tp, t, cp);
+    }
 }
 __device__ __noinline__ void per_thread_range(Smem* sm, IeTableView tv, const uint8_t* __restrict__ tmpl, const uint64_t* __restrict__ offs, uint64_t i,
                                               uint64_t my_off, bool active, uint64_t r, uint8_t* __restrict__ out, uint64_t out_cap,
@@ -583,7 +602,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
     if (NT == TT && tid == 0) sm.t_start[TT] = (uint32_t)(off_end - off0);
     if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; sm.t_splice[tid] = 0; }
-    if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; }
+    if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; sm.q_lvl[0] = 0; sm.q_lvl[1] = 0; sm.q_lvl[2] = 0; }
     if (tid < 17) {
         auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
         sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
@@ -669,13 +688,30 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
         const uint32_t keep_last = ((2u << ((cz - 1) & 15)) - 1u) * 0x10001u;
         // pass 1: count the template's events; `nonempty` = which of its first 32 chunks hold any
         uint32_t ne = 0, nonempty = 0;
-        for (uint32_t c = c0; c < c1; ++c) {
-            uint32_t m = sm.u.scan.cm[c];
-            if (c == c0) m &= keep_first;
-            if (c + 1 == c1) m &= keep_last;
-            const uint32_t cnt = __popc((m | (m >> 16)) & 0xFFFFu);
-            ne += cnt;
-            if (cnt && c - c0 < 32) nonempty |= 1u << (c - c0);
+        if (c1 > c0) {
+            // first and last chunk with their masks, the chunks between them plain; bit k of `nonempty` = chunk c0 + k
+            uint32_t m = sm.u.scan.cm[c0] & keep_first;
+            if (c0 + 1 == c1) m &= keep_last;
+            uint32_t cnt = __popc((m | (m >> 16)) & 0xFFFFu);
+            ne = cnt;
+            nonempty = cnt ? 1u : 0u;
+            const uint32_t mid_end = min(c1 - 1, c0 + 32);
+            uint32_t bit = 2;
+            for (uint32_t c = c0 + 1; c < mid_end; ++c, bit <<= 1) {
+                const uint32_t mm = sm.u.scan.cm[c];
+                ne += __popc((mm | (mm >> 16)) & 0xFFFFu);
+                if (mm) nonempty |= bit;
+            }
+            for (uint32_t c = mid_end; c + 1 < c1; ++c) {  // templates longer than 32 chunks: counted only
+                const uint32_t mm = sm.u.scan.cm[c];
+                ne += __popc((mm | (mm >> 16)) & 0xFFFFu);
+            }
+            if (c0 + 1 < c1) {
+                m = sm.u.scan.cm[c1 - 1] & keep_last;
+                cnt = __popc((m | (m >> 16)) & 0xFFFFu);
+                ne += cnt;
+                if (cnt && c1 - 1 - c0 < 32) nonempty |= 1u << (c1 - 1 - c0);
+            }
         }
         uint32_t incl = ne;
 #pragma unroll
@@ -797,13 +833,34 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     }
 
     // ---- P3: lookups, one thread per leaf group (and up its parent chain) ------------------------------
+    // (IE_P3_LEVELS, experiment: level by level instead.  Level 0 = the leaf groups P2 queued; a thread that resolves the
+    // last child of a group appends that group to the queue and the next level starts behind ONE barrier.  The queue is
+    // one linear array - a group enters it once - and the levels' sizes rotate through three counters so that every
+    // thread sees the same level bounds without a second barrier.)
     {
+#ifndef IE_P3_LEVELS
         const uint32_t nq = sm.q_n[0];
         for (uint32_t k = tid; k < nq; k += NT) {
             const uint32_t item = sm.u.scan.q[k];
             if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
             resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }
+#else
+        uint32_t lo = 0, hi = sm.q_n[0];
+        for (uint32_t lvl = 0; lo < hi; ++lvl) {
+            uint32_t* const next_n = &sm.q_lvl[(lvl + 1) % 3];
+            if (tid == 0) sm.q_lvl[(lvl + 2) % 3] = 0;
+            for (uint32_t k = lo + tid; k < hi; k += NT) {
+                const uint32_t item = sm.u.scan.q[k];
+                if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
+                const uint32_t parent = resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
+                if (parent != NONE16) sm.u.scan.q[hi + atomicAdd(next_n, 1u)] = (item & 0xFFFF0000u) | parent;
+            }
+            __syncthreads();
+            lo = hi;
+            hi += *next_n;
+        }
+#endif
     }
     PHASE_MARK(5);
     __syncthreads();
@@ -892,7 +949,14 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; return true; }
     if (!seg_ok) {
         // segment table overflow: every thread copies its own pieces
-        if (active && olen) copy_own_pieces<ROUNDS>(&sm, tv, tp, tid, mode, err_g, out + off, olen);
+        static_assert(5 * TT <= S_CAP + 2, "the overflow copy keeps five words per template in the segment table");
+        __syncthreads();  // (nobody emitted segments: the table is free)
+        if (active) {
+            uint32_t* par = &sm.u.seg.out[5 * tid];
+            par[0] = mode; par[1] = err_g; par[2] = (uint32_t)off; par[3] = (uint32_t)(off >> 32); par[4] = olen;
+        }
+        __syncthreads();
+        copy_own_pieces<ROUNDS>(&sm, tv, tp, nt, out);
         return true;
     }
     uint8_t* gout = out + tile_begin;
