@@ -258,7 +258,14 @@ void ie_host_free(void* h_ptr);
  * wildcard_captures (runtime.rs:1754), delete / delete_except (runtime.rs:1198 / 1219),
  * replace_map (runtime.rs:1649; args item, wildcard_maps, repeat_until_done) and goto_map (runtime.rs:1085-1133;
  * args text, target_maps -> {"value", "target", "interpolation_error"}), add_line_numbers / load_program
- * (parser.rs:74 / :8; arg text; host only).  Returns malloc'ed UTF-8 JSON
+ * (parser.rs:74 / :8; arg text; host only), interpolation_trace (arg value: the strings recursive_interpolate sends
+ * to the resolver, in order).
+ * A caller that keeps ONE inserts map over many calls (the reference's run loop) registers it once -
+ * {"fn": "snapshot_create", "inserts": {...}} -> id - mirrors its set_interpdata / delete_interpdata calls with
+ * {"fn": "snapshot_set", "snapshot": id, "key", "value"} / {"fn": "snapshot_delete", "snapshot": id, "key"} (the
+ * packed device table is patched in place, ie_table_set / ie_table_delete) and passes {"snapshot": id} instead of
+ * "inserts" to every function above: no per-call serialisation, packing or upload of the state.  "snapshot_free"
+ * releases it (ie_engine_destroy releases what is left).  Returns malloc'ed UTF-8 JSON
  * {"ok": value} | {"err": {"code", "message", "payload"}}; free with ie_free. */
 ie_status_t ie_call_json(ie_engine* e, const char* args_json, size_t len, char** out_json, size_t* out_len);
 void ie_free(void* p);

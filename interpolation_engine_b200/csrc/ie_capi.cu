@@ -218,6 +218,7 @@ ie_status_t ie_engine_create(int device, ie_engine** out) {
 
 void ie_engine_destroy(ie_engine* e) {
     if (!e) return;
+    ie_host::drop_engine(e);
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (DevBuf* b : {&e->ws_zero, &e->ws_list, &e->ws_scratch, &e->d_in, &e->d_in_offs, &e->d_out, &e->d_out_offs, &e->d_out_lens,

@@ -18,6 +18,7 @@
 #include <ctime>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <set>
 #include <sstream>
@@ -304,7 +305,11 @@ struct Session {
     std::string hhmm, hhmmss, inserts_dir;
     bool has_dir = false;
     ie_table* table = nullptr;
-    std::vector<const JVal*> entry_vals;
+    // entry ids the device reports for typed results: [0, n0) = the inserts as packed, n0 / n0 + 1 = the clock keys,
+    // n0 + 2 + k = the k-th key set after the pack (set_interpdata on the packed table, ie_table_set)
+    std::vector<const JVal*> entry_vals, extra_vals;
+    std::map<std::string, uint32_t> entry_ids;
+    std::string packed_hhmm, packed_hhmmss;
     std::map<std::string, std::string> dir_errors;
     std::map<std::string, bool> dir_probed;
 
@@ -314,19 +319,27 @@ struct Session {
             if (it != args.o->end() && it->second.t == JVal::Obj) inserts = *it->second.o;
             auto d = args.o->find("inserts_dir");
             if (d != args.o->end() && d->second.t == JVal::Str) { inserts_dir = d->second.s; has_dir = true; }
+        }
+        read_clock(args, &hhmm, &hhmmss);
+    }
+    // the "clock" argument of a call (tests inject a fixed one), else chrono::Local::now() (interp.rs:98,102), once per call
+    static void read_clock(const JVal& args, std::string* hm, std::string* hs) {
+        hm->clear();
+        hs->clear();
+        if (args.t == JVal::Obj) {
             auto c = args.o->find("clock");
             if (c != args.o->end() && c->second.t == JVal::Obj) {
-                auto a = c->second.o->find("hhmm"); if (a != c->second.o->end()) hhmm = a->second.s;
-                auto b = c->second.o->find("hhmmss"); if (b != c->second.o->end()) hhmmss = b->second.s;
+                auto a = c->second.o->find("hhmm"); if (a != c->second.o->end()) *hm = a->second.s;
+                auto b = c->second.o->find("hhmmss"); if (b != c->second.o->end()) *hs = b->second.s;
             }
         }
-        if (hhmm.empty() || hhmmss.empty()) {  // chrono::Local::now() (interp.rs:98,102), snapshotted once per call
+        if (hm->empty() || hs->empty()) {
             std::time_t now = std::time(nullptr);
             std::tm tmv{};
             localtime_r(&now, &tmv);
             char buf[16];
-            if (hhmm.empty()) { std::strftime(buf, sizeof buf, "%H:%M", &tmv); hhmm = buf; }
-            if (hhmmss.empty()) { std::strftime(buf, sizeof buf, "%H:%M:%S", &tmv); hhmmss = buf; }
+            if (hm->empty()) { std::strftime(buf, sizeof buf, "%H:%M", &tmv); *hm = buf; }
+            if (hs->empty()) { std::strftime(buf, sizeof buf, "%H:%M:%S", &tmv); *hs = buf; }
         }
     }
     ~Session() { if (table) ie_table_free(table); }
@@ -336,20 +349,73 @@ struct Session {
         Arena keys, vals;
         std::vector<uint8_t> tags;
         entry_vals.clear();
+        extra_vals.clear();
+        entry_ids.clear();
         for (auto& kv : inserts) {
             keys.push(kv.first);
             vals.push(value_to_string(kv.second));
             tags.push_back(tag_of(kv.second));
+            entry_ids[kv.first] = (uint32_t)entry_vals.size();
             entry_vals.push_back(&kv.second);
         }
         static const uint8_t z = 0;
         check(ie_table_pack(e, keys.n(), keys.data(), keys.offs.data(), vals.data(), vals.offs.data(), tags.empty() ? &z : tags.data(),
                             hhmm.c_str(), hhmmss.c_str(), &table));
+        packed_hhmm = hhmm;
+        packed_hhmmss = hhmmss;
     }
 
     JVal entry_value(uint32_t entry) const {
-        if (entry < entry_vals.size()) return *entry_vals[entry];
-        return JVal::str(entry == entry_vals.size() ? hhmm : hhmmss);
+        const uint32_t n0 = (uint32_t)entry_vals.size();
+        if (entry < n0) return *entry_vals[entry];
+        if (entry < n0 + 2) return JVal::str(entry == n0 ? hhmm : hhmmss);
+        return *extra_vals[entry - n0 - 2];
+    }
+
+    // set_interpdata (interp.rs:139-141): the map and, when a table is packed, the table in place (ie_table_set); a table
+    // without room for the operation is packed again.
+    void set(const std::string& key, const JVal& value) {
+        JVal& slot = inserts[key];
+        slot = value;  // (map nodes do not move: entry_vals / extra_vals keep pointing at live values)
+        if (!table || key == "HH:MM" || key == "HH:MM:SS") return;  // (the table's clock entries shadow inserts of those names)
+        auto it = entry_ids.find(key);
+        uint32_t id;
+        if (it != entry_ids.end()) id = it->second;
+        else {
+            id = (uint32_t)(entry_vals.size() + 2 + extra_vals.size());
+            extra_vals.push_back(&slot);
+            entry_ids[key] = id;
+        }
+        const std::string text = value_to_string(value);
+        const uint64_t ko[2] = {0, key.size()}, vo[2] = {0, text.size()};
+        const uint8_t tag = tag_of(value);
+        const ie_status_t st = ie_table_set(e, table, 0, 1, (const uint8_t*)key.data(), ko, (const uint8_t*)text.data(), vo, &tag, &id);
+        if (st == IE_E_OVERFLOW) pack();
+        else check(st);
+    }
+    // delete_interpdata (interp.rs:143-145)
+    void del(const std::string& key) {
+        if (!inserts.erase(key)) return;
+        entry_ids.erase(key);
+        if (!table || key == "HH:MM" || key == "HH:MM:SS") return;
+        const uint64_t ko[2] = {0, key.size()};
+        check(ie_table_delete(e, table, 0, 1, (const uint8_t*)key.data(), ko));
+    }
+    // A session that outlives a call: the clock keys of its table follow the wall clock (interp.rs:96-104 reads it per
+    // lookup; here it is read once per call and patched in place when its rendering changed).
+    void refresh_clock(const std::string& new_hhmm, const std::string& new_hhmmss) {
+        hhmm = new_hhmm;
+        hhmmss = new_hhmmss;
+        if (!table || (hhmm == packed_hhmm && hhmmss == packed_hhmmss)) return;
+        const std::string keys = "HH:MMHH:MM:SS", vals = hhmm + hhmmss;
+        const uint64_t ko[3] = {0, 5, 13}, vo[3] = {0, hhmm.size(), hhmm.size() + hhmmss.size()};
+        const uint8_t tags[2] = {IE_TAG_STRING, IE_TAG_STRING};
+        const uint32_t ids[2] = {(uint32_t)entry_vals.size(), (uint32_t)entry_vals.size() + 1};
+        const ie_status_t st = ie_table_set(e, table, 0, 2, (const uint8_t*)keys.data(), ko, (const uint8_t*)vals.data(), vo, tags, ids);
+        if (st == IE_E_OVERFLOW) { pack(); return; }
+        check(st);
+        packed_hhmm = hhmm;
+        packed_hhmmss = hhmmss;
     }
 
     // interp.rs:122-134: `<dir>/<key>.json5` (parsed, recursive_escape'd) then `<dir>/<key>` (trimmed, escaped)
@@ -676,15 +742,21 @@ std::string replace_str(ie_engine* e, const JVal& args, Session& s, std::string 
         if (f < 0 && pending) throw *pending;
         std::string new_text = current;
         if (f >= 0) {
+            // runtime.rs:1688-1694: the value is resolved against inserts + {"1": capture 1, ...}.  The captures are set on
+            // the session's own table in place and taken back afterwards (set_interpdata / delete_interpdata on the device
+            // table) instead of packing inserts + captures as a new snapshot per iteration.
             const std::vector<std::string> caps = wildcard_captures(keys[f], current);
-            JVal args2 = args;
-            args2.o = std::make_shared<JObj>(*args.o);
-            JObj extra = s.inserts;
-            for (size_t i = 0; i < caps.size(); ++i) extra[std::to_string(i + 1)] = JVal::str(caps[i]);
-            (*args2.o)["inserts"] = JVal::obj(std::move(extra));
-            (*args2.o)["clock"] = JVal::obj({{"hhmm", JVal::str(s.hhmm)}, {"hhmmss", JVal::str(s.hhmmss)}});
-            Session s2(e, args2);
-            new_text = value_to_string(outcome_value(s2.resolve({maps[which[f]].val})[0]));
+            std::vector<std::pair<std::string, std::pair<bool, JVal>>> saved;
+            for (size_t i = 0; i < caps.size(); ++i) {
+                const std::string k = std::to_string(i + 1);
+                auto it = s.inserts.find(k);
+                saved.push_back({k, {it != s.inserts.end(), it != s.inserts.end() ? it->second : JVal()}});
+                s.set(k, JVal::str(caps[i]));
+            }
+            auto restore = [&]() { for (auto& sv : saved) { if (sv.second.first) s.set(sv.first, sv.second.second); else s.del(sv.first); } };
+            try { new_text = value_to_string(outcome_value(s.resolve({maps[which[f]].val})[0])); }
+            catch (...) { restore(); throw; }
+            restore();
         }
         if (!repeat || new_text == text) return new_text;
         text = new_text;
@@ -865,14 +937,63 @@ JVal load_program(const std::string& raw) {
     return JVal::obj(std::move(out));
 }
 
+// ---- snapshots that outlive a call ------------------------------------------------------------------------------------
+// The reference keeps ONE inserts map per run, mutates it between tasks (set_interpdata, 17 call sites in runtime.rs) and
+// resolves against it task after task.  A caller that follows that pattern creates a snapshot once ("snapshot_create"),
+// mirrors its set_interpdata / delete_interpdata calls ("snapshot_set" / "snapshot_delete": the packed table is patched in
+// place) and passes {"snapshot": id} instead of {"inserts": {...}} to every other function: no per-call serialisation,
+// packing or upload of the state.
+std::mutex g_snap_mu;
+std::map<std::pair<ie_engine*, uint64_t>, std::unique_ptr<Session>> g_snaps;
+uint64_t g_snap_next = 1;
+
+struct Hold {  // the session of one call: a registered snapshot (clock refreshed) or a temporary built from "inserts"
+    std::unique_ptr<Session> own;
+    Session* s = nullptr;
+    Hold(ie_engine* e, const JVal& args) {
+        const JVal* id = nullptr;
+        if (args.t == JVal::Obj) { auto it = args.o->find("snapshot"); if (it != args.o->end()) id = &it->second; }
+        if (!id) { own.reset(new Session(e, args)); s = own.get(); return; }
+        std::lock_guard<std::mutex> lk(g_snap_mu);
+        auto it = g_snaps.find({e, (uint64_t)std::strtoull(id->s.c_str(), nullptr, 10)});
+        if (id->t != JVal::Num || it == g_snaps.end()) throw std::runtime_error("unknown snapshot");
+        s = it->second.get();
+        std::string hm, hs;
+        Session::read_clock(args, &hm, &hs);
+        s->refresh_clock(hm, hs);
+        auto d = args.o->find("inserts_dir");
+        s->has_dir = d != args.o->end() && d->second.t == JVal::Str;
+        if (s->has_dir && s->inserts_dir != d->second.s) { s->inserts_dir = d->second.s; s->dir_probed.clear(); s->dir_errors.clear(); }
+    }
+};
+
 JVal dispatch(ie_engine* e, const JVal& args) {
     const std::string& fn = sarg(args, "fn");
+    if (fn == "snapshot_create") {
+        std::unique_ptr<Session> ns(new Session(e, args));
+        ns->pack();
+        std::lock_guard<std::mutex> lk(g_snap_mu);
+        const uint64_t id = g_snap_next++;
+        g_snaps[{e, id}] = std::move(ns);
+        return JVal::num(std::to_string(id));
+    }
+    if (fn == "snapshot_set" || fn == "snapshot_delete" || fn == "snapshot_free" || fn == "snapshot_inserts") {
+        const JVal& idv = arg(args, "snapshot");
+        std::lock_guard<std::mutex> lk(g_snap_mu);
+        auto it = g_snaps.find({e, (uint64_t)std::strtoull(idv.s.c_str(), nullptr, 10)});
+        if (idv.t != JVal::Num || it == g_snaps.end()) throw std::runtime_error("unknown snapshot");
+        if (fn == "snapshot_free") { g_snaps.erase(it); return JVal(); }
+        if (fn == "snapshot_inserts") return JVal::obj(JObj(it->second->inserts));  // the map as the host mirror holds it
+        if (fn == "snapshot_set") it->second->set(sarg(args, "key"), arg(args, "value"));  // interp.rs:139
+        else it->second->del(sarg(args, "key"));                                           // interp.rs:143
+        return JVal();
+    }
     if (fn == "interpolate_inserts") {  // interp.rs:31
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         return outcome_value(s.resolve({sarg(args, "content")})[0]);
     }
     if (fn == "interpolate_many") {  // batch form: [{ok|err}] per template, one launch
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         std::vector<std::string> ts;
         for (auto& x : *arg(args, "contents").a) ts.push_back(x.s);
         JArr out;
@@ -889,11 +1010,11 @@ JVal dispatch(ie_engine* e, const JVal& args) {
         return simple_insertkey(sarg(args, "content"), &k) ? JVal::str(k) : JVal();
     }
     if (fn == "get_interpdata") {  // interp.rs:91
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         return lookup_keys(s, {sarg(args, "key")})[0];
     }
     if (fn == "recursive_interpolate") {  // interp.rs:179
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         const JVal& v = arg(args, "value");
         Gather g;
         gather(v, g);
@@ -962,7 +1083,7 @@ JVal dispatch(ie_engine* e, const JVal& args) {
     if (fn == "replace_map") {  // runtime.rs:1146-1169, 1649
         const JVal& maps = arg(args, "wildcard_maps");
         if (maps.t != JVal::Arr) throw task_error("replace_map.wildcard_maps must be array");
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         JVal null_value;
         const bool has_null = find_null_map_value(s, maps, &null_value);
         const JVal& rep = arg(args, "repeat_until_done");
@@ -971,13 +1092,18 @@ JVal dispatch(ie_engine* e, const JVal& args) {
     if (fn == "goto_map") {  // runtime.rs:1085-1133
         const JVal& maps = arg(args, "target_maps");
         if (maps.t != JVal::Arr) throw task_error("goto_map.target_maps must be array");
-        Session s(e, args);
+        Hold h(e, args); Session& s = *h.s;
         return goto_map(e, s, sarg(args, "text"), maps);
     }
     throw std::runtime_error("unknown fn '" + fn + "'");
 }
 
 }  // namespace
+
+void drop_engine(ie_engine* e) {  // ie_engine_destroy: the engine's registered snapshots (and their tables) go first
+    std::lock_guard<std::mutex> lk(g_snap_mu);
+    for (auto it = g_snaps.begin(); it != g_snaps.end();) it = it->first.first == e ? g_snaps.erase(it) : std::next(it);
+}
 
 ie_status_t call_json(ie_engine* e, const std::string& args_json, std::string* out_json, std::string* why) {
     JObj res;

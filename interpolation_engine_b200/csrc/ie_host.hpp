@@ -16,5 +16,6 @@ bool build_table_image(uint64_t n, const uint8_t* keys, const uint64_t* key_offs
                        std::string* why, bool compact = false, bool* any_balanced = nullptr);
 
 ie_status_t call_json(ie_engine* e, const std::string& args_json, std::string* out_json, std::string* why);
+void drop_engine(ie_engine* e);  // frees the snapshots registered through call_json for this engine
 
 }  // namespace ie_host

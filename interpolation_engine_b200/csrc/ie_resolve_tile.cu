@@ -47,6 +47,26 @@ __device__ unsigned long long g_phase_cycles[16];
 #define PHASE_INIT() do { } while (0)
 #endif
 
+// -DIE_DEBUG_BOUNDS: every index into a tile table is checked against the table's capacity before it is used; a
+// violation is counted (and the first one recorded) instead of corrupting shared memory.  compute-sanitizer is not
+// available on the GPU pool, this build takes its place: tests/fuzz_campaign.py runs against it unchanged and
+// ie_debug_bound_violations() must stay 0 (profiles/r02_debug_bounds_fuzz.txt).
+#ifdef IE_DEBUG_BOUNDS
+namespace {
+__device__ unsigned long long g_bound_violations[4];  // count, line, index, capacity of the first one (per translation unit)
+__device__ __noinline__ void ie_bound_report(uint32_t i, uint32_t cap, int line) {
+    if (atomicAdd(&g_bound_violations[0], 1ull) == 0) { g_bound_violations[1] = (unsigned long long)line; g_bound_violations[2] = i; g_bound_violations[3] = cap; }
+}
+__device__ __forceinline__ uint32_t ie_bound_check(uint32_t i, uint32_t cap, int line) {
+    if (i >= cap) { ie_bound_report(i, cap, line); return 0u; }
+    return i;
+}
+}  // namespace
+#define IE_BOUND(i, cap) ie_bound_check((uint32_t)(i), (uint32_t)(cap), __LINE__)
+#else
+#define IE_BOUND(i, cap) (i)
+#endif
+
 namespace {
 
 using namespace ie_dev;
@@ -85,7 +105,7 @@ constexpr uint32_t NONE16 = 0xFFFFu;
 enum : uint32_t { TF_PUNT = 1, TF_VERBATIM = 2, TF_AGAIN = 4 };
 constexpr uint32_t CS_EDGE = 0x8000u;    // cs[]: the chunk is not covered by ONE segment (pass B assembles it)
 
-__device__ __forceinline__ uint32_t EI(uint32_t e) { return e + (e >> 5); }  // padded event index
+__device__ __forceinline__ uint32_t EI(uint32_t e) { return IE_BOUND(e + (e >> 5), E_PAD); }  // padded event index
 
 struct Smem {
     ie_scan::TileSmemT<NT> scan;
@@ -340,15 +360,15 @@ struct PieceEmit {
     uint32_t olead;  // bytes between the 16-byte aligned floor of the tile's output address and that address
     bool index_chunks;
     __device__ __forceinline__ void operator()(const uint8_t* src, uint32_t len) {
-        sm.u.seg.out[idx] = off;
-        sm.u.seg.src[idx] = (uint64_t)(uintptr_t)src;
+        sm.u.seg.out[IE_BOUND(idx, S_CAP)] = off;
+        sm.u.seg.src[IE_BOUND(idx, S_CAP)] = (uint64_t)(uintptr_t)src;
         if (index_chunks) {
             // every 16-byte aligned output chunk whose first byte lies in this piece points back at it; only the last
             // of them can reach beyond the piece's end (CS_EDGE: pass B assembles that chunk)
             const uint32_t lo = off + olead, hi = lo + len;  // the piece in chunk coordinates
             uint32_t c = (lo + 15) >> 4;
-            for (; (c << 4) + 16 <= hi; ++c) sm.u.seg.cs[c] = (uint16_t)idx;
-            if ((c << 4) < hi) sm.u.seg.cs[c] = (uint16_t)(idx | CS_EDGE);
+            for (; (c << 4) + 16 <= hi; ++c) sm.u.seg.cs[IE_BOUND(c, C_CAP + 2)] = (uint16_t)idx;
+            if ((c << 4) < hi) sm.u.seg.cs[IE_BOUND(c, C_CAP + 2)] = (uint16_t)(idx | CS_EDGE);
         }
         ++idx;
         off += len;
@@ -663,7 +683,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
 #pragma unroll
             for (int u = 0; u < P1_BATCH; ++u) {
                 const uint32_t c = cb + u * NT;
-                if (c < n_chunks) sm.u.scan.cm[c] = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
+                if (c < n_chunks) sm.u.scan.cm[IE_BOUND(c, M_CAP)] = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
             }
         }
     }
@@ -776,7 +796,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
                             sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
                             cur_open = sm.ev_c[EI(o)];
                             if (o + 1 == e) {  // closes without children: a leaf group
-                                if (k <= 32) leaf_lo |= 1u << (k - 1); else sm.u.scan.q[atomicAdd(&sm.q_n[0], 1u)] = (tid << 16) | o;
+                                if (k <= 32) leaf_lo |= 1u << (k - 1); else sm.u.scan.q[IE_BOUND(atomicAdd(&sm.q_n[0], 1u), Q_CAP)] = (tid << 16) | o;
                             }
                         }
                     }
@@ -817,7 +837,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
         while (leaf_lo) {
             const uint32_t k1 = (uint32_t)__ffs(leaf_lo) - 1u;  // the leaf's close is event k1 + 1 of the template, its open event k1
             leaf_lo &= leaf_lo - 1u;
-            sm.u.scan.q[qi++] = (tid << 16) | (eb0 + k1);
+            sm.u.scan.q[IE_BOUND(qi, Q_CAP)] = (tid << 16) | (eb0 + k1);
+            ++qi;
         }
     }
     PHASE_MARK(3);
@@ -854,7 +875,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
                 const uint32_t item = sm.u.scan.q[k];
                 if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
                 const uint32_t parent = resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
-                if (parent != NONE16) sm.u.scan.q[hi + atomicAdd(next_n, 1u)] = (item & 0xFFFF0000u) | parent;
+                if (parent != NONE16) sm.u.scan.q[IE_BOUND(hi + atomicAdd(next_n, 1u), Q_CAP)] = (item & 0xFFFF0000u) | parent;
             }
             __syncthreads();
             lo = hi;
@@ -970,9 +991,9 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     if (tile_out == 0) return true;
     if (index_chunks) {
         for (uint32_t c = tid; c < o_chunks; c += NT) {
-            const uint32_t sidx = sm.u.seg.cs[c];
+            const uint32_t sidx = sm.u.seg.cs[IE_BOUND(c, C_CAP + 2)];
             if (sidx & CS_EDGE) continue;  // ragged edge of the tile, or a segment ends inside this chunk: pass B
-            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (c * 16 - olead - sm.u.seg.out[sidx]);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[IE_BOUND(sidx, S_CAP)]) + (c * 16 - olead - sm.u.seg.out[sidx]);
             *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
         }
     } else {
@@ -1145,6 +1166,19 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
                                                               d_aux, ws, d_info, out_bias, tt, rd);
     return cudaGetLastError();
 }
+
+#ifdef IE_DEBUG_BOUNDS
+// out4: violations counted so far, then source line / index / capacity of the first one (this build of the kernel: the
+// 128-template and the 32-template build count separately)
+#ifdef IE_TILE_SMALL
+extern "C" int ie_debug_bound_violations_small(unsigned long long* out4) {
+#else
+extern "C" int ie_debug_bound_violations(unsigned long long* out4) {
+#endif
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out4, g_bound_violations, sizeof(unsigned long long) * 4) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 #if defined(IE_PHASE_TIMING) && !defined(IE_TILE_SMALL)
 extern "C" int ie_debug_phase_cycles(unsigned long long* out16, int reset) {

@@ -2,9 +2,10 @@
 //!
 //! Same public items (names, argument meaning, `anyhow` error texts) as `interp.rs:7-322`; the work is done
 //! by the B200 engine (`libie_b200.so`, `include/ie_b200.h`).  There is no CPU fallback: creating the engine
-//! fails without a CUDA device.  Batch entry points (`Snapshot`, `interpolate_many`, `SnapshotSet`) are what
-//! a caller with many templates or many cloned states should use; the single-call functions below wrap them
-//! so that `runtime.rs`, `math.rs` and `analyzer.rs` compile unchanged.
+//! fails without a CUDA device.  Batch entry points (`Snapshot`, `interpolate_many`) are what a caller with many
+//! templates or many cloned states should use; `LiveInserts` is the run loop's mutable map with its device table
+//! patched in place; the single-call functions keep the `interp.rs` signatures so that `runtime.rs`, `math.rs`
+//! and `analyzer.rs` compile unchanged.
 //!
 //! NOT COMPILED in the build container of this repository (no Rust toolchain there); the C ABI it binds is
 //! covered by the Python parity tests in `tests/`.
@@ -118,14 +119,12 @@ fn tag_of(v: &Value) -> u8 {
     }
 }
 
-/// `interp.rs:314-322`.
+/// `interp.rs:314-322`, through the host mirror like every other function (one rendering of `serde_json`'s
+/// number and object text: the library's).
 pub fn value_to_string(value: &Value) -> String {
-    match value {
-        Value::String(s) => s.clone(),
-        Value::Number(n) => n.to_string(),
-        Value::Bool(b) => b.to_string(),
-        Value::Array(items) => items.iter().map(value_to_string).collect::<String>(),
-        other => serde_json::to_string(other).unwrap_or_default(),
+    match engine().call(json!({"fn": "value_to_string", "value": value})) {
+        Ok(Value::String(s)) => s,
+        _ => String::new(),
     }
 }
 
@@ -225,26 +224,69 @@ fn ctx_json(ctx: &ProgramLoadContext) -> Value {
     }
 }
 
-/// interp.rs:11-29 — pure scan, no device work.
+/// interp.rs:11-29.
 pub fn get_simple_insertkey(content: &str) -> Option<String> {
-    let chars: Vec<char> = content.chars().collect();
-    let n = chars.len();
-    if n < 2 || chars[0] != INSERT_START || chars[n - 1] != INSERT_STOP {
-        return None;
+    match engine().call(json!({"fn": "get_simple_insertkey", "content": content})) {
+        Ok(Value::String(s)) => Some(s),
+        _ => None,
     }
-    let mut depth: i64 = 0;
-    for (i, ch) in chars.iter().enumerate() {
-        if *ch == INSERT_STOP {
-            depth -= 1;
-        }
-        if (depth == 0) != (i == 0 || i == n - 1) {
-            return None;
-        }
-        if *ch == INSERT_START {
-            depth += 1;
-        }
+}
+
+/// The reference's run loop keeps ONE inserts map, mutates it between tasks (`set_interpdata`, 17 call sites in
+/// `runtime.rs`) and resolves against it task after task (`runtime.rs:700`).  `LiveInserts` is that map with its
+/// packed device table kept alive next to it: `set` / `delete` patch the table in place (`ie_table_set` /
+/// `ie_table_delete` behind the mirror's "snapshot_set" / "snapshot_delete"), and every resolver call passes the
+/// snapshot id instead of serialising the map.
+pub struct LiveInserts {
+    pub map: Map<String, Value>,
+    id: u64,
+}
+
+impl LiveInserts {
+    pub fn new(map: Map<String, Value>) -> Result<LiveInserts> {
+        let id = engine().call(json!({"fn": "snapshot_create", "inserts": map}))?.as_u64().ok_or_else(|| anyhow!("ie_b200: malformed snapshot id"))?;
+        Ok(LiveInserts { map, id })
     }
-    Some(chars[1..n - 1].iter().collect())
+    /// interp.rs:139.
+    pub fn set(&mut self, key: &str, value: Value) -> Result<()> {
+        engine().call(json!({"fn": "snapshot_set", "snapshot": self.id, "key": key, "value": value}))?;
+        self.map.insert(key.to_string(), value);
+        Ok(())
+    }
+    /// interp.rs:143.
+    pub fn delete(&mut self, key: &str) -> Result<()> {
+        engine().call(json!({"fn": "snapshot_delete", "snapshot": self.id, "key": key}))?;
+        self.map.remove(key);
+        Ok(())
+    }
+    /// interp.rs:31.
+    pub fn interpolate_inserts(&self, content: &str, ctx: &ProgramLoadContext) -> Result<Value> {
+        engine().call(json!({"fn": "interpolate_inserts", "snapshot": self.id, "content": content, "inserts_dir": ctx_json(ctx)}))
+    }
+    /// interp.rs:179.
+    pub fn recursive_interpolate(&self, value: Value, ctx: &ProgramLoadContext) -> Result<Value> {
+        engine().call(json!({"fn": "recursive_interpolate", "snapshot": self.id, "value": value, "inserts_dir": ctx_json(ctx)}))
+    }
+    /// interp.rs:91.
+    pub fn get_interpdata(&self, insertkey: &str, ctx: &ProgramLoadContext) -> Result<Value> {
+        engine().call(json!({"fn": "get_interpdata", "snapshot": self.id, "key": insertkey, "inserts_dir": ctx_json(ctx)}))
+    }
+    /// runtime.rs:1649.
+    pub fn replace_map(&self, item: Value, maps: &[Value], ctx: &ProgramLoadContext, repeat_until_done: bool) -> Result<Value> {
+        engine().call(json!({"fn": "replace_map", "snapshot": self.id, "item": item, "wildcard_maps": maps,
+                             "repeat_until_done": repeat_until_done, "inserts_dir": ctx_json(ctx)}))
+    }
+    /// runtime.rs:1085-1133.
+    pub fn goto_map_target(&self, text: &str, target_maps: &[Value], ctx: &ProgramLoadContext) -> Result<String> {
+        let reply = engine().call(json!({"fn": "goto_map", "snapshot": self.id, "text": text, "target_maps": target_maps, "inserts_dir": ctx_json(ctx)}))?;
+        reply["target"].as_str().map(str::to_string).ok_or_else(|| anyhow!("ie_b200: malformed goto_map reply"))
+    }
+}
+
+impl Drop for LiveInserts {
+    fn drop(&mut self) {
+        let _ = engine().call(json!({"fn": "snapshot_free", "snapshot": self.id}));
+    }
 }
 
 /// interp.rs:31.
