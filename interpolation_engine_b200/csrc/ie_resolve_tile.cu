@@ -139,6 +139,7 @@ struct Smem {
     uint32_t warp_scan[NW];
     uint32_t q_n[1];
     uint32_t q_lvl[3];         // P3: groups appended per level (rotating)
+    uint32_t q_nb;             // leaf groups queued from the back of q[] (top-level leaves)
     uint32_t ev_n;             // events allocated
     uint32_t overflow;
 };
@@ -622,7 +623,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     if (tid <= TT) sm.t_start[tid] = (uint32_t)(my_off - off0);
     if (NT == TT && tid == 0) sm.t_start[TT] = (uint32_t)(off_end - off0);
     if (tid < TT) { sm.t_err[tid] = 0; sm.t_flags[tid] = 0; sm.t_splice[tid] = 0; }
-    if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; sm.q_lvl[0] = 0; sm.q_lvl[1] = 0; sm.q_lvl[2] = 0; }
+    if (tid == 0) { sm.q_n[0] = 0; sm.overflow = 0; sm.ev_n = 0; sm.q_lvl[0] = 0; sm.q_lvl[1] = 0; sm.q_lvl[2] = 0; sm.q_nb = 0; }
     if (tid < 17) {
         auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
         sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
@@ -743,7 +744,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
         if (lane == 31 && incl) wbase = atomicAdd(&sm.ev_n, incl);
         wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
         const uint32_t eb = wbase + incl - ne;
-        uint32_t flags = 0, leaf_lo = 0;  // leaf_lo: which of the template's first 32 events are leaf groups
+        uint32_t flags = 0, leaf_lo = 0, leaf_top = 0;  // which of the template's first 32 events are leaf groups / leaf groups at the top level
         bool fits = true;
         if (active && eb + ne > (uint32_t)E_CAP) { sm.overflow = 1; fits = false; }  // more brace events than the tile's tables hold
         else if (active) {
@@ -796,7 +797,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
                             sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
                             cur_open = sm.ev_c[EI(o)];
                             if (o + 1 == e) {  // closes without children: a leaf group
-                                if (k <= 32) leaf_lo |= 1u << (k - 1); else sm.u.scan.q[IE_BOUND(atomicAdd(&sm.q_n[0], 1u), Q_CAP)] = (tid << 16) | o;
+                                if (k <= 32) { leaf_lo |= 1u << (k - 1); if (cur_open == NONE16) leaf_top |= 1u << (k - 1); }
+                                else sm.u.scan.q[IE_BOUND(atomicAdd(&sm.q_n[0], 1u), Q_CAP)] = (tid << 16) | o;
                             }
                         }
                     }
@@ -822,23 +824,38 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
             sm.t_ne[tid] = (uint16_t)ne;
             sm.t_flags[tid] = flags;
         }
-        // the leaves found above go to the lookup queue: one shared atomic per warp instead of one per leaf
-        const uint32_t nl = (active && fits) ? (uint32_t)__popc(leaf_lo) : 0u;
-        uint32_t lincl = nl;
+        // The leaves found above go to the lookup queue, one shared atomic per warp and class instead of one per leaf.
+        // Two classes: leaves INSIDE another group enter from the front, leaves at the top level from the back.  P3 hands
+        // the queue out in that order, so the threads that will climb a parent chain (`{q-{idx-{slot-A}}}`: three
+        // lookups) sit together in the same warps and those warps keep all their lanes busy on every hop; the warps that
+        // hold top-level leaves are done after one lookup.  (Mixed, every warp ran its later hops at half its lanes.)
+#ifdef IE_P3_LEVELS
+        leaf_top = 0;
+#endif
+        if (!(active && fits)) { leaf_lo = 0; leaf_top = 0; }
+        const uint32_t n_in = (uint32_t)__popc(leaf_lo & ~leaf_top), n_top = (uint32_t)__popc(leaf_top);
+        uint32_t packed = n_in | (n_top << 16), pincl = packed;  // both counts through one warp scan
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, lincl, d);
-            if ((int)lane >= d) lincl += y;
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pincl, d);
+            if ((int)lane >= d) pincl += y;
         }
-        uint32_t qbase = 0;
-        if (lane == 31 && lincl) qbase = atomicAdd(&sm.q_n[0], lincl);
-        uint32_t qi = __shfl_sync(0xFFFFFFFFu, qbase, 31) + lincl - nl;
+        uint32_t base_in = 0, base_top = 0;
+        if (lane == 31) {
+            if (pincl & 0xFFFFu) base_in = atomicAdd(&sm.q_n[0], pincl & 0xFFFFu);
+            if (pincl >> 16) base_top = atomicAdd(&sm.q_nb, pincl >> 16);
+        }
+        const uint32_t excl = pincl - packed;
+        uint32_t qi = __shfl_sync(0xFFFFFFFFu, base_in, 31) + (excl & 0xFFFFu);
+        uint32_t qj = __shfl_sync(0xFFFFFFFFu, base_top, 31) + (excl >> 16);
         const uint32_t eb0 = wbase + incl - ne;
         while (leaf_lo) {
             const uint32_t k1 = (uint32_t)__ffs(leaf_lo) - 1u;  // the leaf's close is event k1 + 1 of the template, its open event k1
             leaf_lo &= leaf_lo - 1u;
-            sm.u.scan.q[IE_BOUND(qi, Q_CAP)] = (tid << 16) | (eb0 + k1);
-            ++qi;
+            const bool top = (leaf_top >> k1) & 1u;
+            const uint32_t at = top ? (uint32_t)Q_CAP - 1u - qj : qi;
+            sm.u.scan.q[IE_BOUND(at, Q_CAP)] = (tid << 16) | (eb0 + k1);
+            if (top) ++qj; else ++qi;
         }
     }
     PHASE_MARK(3);
@@ -860,9 +877,9 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
     // thread sees the same level bounds without a second barrier.)
     {
 #ifndef IE_P3_LEVELS
-        const uint32_t nq = sm.q_n[0];
+        const uint32_t n_in = sm.q_n[0], nq = n_in + sm.q_nb;  // leaves inside other groups first, then the top-level ones (from the back)
         for (uint32_t k = tid; k < nq; k += NT) {
-            const uint32_t item = sm.u.scan.q[k];
+            const uint32_t item = sm.u.scan.q[k < n_in ? k : (uint32_t)Q_CAP - 1u - (k - n_in)];
             if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
             resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
         }

@@ -257,8 +257,68 @@ def host_mirror(eng, oracle, seed, ins, templates, bad, rounds=25):
     return n
 
 
+def deep_and_mutate(eng, oracle, seed, bad):
+    """(1) Inputs that need more than the default bounds - value chains with text left of every group (one splice frame
+    per level), results of hundreds of kilobytes on the general path, thousands of lookups in one template - through the
+    host API with default limits: wherever the oracle (given generous bounds) resolves, the engine must too, never
+    "limit".  (2) A table patched in place by random set / delete operations against a dict that follows them."""
+    rng = random.Random(seed ^ 0xDEE9)
+    n = 0
+    depth = rng.choice([3, 26, 60, 150, 400, 1500])
+    ins = {"A%d" % k: rng.choice(["x%d" % k, "", "lit "]) + "{A%d}" % (k + 1) + rng.choice(["", ".", "!"]) for k in range(1, depth)}
+    ins["A%d" % depth] = rng.choice(["end", "", "y" * rng.choice([10, 3000, 70000])])
+    ins.update({"big": "ab" * rng.choice([10, 40000, 300000]), "k": "v", "e": ""})
+    many = rng.choice([10, 3000, 6000])
+    templates = ["v={A1}", "{A1}", "." + BS + "}{A1}", "<{A%d}>" % max(1, depth // 2), "." + BS + "}" + "{k}{e}" * many, "{k}{e}" * many, "." + BS + "}<{big}>{big}",
+                 "{big}{big}", "." + BS + "}{A%d}|{big}" % max(1, depth - 2)]
+    kind, res = eng.call("interpolate_many", inserts=ins, contents=templates, clock=CLOCK)
+    assert kind == "ok"
+    for t, r in zip(templates, res):
+        want = oracle.call("interpolate_inserts", inserts=ins, content=t, clock=CLOCK, max_iterations=100000, max_bytes=1 << 26)
+        got = ("ok", r["ok"]) if "ok" in r else ("err", r["err"])
+        n += 1
+        if got != want:
+            bad.append(("deep", seed, t[:80]))
+            if len(bad) < 6:
+                print("MISMATCH deep seed", seed, "depth", depth, repr(t)[:120], "\n  gpu   ", repr(got)[:200], "\n  oracle", repr(want)[:200], flush=True)
+    # (2) in-place mutation
+    cur = {"a": "A", "i": 1, "q-1": "first", "lst": ["x", 2]}
+    cur.update({"pad-%d" % k: "p%d" % k for k in range(rng.choice([0, 40, 5000]))})
+    table = eng.pack(ie.PackedInserts.from_dict(cur))
+    keys = ["a", "b", "c", "i", "q-1", "q-2", "k" * 16, "K" * 17, "a key that is clearly longer than sixteen bytes", "pad-3"]
+    values = ["", "v", "x" * 15, "y" * 16, "z" * 17, "long value " * rng.randint(2, 40), 3, -5, ["l", 2], True, None, {"o": 1}]
+    tpl = ["{a}", "<{a}|{b}|{c}>", "{%s}" % ("k" * 16), "x{%s}" % ("K" * 17), "{a key that is clearly longer than sixteen bytes}!", "{q-{i}}", "{i}", "{missing}", "{{b}}",
+           "{pad-3}{pad-4}", "{lst}"]
+    arena = ie.Arena.from_strings(tpl)
+    for step in range(25):
+        try:
+            if rng.random() < 0.7:
+                ops = [(rng.choice(keys), rng.choice(values)) for _ in range(rng.randint(1, 5))]
+                table.set(ops)
+                for k, v in ops:
+                    cur[k] = v
+            else:
+                ks = [rng.choice(keys + ["never-there"]) for _ in range(rng.randint(1, 3))]
+                table.delete(ks)
+                for k in ks:
+                    cur.pop(k, None)
+        except ie.EngineError as ex:  # no room left: a fresh pack takes over (the operations that fit were applied)
+            assert "pack the snapshot again" in str(ex)
+            cur = None
+        if cur is None:
+            break
+        got = eng.resolve_batch(table, arena)
+        out, offs, status, aux = oracle.build_table(ie.PackedInserts.from_dict(cur)).resolve_batch(arena.bytes, arena.offs)
+        compare("mutate step %d" % step, seed, cur, tpl, got.status_raw, got.lens, got.get, got.tags, out, offs, status, aux, bad)
+        n += len(tpl)
+    return n
+
+
 def main():
     argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for a in sys.argv[1:]:
+        if a.startswith("--lib="):  # e.g. --lib=libie_b200_dbg.so: the IE_DEBUG_BOUNDS build of the library
+            ie.LIB_PATH = os.path.join(os.path.dirname(ie.LIB_PATH), a[len("--lib="):])
     seconds = float(argv[0]) if argv else 60.0
     seed = first_seed = int(argv[1]) if len(argv) > 1 else 1
     eng, oracle = ie.Engine(0), oracle_lib.load()
@@ -296,8 +356,17 @@ def main():
         n_done += len(templates) * 5 + glob_and_escape(eng, oracle, seed, templates, bad)
         n_done += many_states(eng, oracle, seed, ins, templates, bad)
         n_done += host_mirror(eng, oracle, seed, ins, templates, bad)
+        n_done += deep_and_mutate(eng, oracle, seed, bad)
         seed += 1
     print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - first_seed, len(bad)))
+    for name in ("ie_debug_bound_violations", "ie_debug_bound_violations_small"):
+        if hasattr(eng.lib, name):  # IE_DEBUG_BOUNDS build: every tile-table index was checked against its capacity
+            import ctypes
+            v = (ctypes.c_ulonglong * 4)()
+            getattr(eng.lib, name)(v)
+            print("%s: %d violations (first: line %d, index %d, capacity %d)" % (name, v[0], v[1], v[2], v[3]))
+            if v[0]:
+                bad.append(("bounds", name))
     sys.exit(1 if bad else 0)
 
 
