@@ -596,7 +596,7 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     if (n * t->n_states >= 0xFFFFFFFFull) return fail(IE_E_INVALID, "resolve: at most 2^32-2 (snapshot, template) pairs per batch");
     if (s != e->stream && t->ready) CU(cudaStreamWaitEvent(s, t->ready, 0));
     if (rounds > 3) rounds = 3;
-    if (t->n_states != 1 || !t->has_balanced) rounds = 0;  // no value could be spliced: the rounds would be empty launches
+    if (!t->has_balanced) rounds = 0;  // no value could be spliced: the rounds would be empty launches
     ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0, rounds != 0);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->d_views, t->n_states, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
@@ -1020,14 +1020,20 @@ ie_status_t ie_shards_gather(const ie_shard_result* shards, uint32_t n_shards, u
     auto copy = [&](uint32_t g) {
         const ie_shard_result& sh = shards[g];
         uint64_t at = base[g];
-        for (uint64_t i = 0; i < sh.n; ++i) {
-            const uint32_t len = sh.res.out_lens[i];
-            out_offs[sh.first + i] = at;
-            if (len) std::memcpy(out + at, sh.res.out + sh.res.out_offs[i], len);
-            at += len;
-            status[sh.first + i] = sh.res.status[i];
-            aux[sh.first + i] = sh.res.aux[i];
+        // results of one tile lie back to back in template order in the shard's arena: copy whole runs, not strings
+        for (uint64_t i = 0; i < sh.n;) {
+            const uint64_t src0 = sh.res.out_offs[i];
+            uint64_t run = 0, j = i;
+            for (; j < sh.n && sh.res.out_offs[j] == src0 + run; ++j) {
+                out_offs[sh.first + j] = at + run;
+                run += sh.res.out_lens[j];
+            }
+            if (run) std::memcpy(out + at, sh.res.out + src0, run);
+            at += run;
+            i = j;
         }
+        std::memcpy(status + sh.first, sh.res.status, sh.n * sizeof(int32_t));
+        std::memcpy(aux + sh.first, sh.res.aux, sh.n * sizeof(uint32_t));
     };
     std::vector<std::thread> th;
     for (uint32_t g = 1; g < n_shards; ++g) th.emplace_back(copy, g);

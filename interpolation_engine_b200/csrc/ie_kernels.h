@@ -82,6 +82,10 @@ struct IeRound {
     uint64_t* again_bytes;       // out: bytes of their texts, each rounded up to 16
     uint32_t allow_splice;       // 0: values with groups of their own are punted to the general path (no rounds)
     uint32_t last_round;         // 1: what would need yet another round goes to the general path instead
+    // rounds >= 2 on a table of several snapshots: a round's tile mixes templates of different snapshots, so every
+    // template finds its own table through its result index (result_map[i] / per_state); 0 = one snapshot
+    uint32_t per_state;
+    const IeTableView* views_all;
 };
 
 cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,

@@ -451,7 +451,7 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if (n == 0) return cudaSuccess;
     // rounds need one snapshot (the table must stay tile-uniform) and result indices that fit the round map
     // (the gather hands out index and byte offset in one 64-bit atomic, 24 bits of it for the index)
-    if (!ws.round_ctl || n_states != 1 || n >= (1u << 24)) rescan_rounds = 0;
+    if (!ws.round_ctl || n * n_states >= (1u << 24)) rescan_rounds = 0;
     IeRound rd{};
     rd.allow_splice = rescan_rounds ? 1u : 0u;
     if (rescan_rounds) { rd.again_list = ws.round_list[0]; rd.again_count = &ws.round_ctl->count[0]; rd.again_bytes = &ws.round_ctl->bytes[0]; }
@@ -478,9 +478,11 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
         r2.again_bytes = &ws.round_ctl->bytes[in ^ 1];
         r2.allow_splice = 1;
         r2.last_round = k + 1 == rescan_rounds;
+        r2.per_state = n_states > 1 ? (uint32_t)n : 0u;  // several snapshots: every template of the round finds its own table
+        r2.views_all = d_views;
         // templates = the gathered texts inside the out arena (absolute offsets in round_offs); results still go to
         // the caller's arrays at the original result indices
-        if ((err = ie_launch_resolve_tiles(d_views, 1, d_out, ws.round_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+        if ((err = ie_launch_resolve_tiles(d_views, 1, d_out, ws.round_offs, n * n_states, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                            d_info, out_bias, tt, r2, stream)) != cudaSuccess)
             return err;
     }

@@ -545,10 +545,12 @@ __device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& t
 // per template took 11 ms for a single 16 KB template with 600 groups.)  The per-template parameters come from the
 // dead segment table: five words per template.
 template <bool ROUNDS>
-__device__ __noinline__ void copy_own_pieces(Smem* smp, IeTableView tv, const uint8_t* __restrict__ tp, uint32_t nt, uint8_t* out) {
+__device__ __noinline__ void copy_own_pieces(Smem* smp, IeTableView tv0, const uint8_t* __restrict__ tp, uint32_t nt, uint8_t* out,
+                                             const uint32_t* __restrict__ map_i0, uint32_t per_state, const IeTableView* __restrict__ views_all) {
     Smem& sm = *smp;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t t = warp; t < nt; t += NW) {
+        const IeTableView tv = (ROUNDS && map_i0 && per_state) ? views_all[(__ldg(map_i0 + t) & IE_AGAIN_INDEX_MASK) / per_state] : tv0;
         const uint32_t* par = &sm.u.seg.out[5 * t];
         const uint32_t mode = par[0], err_g = par[1], olen = par[4];
         if (!olen) continue;
@@ -597,7 +599,7 @@ __device__ __noinline__ void per_thread_range(Smem* sm, IeTableView tv, const ui
 // of at most IE_SPLIT_MIN templates that still does not fit takes the exact per-thread path instead.
 #define IE_SPLIT_MIN 1u
 template <bool ROUNDS>
-__device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, uint32_t state, const uint8_t* __restrict__ tmpl,
+__device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv_tile, uint32_t state, const uint8_t* __restrict__ tmpl,
                                               const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out, uint64_t out_cap,
                                               uint64_t* __restrict__ out_offs, uint32_t* __restrict__ out_lens,
                                               int32_t* __restrict__ status_out, uint32_t* __restrict__ aux_out, const IeWorkspace& ws,
@@ -605,6 +607,14 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
                                               uint64_t i0, uint32_t nt) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PHASE_INIT();
+    // The table a template is resolved against: the tile's snapshot, except in a rescan round on a table of several
+    // snapshots, where the round's templates come from all of them and each one finds its own through its result index.
+    const bool per_template_view = ROUNDS && rd.result_map && rd.per_state;
+    auto view_of = [&](uint32_t t) -> IeTableView {
+        if (!per_template_view) return tv_tile;
+        return rd.views_all[(__ldg(rd.result_map + i0 + t) & IE_AGAIN_INDEX_MASK) / rd.per_state];
+    };
+    const IeTableView tv = (per_template_view && tid < nt) ? view_of(tid) : tv_tile;  // this thread's own template (P2, P4)
     const uint64_t i = i0 + tid;                    // template
     const bool active = tid < nt;
     // result index; in a rescan round the map also says whether the ORIGINAL template was one whole group (only
@@ -881,7 +891,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
         for (uint32_t k = tid; k < nq; k += NT) {
             const uint32_t item = sm.u.scan.q[k < n_in ? k : (uint32_t)Q_CAP - 1u - (k - n_in)];
             if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
-            resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
+            if (per_template_view) { const IeTableView tvi = view_of(item >> 16); resolve_group<ROUNDS>(sm, tvi, tp, item >> 16, item & 0xFFFFu); }
+            else resolve_group<ROUNDS>(sm, tv_tile, tp, item >> 16, item & 0xFFFFu);
         }
 #else
         uint32_t lo = 0, hi = sm.q_n[0];
@@ -891,7 +902,8 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
             for (uint32_t k = lo + tid; k < hi; k += NT) {
                 const uint32_t item = sm.u.scan.q[k];
                 if (sm.t_flags[item >> 16] & (TF_PUNT | TF_VERBATIM)) continue;  // punted after some of its leaves were queued
-                const uint32_t parent = resolve_group<ROUNDS>(sm, tv, tp, item >> 16, item & 0xFFFFu);
+                const IeTableView tvi = view_of(item >> 16);
+                const uint32_t parent = resolve_group<ROUNDS>(sm, tvi, tp, item >> 16, item & 0xFFFFu);
                 if (parent != NONE16) sm.u.scan.q[IE_BOUND(hi + atomicAdd(next_n, 1u), Q_CAP)] = (item & 0xFFFF0000u) | parent;
             }
             __syncthreads();
@@ -994,7 +1006,7 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv, u
             par[0] = mode; par[1] = err_g; par[2] = (uint32_t)off; par[3] = (uint32_t)(off >> 32); par[4] = olen;
         }
         __syncthreads();
-        copy_own_pieces<ROUNDS>(&sm, tv, tp, nt, out);
+        copy_own_pieces<ROUNDS>(&sm, tv, tp, nt, out, (ROUNDS && rd.result_map) ? rd.result_map + i0 : nullptr, rd.per_state, rd.views_all);
         return true;
     }
     uint8_t* gout = out + tile_begin;
