@@ -690,8 +690,7 @@ def test_rescan_rounds_on_many_snapshots(eng, oracle):
         for j in range(n):
             if status[j] != KIND_TO_CODE["limit"]:
                 assert got.get(s * n + j) == out[int(offs[j]):int(offs[j + 1])].tobytes(), (s, templates[j])
-    # only what needs a third round (">> {deep} <<": deep -> greet -> name; "-{q-{i}}-" with i = 3) and the runaway state took the general path
-    assert got.n_general < S * 3, got.n_general
+    assert got.n_general < S // 10, got.n_general  # the rounds did the work, not the one-lane general path
     none = eng.resolve_batch(table, arena, limits=(0, 0, 0, 0, 0))
     d_t, d_o = eng.alloc(arena.bytes.nbytes + 16).upload(arena.bytes), eng.alloc((n + 1) * 8).upload(arena.offs)
     nr = S * n
@@ -704,7 +703,9 @@ def test_rescan_rounds_on_many_snapshots(eng, oracle):
         generals.append(int(bufs[5].download(np.uint64, 8)[2]))
         st = bufs[3].download(np.int32, nr)
         assert np.array_equal(st & 0xFF, none.status), rounds
-    assert generals[0] > 4 * S and generals[1] < 3 * S, generals
+    # without rounds every template whose lookup returns a brace-holding value is the general path's (3-4 per state); two
+    # rescan rounds after the first pass resolve chains three values deep (">> {deep} <<": deep -> greet -> name)
+    assert generals[0] > 3 * S and generals[1] < S // 10, generals
 
 
 def test_snapshots_that_outlive_a_call(eng, oracle):
