@@ -187,6 +187,9 @@ __global__ void __launch_bounds__(IE_GENERAL_SMALL_THREADS) ie_resolve_general_k
     // per template, so 32 templates on the lanes of one warp run one after the other anyway (measured: 2.5 ms per
     // template that way); one lane per warp lets the SM interleave dozens of independent automata instead.  The other
     // lanes join for the bulk passes around the machine (brace count, result copies).
+    // Launched with programmatic stream serialisation (IE_PDL): the launch itself overlaps the tail of the kernel before it
+    // in the stream; nothing that kernel wrote (the work lists and their counts) is read before this wait returns.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t worker = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     // the full-size tier has ws.general_workers scratch areas, which need not fill the last block
@@ -495,14 +498,31 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ie_resolve_general_kernel<true><<<sms * 3, IE_GENERAL_SMALL_THREADS, smem, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
-                                                                                d_status, d_aux, ws, d_info, max_expansions, small_t,
-                                                                                IE_GENERAL_SMALL_KEY, out_bias, ws.general_list, ws.general_count,
-                                                                                ws.retry_list, ws.retry_count, stride, 0u);
-    if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    ie_resolve_general_kernel<false><<<ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32), IE_GENERAL_SMALL_THREADS, 0, stream>>>(d_views, n, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens,
-                                                                         d_status, d_aux, ws, d_info, max_expansions, tcap, IE_KEY_SCRATCH,
-                                                                         out_bias, ws.retry_list, ws.retry_count, nullptr, nullptr, 0u, ie_general_fcap(tcap));
+    // Both tiers are usually empty (C4: nothing is punted) and then cost only their launch; with programmatic stream
+    // serialisation that launch overlaps the tail of the kernel in front (the kernels start with griddepcontrol.wait).
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = stream;
+    cfg.attrs = pdl;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(sms * 3));
+    cfg.blockDim = dim3(IE_GENERAL_SMALL_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    const uint64_t per_state = n;
+    const uint32_t key_small = IE_GENERAL_SMALL_KEY, key_full = IE_KEY_SCRATCH, zero = 0u, fcap = ie_general_fcap(tcap);
+    uint32_t* const no_list = nullptr;
+    if ((err = cudaLaunchKernelEx(&cfg, ie_resolve_general_kernel<true>, d_views, per_state, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+                                  d_info, max_expansions, small_t, key_small, out_bias, (const uint32_t*)ws.general_list, (const uint32_t*)ws.general_count,
+                                  ws.retry_list, ws.retry_count, stride, zero)) != cudaSuccess)
+        return err;
+    cfg.gridDim = dim3(ws.general_workers / (IE_GENERAL_SMALL_THREADS / 32));
+    cfg.dynamicSmemBytes = 0;
+    if ((err = cudaLaunchKernelEx(&cfg, ie_resolve_general_kernel<false>, d_views, per_state, d_tmpl, d_offs, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+                                  d_info, max_expansions, tcap, key_full, out_bias, (const uint32_t*)ws.retry_list, (const uint32_t*)ws.retry_count, no_list,
+                                  no_list, zero, fcap)) != cudaSuccess)
+        return err;
     return cudaGetLastError();
 }
 

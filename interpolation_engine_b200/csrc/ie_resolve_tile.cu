@@ -768,7 +768,10 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv_ti
                 // pass 2: ONE loop over the events (every lane runs its `ne` iterations of the same body; a loop over
                 // chunks with an inner loop over their events ran at 6 of 32 lanes: templates start at different chunk
                 // phases, so at any chunk step only a few lanes have events)
-                uint32_t n_open = 0, cur_open = NONE16;
+                // The open group and its two nearest ancestors live in registers (par1 = parent of cur_open, par2 = its
+                // parent); the links in ev_c[] are written for P3 but read back here only three levels up, off the
+                // loop's dependent chain.  Child counts are bumped with fire-and-forget shared atomics.
+                uint32_t n_open = 0, cur_open = NONE16, par1 = NONE16, par2 = NONE16;
                 bool punt = false, stray = false;
                 uint32_t c = c0, m = 0, ev = 0;
                 for (uint32_t k = 0; k < ne; ++k) {
@@ -797,15 +800,16 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv_ti
                         sm.ev_pos[EI(e)] = pos;
                         sm.ev_c[EI(e)] = (uint16_t)cur_open;
                         sm.ev_a[EI(e)] = 0;
-                        if (cur_open != NONE16) sm.ev_a[EI(cur_open)] += 1;
-                        cur_open = e;
+                        if (cur_open != NONE16) atomicAdd(&sm.ev_a[EI(cur_open)], 1u);  // (result unused: no round trip)
+                        par2 = par1; par1 = cur_open; cur_open = e;
                     } else {
                         sm.ev_pos[EI(e)] = pos | EV_CLOSE;
                         if (cur_open == NONE16) stray = true;
                         else {
                             const uint32_t o = cur_open;
                             sm.ev_match[EI(o)] = (uint16_t)e; sm.ev_match[EI(e)] = (uint16_t)o;
-                            cur_open = sm.ev_c[EI(o)];
+                            cur_open = par1; par1 = par2;
+                            par2 = par1 != NONE16 ? (uint32_t)sm.ev_c[EI(par1)] : NONE16;
                             if (o + 1 == e) {  // closes without children: a leaf group
                                 if (k <= 32) { leaf_lo |= 1u << (k - 1); if (cur_open == NONE16) leaf_top |= 1u << (k - 1); }
                                 else sm.u.scan.q[IE_BOUND(atomicAdd(&sm.q_n[0], 1u), Q_CAP)] = (tid << 16) | o;

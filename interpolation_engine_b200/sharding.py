@@ -1,5 +1,6 @@
-"""Sharding of independent work units over GPUs (SURVEY.md §8 e): contiguous ranges, no data-path
-collective; the only cross-rank steps are the timing reduction and the host-side gather."""
+"""Sharding of independent work units over GPUs (SURVEY.md §8 e): contiguous ranges, no data-path collective.
+`shard_range` is the partition ie_resolve_batch_multi applies inside one process (the host gather is ie_shards_gather, in
+C); with one process per GPU (bench.py under torchrun) the only cross-rank step is the timing reduction below."""
 
 
 def shard_range(n_total, rank, world):
@@ -7,15 +8,6 @@ def shard_range(n_total, rank, world):
     per = -(-n_total // world)
     lo = min(n_total, rank * per)
     return lo, min(n_total, lo + per)
-
-
-def gather_offsets(shard_out_bytes):
-    """Base offset of every shard's result arena in the concatenated result (host prefix over shard totals)."""
-    bases, acc = [], 0
-    for b in shard_out_bytes:
-        bases.append(acc)
-        acc += int(b)
-    return bases, acc
 
 
 def reduce_timing(dist, local_ms, local_units):

@@ -208,12 +208,26 @@ int orc_resolve_batch(void* table, const uint8_t* tmpl, const uint64_t* offs, ui
     for (int k = 1; k < threads; ++k) th.emplace_back(work, k);
     work(0);
     for (auto& x : th) x.join();
-    uint64_t total = 0, i = 0;
-    for (auto& o : outs) for (auto& s : o) { out_offs[i++] = total; total += s.size(); }
+    // the result arena is assembled by the same threads, each copying its own strings behind a prefix over the
+    // per-thread totals (a serial 284 MB copy here was a third of the measured CPU time on 16 threads)
+    std::vector<uint64_t> tbytes((size_t)threads + 1, 0), tfirst((size_t)threads + 1, 0);
+    for (int k = 0; k < threads; ++k) {
+        uint64_t b = 0;
+        for (auto& s : outs[(size_t)k]) b += s.size();
+        tbytes[(size_t)k + 1] = tbytes[(size_t)k] + b;
+        tfirst[(size_t)k + 1] = tfirst[(size_t)k] + outs[(size_t)k].size();
+    }
+    const uint64_t total = tbytes[(size_t)threads];
     out_offs[n] = total;
     uint8_t* arena = (uint8_t*)std::malloc(total ? total : 1);
-    i = 0;
-    for (auto& o : outs) for (auto& s : o) { std::memcpy(arena + out_offs[i++], s.data(), s.size()); }
+    auto copy = [&](int tid) {
+        uint64_t at = tbytes[(size_t)tid], i = tfirst[(size_t)tid];
+        for (auto& s : outs[(size_t)tid]) { out_offs[i++] = at; std::memcpy(arena + at, s.data(), s.size()); at += s.size(); }
+    };
+    std::vector<std::thread> tc;
+    for (int k = 1; k < threads; ++k) tc.emplace_back(copy, k);
+    copy(0);
+    for (auto& x : tc) x.join();
     *out_arena = arena;
     return 0;
 }

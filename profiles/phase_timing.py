@@ -1,5 +1,5 @@
 import ctypes, os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import interpolation_engine_b200 as ie
 ie.LIB_PATH = os.path.join(os.path.dirname(ie.LIB_PATH), 'libie_b200_timing.so')
 from interpolation_engine_b200 import workloads
@@ -15,7 +15,7 @@ lib = ctypes.CDLL(ie.LIB_PATH)
 lib.ie_debug_phase_cycles(buf, 1)
 r = eng.resolve_batch(table, tmpl)
 lib.ie_debug_phase_cycles(buf, 1)
-names = ['-','P0+P1','sync1','P2b','sync2b','P3','sync3','P4 sizes','scan+emit','claim+offs','P5 passA','P5 passB','P2a','sync2a']
+names = ['-','P0+P1','sync1','P2 events+structure','sync2','P3 lookups','sync3','P4 sizes','scan+emit','claim+offs','P5 passA','P5 passB','-','-']
 tiles = (tmpl.n + 127)//128
 tot = sum(buf[k] for k in range(14))
 for k,nm in enumerate(names): print(f"{nm:14s} {buf[k]/tiles:10.0f} cyc/tile  {100*buf[k]/tot:5.1f}%")

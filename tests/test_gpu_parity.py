@@ -780,7 +780,8 @@ def test_resolve_batch_multi_and_gather(eng, oracle):
         tmpl = workloads.c4_templates(max(n, 1), start=77)
         arena = ie.Arena(tmpl.bytes[:int(tmpl.offs[n])], tmpl.offs[:n + 1])
         per, (out, offs, status, aux) = ie.resolve_batch_multi(engines, tables, arena)
-        assert [first for first, _ in per] == [min(n, g * -(-n // G)) for g in range(G)] and sum(len(b.lens) for _, b in per) == n
+        from interpolation_engine_b200 import sharding
+        assert [(first, first + len(b.lens)) for first, b in per] == [sharding.shard_range(n, g, G) for g in range(G)]  # the documented partition
         w_out, w_offs, w_status, _ = oracle.build_table(state).resolve_batch(arena.bytes, arena.offs, threads=8)
         assert np.array_equal(status & 0xFF, w_status) and np.array_equal(offs, w_offs) and np.array_equal(out, w_out)
         for first, b in per:  # every shard by itself too

@@ -47,4 +47,3 @@ def test_shard_ranges_cover_everything():
             r = [sharding.shard_range(n, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
-    assert sharding.gather_offsets([5, 0, 7]) == ([0, 5, 5], 12)
