@@ -28,17 +28,19 @@
 // internal per-template status while a batch is in flight
 #define IE_RES_PUNT 0xFF  // fast path declined; the general kernel resolves it
 
-// The first 16 bytes hold everything a hit needs besides the key itself, so a probe is two
-// independent 16-byte loads (header + inline key) = one L2 round trip.
-struct __align__(16) IeSlot {
+// A probe reads the slot's FIRST 32 bytes - everything a hit needs (hash, key length, value length / tag / flags, value
+// reference) and the inline key - with ONE 256-bit load (LDG.E.256, sm_100a): one L1 tag request and one L2 round trip
+// per probe.  The second 32 bytes (entry index, key reference, the inline value) are read only when the value itself is
+// needed right away (the next hop of a `{q-{idx-{slot-A}}}` chain, a typed simple-path result).
+struct __align__(32) IeSlot {
     uint32_t hash;       // murmur3_32(key)
-    uint32_t key_len;    // IE_SLOT_EMPTY when free
+    uint32_t key_len;    // IE_SLOT_EMPTY when free, IE_SLOT_TOMB when deleted
     uint32_t vl_tf;      // value length (25 bits) | tag << 25 | value flags << 28
     uint32_t val_off16;  // value bytes at base + 16 * val_off16
+    uint8_t key_inline[IE_INLINE_BYTES];
     uint32_t entry;      // index of the insert in the caller's packed arrays (n, n+1: clock keys)
     uint32_t key_off16;  // key bytes at base + 16 * key_off16
-    uint32_t pad[2];
-    uint8_t key_inline[IE_INLINE_BYTES];
+    uint32_t pad[2];     // pad[0]: claim word of the device-side build
     uint8_t val_inline[IE_INLINE_BYTES];
 };
 #define IE_VLEN_MAX 0x01FFFFFFu

@@ -441,7 +441,7 @@ __device__ __forceinline__ uint32_t hash_short(const uint4& k, uint32_t klen) { 
 template <bool ROUNDS>
 __device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& tv, const uint8_t* __restrict__ tp, uint32_t t, uint32_t g) {
   uint32_t carry_e = NONE16;
-  uint4 carry_v = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
+  uint4 carry_v = make_uint4(0, 0, 0, 0);
   for (;;) {
     const uint32_t c = sm.ev_match[EI(g)];
     const bool simple = (sm.ev_pos[EI(g)] & EV_SIMPLE) != 0;
@@ -449,16 +449,26 @@ __device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& t
     const IeSlot* hit = nullptr;
     uint4 key;
     const IeSlot* slots = reinterpret_cast<const IeSlot*>(tv.base);
+    // the typed simple path reports the entry, a group inside another group hands its (inline) value to the parent's key
+    const bool want_tail = simple || sm.ev_c[EI(g)] != NONE16;
+    uint4 tail_hdr = make_uint4(0, 0, 0, 0), tail_val = make_uint4(0, 0, 0, 0);
     if (short_key(sm, tv, tp, g, key, klen, carry_e, carry_v)) {
         if (klen == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
         else {
             const uint32_t h = hash_short(key, klen);
             uint32_t idx = h & tv.mask;
             for (;;) {
-                // header and inline key are independent 16-byte loads: one L2 round trip per probe
-                const uint4* sp = reinterpret_cast<const uint4*>(slots + idx);
-                const uint4 q0 = __ldg(sp), q2 = __ldg(sp + 2);
-                q3 = __ldg(sp + 3);  // inline value: same 32-byte sector as the inline key
+                // header and inline key come with ONE 256-bit load: one L1 tag request, one L2 round trip per probe; the
+                // slot's second half (entry index, inline value) rides along only when a hit will need it right away
+                uint4 q0, q2;
+                asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w)
+                             : "l"(slots + idx));
+                if (want_tail)
+                    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(tail_hdr.x), "=r"(tail_hdr.y), "=r"(tail_hdr.z), "=r"(tail_hdr.w), "=r"(tail_val.x), "=r"(tail_val.y),
+                                   "=r"(tail_val.z), "=r"(tail_val.w)
+                                 : "l"(reinterpret_cast<const uint8_t*>(slots + idx) + 32));
                 if (q0.y == IE_SLOT_EMPTY) break;
                 if (q0.x == h && q0.y == klen && q2.x == key.x && q2.y == key.y && q2.z == key.z && q2.w == key.w) {
                     hit = slots + idx; vl_tf = q0.z; val_off16 = q0.w;
@@ -520,7 +530,7 @@ __device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& t
     }
     const uint32_t parent = sm.ev_c[EI(g)];
     if (parent == NONE16) {
-        if (simple) { sm.t_aux[t] = __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
+        if (simple) { sm.t_aux[t] = klen <= 16 ? tail_hdr.x : __ldg(&hit->entry); sm.t_tag[t] = (uint8_t)IE_SLOT_TAG(vl_tf); }
         return NONE16;
     }
     // one child of `parent` resolved; whoever resolves the last one carries on with the parent / hands it to the next level
@@ -530,9 +540,9 @@ __device__ __forceinline__ uint32_t resolve_group(Smem& sm, const IeTableView& t
     return parent;  // (the level barrier orders the siblings' results before the parent's lookup)
 #endif
     __threadfence_block();  // the siblings' results (written before their decrements) are visible from here on
-    // short-key hits leave the slot's inline value in q3 (valid when the value is inline)
+    // short-key hits leave the slot's inline value in tail_val (valid when the value is inline)
     carry_e = (klen <= 16 && IE_SLOT_VLEN(vl_tf) <= IE_INLINE_BYTES) ? g : NONE16;
-    carry_v = q3;
+    carry_v = tail_val;
     g = parent;
   }
 }
@@ -679,17 +689,28 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv_ti
     }
 #else
     if (!too_big) {
-        for (uint32_t cb = tid; cb < n_chunks; cb += NT * P1_BATCH) {
+        // (the loop runs per warp, not per lane: the byte before a chunk comes from the neighbouring lane's chunk by
+        // shuffle - a byte load per chunk cost as many L1 tag requests as the chunk loads themselves - and only lane 0
+        // reads its predecessor from memory)
+        for (uint32_t cw = tid & ~31u; cw < n_chunks; cw += NT * P1_BATCH) {
+            const uint32_t cb = cw + lane;
             uint4 v[P1_BATCH];
             uint32_t pv[P1_BATCH];
 #pragma unroll
             for (int u = 0; u < P1_BATCH; ++u) {
                 const uint32_t c = cb + u * NT;
+                v[u] = make_uint4(0, 0, 0, 0);
+                pv[u] = 0;
                 if (c < n_chunks) {
                     v[u] = __ldg(reinterpret_cast<const uint4*>(a0 + (size_t)c * 16));
                     const int32_t p0 = (int32_t)(c * 16) - (int32_t)lead;
-                    pv[u] = p0 > 0 ? __ldg(tp + p0 - 1) : 0u;  // the byte before the chunk (flat stream)
+                    if (lane == 0 && p0 > 0) pv[u] = __ldg(tp + p0 - 1);  // the byte before the chunk (flat stream)
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < P1_BATCH; ++u) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, v[u].w >> 24, 1);
+                if (lane) pv[u] = up;
             }
 #pragma unroll
             for (int u = 0; u < P1_BATCH; ++u) {
@@ -1072,17 +1093,32 @@ __device__ __forceinline__ bool resolve_range(Smem& sm, const IeTableView& tv_ti
         uint32_t sidx = j ? j - 1 : 0;
         if (j == total_seg) { while (sm.u.seg.out[sidx] > xb) --sidx; }
         uint32_t so = sm.u.seg.out[sidx], se = sm.u.seg.out[sidx + 1];
+        // The pieces' bytes land at their place in the chunk through virtual source addresses (load16_range).  The first two
+        // pieces (a boundary chunk nearly always has exactly two) are set up together so that their loads are in flight
+        // together; a chunk that spans more segments takes the loop.
         uint4 acc = make_uint4(0, 0, 0, 0);
         uint32_t x = xb;
-        for (;;) {
-            // the piece's bytes land at their place in the chunk through a virtual source address (load16_range)
+        {
+            const uint32_t xn1 = min(xe, se);
+            const bool two = xn1 < xe;
+            const uint32_t se2 = two ? sm.u.seg.out[sidx + 2] : se;
+            const uint32_t xn2 = min(xe, se2);
+            const uint8_t* src1 = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + ((int32_t)x0s - (int32_t)so);
+            const uint8_t* src2 = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[two ? sidx + 1 : sidx]) + ((int32_t)x0s - (int32_t)se);
+            const uint4 v1 = load16_range(sm.lowmask, src1, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn1 - x0s));
+            uint4 v2 = make_uint4(0, 0, 0, 0);
+            if (two) v2 = load16_range(sm.lowmask, src2, (uint32_t)((int32_t)xn1 - x0s), (uint32_t)((int32_t)xn2 - x0s));
+            acc.x = v1.x | v2.x; acc.y = v1.y | v2.y; acc.z = v1.z | v2.z; acc.w = v1.w | v2.w;
+            x = two ? xn2 : xn1;
+            if (two) { ++sidx; so = se; se = se2; }
+        }
+        while (x < xe) {
+            ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
             const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + ((int32_t)x0s - (int32_t)so);
             const uint32_t xn = min(xe, se);
             const uint4 v = load16_range(sm.lowmask, src, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn - x0s));
             acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
             x = xn;
-            if (x >= xe) break;
-            ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
         }
         if (xe - xb == 16) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
         else {
