@@ -93,6 +93,11 @@ cudaError_t ie_launch_resolve_tiles(const IeTableView* d_views, uint32_t n_state
                                     const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, const IeRound& rd,
                                     cudaStream_t stream);
 
+// The fused single-pass tile kernel (ie_resolve_fused.cu): launches without rescan rounds on full-size tiles.
+cudaError_t ie_launch_resolve_fused(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
+                                    uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
+                                    const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream);
+
 // The same kernel compiled with 32-template tiles / 64-thread CTAs (ie_resolve_tile.cu with IE_TILE_SMALL): used when
 // every snapshot brings at most IE_SMALL_TILE templates, tt <= IE_SMALL_TILE.
 #define IE_SMALL_TILE 32u

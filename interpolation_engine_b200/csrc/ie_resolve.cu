@@ -462,6 +462,10 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     const bool small_tiles = n_states > 1 && n <= IE_SMALL_TILE;
     if (small_tiles) err = ie_launch_resolve_tiles_small(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                                          d_info, out_bias, tt < IE_SMALL_TILE ? tt : IE_SMALL_TILE, rd, stream);
+#ifndef IE_NO_FUSED
+    else if (!rescan_rounds) err = ie_launch_resolve_fused(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+                                                           d_info, out_bias, tt, stream);
+#endif
     else err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
                                        out_bias, tt, rd, stream);
     if (err != cudaSuccess) return err;
