@@ -600,7 +600,7 @@ static ie_status_t resolve_device(ie_engine* e, const ie_table* t, const uint8_t
     ie_status_t st = prepare_workspace(e, n * t->n_states, tcap, true, &ws, 0, rounds != 0);
     if (st != IE_OK) return st;
     CU(ie_launch_resolve(t->d_views, t->n_states, d_tmpl, d_tmpl_offs, n, d_out, out_capacity, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,
-                         max_exp, tcap, out_bias, tt, rounds, s));
+                         max_exp, tcap, out_bias, tt, rounds, t->bytes, s));
     return IE_OK;
 }
 

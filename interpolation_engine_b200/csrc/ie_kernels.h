@@ -46,11 +46,11 @@ struct IeWorkspace {
 };
 
 // Resolves the n templates against each of the n_states packed snapshots (d_views[s], device array): result
-// index = s * n + template; every output array holds n_states * n entries.
+// index = s * n + template; every output array holds n_states * n entries.  table_bytes = size of the table allocation.
 cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, cudaStream_t stream);
+                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, uint64_t table_bytes, cudaStream_t stream);
 
 cudaError_t ie_launch_general_escalate(const IeTableView* d_views, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                        uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,

@@ -447,7 +447,7 @@ cudaError_t ie_launch_lookup(const IeTableView& tv, const uint8_t* d_keys, const
 cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                               uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                               const IeWorkspace& ws, ie_batch_info* d_info, uint32_t max_expansions, uint32_t tcap,
-                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, cudaStream_t stream) {
+                              uint64_t out_bias, uint32_t tt, uint32_t rescan_rounds, uint64_t table_bytes, cudaStream_t stream) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(ws.zero_base, 0, ws.zero_bytes, stream)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(ie_batch_info), stream)) != cudaSuccess) return err;
@@ -463,7 +463,8 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if (small_tiles) err = ie_launch_resolve_tiles_small(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                                          d_info, out_bias, tt < IE_SMALL_TILE ? tt : IE_SMALL_TILE, rd, stream);
 #ifndef IE_NO_FUSED
-    else if (!rescan_rounds) err = ie_launch_resolve_fused(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
+    else if (!rescan_rounds && table_bytes < (1ull << 35))  // (its segment table keeps value references in 31 bits of 16-byte units)
+        err = ie_launch_resolve_fused(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                                            d_info, out_bias, tt, stream);
 #endif
     else err = ie_launch_resolve_tiles(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws, d_info,

@@ -46,18 +46,27 @@ using namespace ie_tile;
 constexpr int TT = 128;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
 constexpr int NT = 128;  // threads per CTA: one per template
 #ifndef IE_F_CTAS
-#define IE_F_CTAS 7
+#define IE_F_CTAS 8
 #endif
 #ifndef IE_F_SEGS
 #define IE_F_SEGS 8
 #endif
+#ifndef IE_F_P1_BATCH
+#define IE_F_P1_BATCH 4
+#endif
+constexpr int F_P1_BATCH = IE_F_P1_BATCH;  // chunk loads in flight per thread in P1
 constexpr int F_SEGS = IE_F_SEGS;     // copy pieces one template can stage (more: per-thread path)
+#ifndef IE_F_PA_UNROLL
+#define IE_F_PA_UNROLL 2
+#endif
+constexpr int PA_UNROLL = IE_F_PA_UNROLL;  // output chunks per thread and step of the copy sweep's pass A
 constexpr int F_DEPTH = 8;            // nesting depth of the register pass (deeper: per-thread path)
 constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks of template text per tile
 constexpr int S_CAP = F_SEGS * TT;    // copy segments per tile: cannot overflow
 constexpr int C_CAP = 18 * TT;        // 16-byte output chunks with a segment index (288 bytes of output per template)
 constexpr uint32_t CS_EDGE = 0x8000u;  // cs[]: the chunk is not covered by ONE segment (pass B assembles it)
-constexpr uint32_t SEG_VALUE = 0x80000000u;  // staged segment: the source is a value of the table (16-byte units from its base)
+constexpr uint32_t SEG_VALUE = 0x80000000u;  // staged segment (length word): the source is a value of the table (16-byte units from its base)
+constexpr uint32_t SEG_TEXT = 0x80000000u;   // segment table (source word): an offset into the tile's text; the launch keeps tables >= 32 GiB off this kernel
 static_assert(S_CAP < 0x8000, "segment indices share 16 bits with CS_EDGE");
 
 struct SmemF {
@@ -66,14 +75,14 @@ struct SmemF {
         uint32_t cm[M_CAP];  // P1 -> PF: per chunk, bit j = unescaped '{' at byte j, bit 16 + j = '}', both = punt marker
         struct {
             uint32_t out[S_CAP + 2];  // P4 -> P5: tile-local output offset of each segment (+ sentinel)
-            uint64_t src[S_CAP];      //           its source address
+            uint32_t src[S_CAP];      //           its source: a value (16-byte units from the table base) or SEG_TEXT | offset in the tile's text
         } seg;
     } u;
     uint16_t cs[C_CAP + 2];        // segment holding the first byte of each 16-byte aligned output chunk | CS_EDGE
     uint2 stage[F_SEGS * TT];      // PF -> P4: piece k of template t at [k * TT + t]: (source, length | SEG_VALUE)
     uint32_t t_start[TT + 1];      // template start, tile-relative
     uint4 lowmask[17];             // lowmask[k] = the low k bytes of a 16-byte quantity set (load16_range)
-    uint32_t nz[(M_CAP + IE_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds an event
+    uint32_t nz[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds an event
     uint8_t irr[TT];               // templates left to the per-thread path
     uint32_t n_irr;
 };
@@ -173,12 +182,12 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     // ---- P1: flat brace scan (ie_resolve_tile.cu P1) --------------------------------------------------------------
     // Besides the mask of every chunk, ONE bit per chunk says whether it holds any event (a warp scans 32 consecutive
     // chunks per step: the ballot of "mask != 0" is that word); PF jumps from event chunk to event chunk through it.
-    for (uint32_t cw = tid & ~31u; cw < n_chunks; cw += NT * P1_BATCH) {
+    for (uint32_t cw = tid & ~31u; cw < n_chunks; cw += NT * F_P1_BATCH) {
         const uint32_t cb = cw + lane;
-        uint4 v[P1_BATCH];
-        uint32_t pv[P1_BATCH];
+        uint4 v[F_P1_BATCH];
+        uint32_t pv[F_P1_BATCH];
 #pragma unroll
-        for (int u = 0; u < P1_BATCH; ++u) {
+        for (int u = 0; u < F_P1_BATCH; ++u) {
             const uint32_t c = cb + u * NT;
             v[u] = make_uint4(0, 0, 0, 0);
             pv[u] = 0;
@@ -189,12 +198,12 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             }
         }
 #pragma unroll
-        for (int u = 0; u < P1_BATCH; ++u) {
+        for (int u = 0; u < F_P1_BATCH; ++u) {
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, v[u].w >> 24, 1);
             if (lane) pv[u] = up;
         }
 #pragma unroll
-        for (int u = 0; u < P1_BATCH; ++u) {
+        for (int u = 0; u < F_P1_BATCH; ++u) {
             const uint32_t c = cb + u * NT;
             uint32_t mk = 0;
             if (c < n_chunks) {
@@ -419,14 +428,20 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             const uint2 pc = sm.stage[k * TT + tid];
             const uint32_t len = pc.y & ~SEG_VALUE, idx = sbase + k;
             sm.u.seg.out[idx] = off;
-            sm.u.seg.src[idx] = (uint64_t)(uintptr_t)((pc.y & SEG_VALUE) ? tv.base + (size_t)pc.x * 16u : tp + pc.x);
+            sm.u.seg.src[idx] = (pc.y & SEG_VALUE) ? pc.x : (pc.x | SEG_TEXT);
             if (index_chunks) {
                 // every 16-byte aligned output chunk whose first byte lies in this piece points back at it; only the last
                 // of them can reach beyond the piece's end (CS_EDGE: pass B assembles that chunk)
                 const uint32_t lo = off + olead, hi = lo + len;  // the piece in chunk coordinates
-                uint32_t c = (lo + 15) >> 4;
-                for (; (c << 4) + 16 <= hi; ++c) sm.cs[c] = (uint16_t)idx;
-                if ((c << 4) < hi) sm.cs[c] = (uint16_t)(idx | CS_EDGE);
+                // (pieces of C4-like batches span up to seven chunks: eight predicated stores instead of a loop whose trip
+                // count differs from lane to lane; longer pieces finish in the loop)
+                const uint32_t cf = (lo + 15) >> 4, ce = hi >> 4;  // chunks [cf, ce) lie inside the piece
+                uint16_t* row = &sm.cs[cf];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (cf + q < ce) row[q] = (uint16_t)idx;
+                for (uint32_t c = cf + 8; c < ce; ++c) sm.cs[c] = (uint16_t)idx;
+                const uint32_t cl = max(cf, ce);
+                if ((cl << 4) < hi) sm.cs[cl] = (uint16_t)(idx | CS_EDGE);
             }
             off += len;
         }
@@ -459,15 +474,40 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     if (tile_end > out_cap) { if (tid == 0) *ws.overflow = 1u; }
     else if (tile_out) {
         // ---- P5: flat 16-byte output sweep (ie_resolve_tile.cu P5) ------------------------------------------------
+        auto seg_src = [&](uint32_t idx) -> uintptr_t {
+            const uint32_t raw = sm.u.seg.src[idx];
+            return (raw & SEG_TEXT) ? (uintptr_t)tp + (raw & ~SEG_TEXT) : (uintptr_t)tv.base + (uintptr_t)raw * 16u;
+        };
         uint8_t* gout = out + tile_begin;
         const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
         // Pass A: every chunk that lies inside ONE segment: two aligned loads, register selects, one 16-byte store.
         if (index_chunks) {
-            for (uint32_t c = tid; c < o_chunks; c += NT) {
-                const uint32_t sidx = sm.cs[c];
-                if (sidx & CS_EDGE) continue;  // ragged edge of the tile, or a segment ends inside this chunk: pass B
-                const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (c * 16 - olead - sm.u.seg.out[sidx]);
-                *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
+            // (PA_UNROLL chunks per thread and step: their segment lookups first, then all their loads, then the stores)
+            for (uint32_t cb = tid; cb < o_chunks; cb += NT * PA_UNROLL) {
+                uintptr_t sa[PA_UNROLL];
+                bool ok[PA_UNROLL];
+#pragma unroll
+                for (int u = 0; u < PA_UNROLL; ++u) {
+                    const uint32_t c = cb + u * NT;
+                    const uint32_t sidx = c < o_chunks ? sm.cs[c] : CS_EDGE;
+                    ok[u] = !(sidx & CS_EDGE);  // (edge: ragged edge of the tile, or a segment ends inside this chunk: pass B)
+                    sa[u] = 0;
+                    if (ok[u]) sa[u] = seg_src(sidx) + (c * 16 - olead - sm.u.seg.out[sidx]);
+                }
+                uint4 A[PA_UNROLL], B[PA_UNROLL];
+#pragma unroll
+                for (int u = 0; u < PA_UNROLL; ++u) {
+                    A[u] = make_uint4(0, 0, 0, 0); B[u] = A[u];
+                    if (ok[u]) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(sa[u] & ~(uintptr_t)15);
+                        A[u] = __ldg(ap);
+                        if (sa[u] & 15) B[u] = __ldg(ap + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PA_UNROLL; ++u) {
+                    if (ok[u]) *reinterpret_cast<uint4*>(o0 + (size_t)(cb + u * NT) * 16) = align16(A[u], B[u], (uint32_t)(sa[u] & 15));
+                }
             }
         } else {
             for (uint32_t c = tid; c < o_chunks; c += NT) {
@@ -481,7 +521,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 }
                 const uint32_t sidx = lo;
                 if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
-                const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + (xb - sm.u.seg.out[sidx]);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + (xb - sm.u.seg.out[sidx]);
                 *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
             }
         }
@@ -521,8 +561,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 const bool two = xn1 < xe;
                 const uint32_t se2 = two ? sm.u.seg.out[sidx + 2] : se;
                 const uint32_t xn2 = min(xe, se2);
-                const uint8_t* src1 = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + ((int32_t)x0s - (int32_t)so);
-                const uint8_t* src2 = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[two ? sidx + 1 : sidx]) + ((int32_t)x0s - (int32_t)se);
+                const uint8_t* src1 = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + ((int32_t)x0s - (int32_t)so);
+                const uint8_t* src2 = reinterpret_cast<const uint8_t*>(seg_src(two ? sidx + 1 : sidx)) + ((int32_t)x0s - (int32_t)se);
                 const uint4 v1 = load16_range(sm.lowmask, src1, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn1 - x0s));
                 uint4 v2 = make_uint4(0, 0, 0, 0);
                 if (two) v2 = load16_range(sm.lowmask, src2, (uint32_t)((int32_t)xn1 - x0s), (uint32_t)((int32_t)xn2 - x0s));
@@ -532,13 +572,14 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             }
             while (x < xe) {
                 ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
-                const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sm.u.seg.src[sidx]) + ((int32_t)x0s - (int32_t)so);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + ((int32_t)x0s - (int32_t)so);
                 const uint32_t xn = min(xe, se);
                 const uint4 v = load16_range(sm.lowmask, src, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn - x0s));
                 acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
                 x = xn;
             }
-            if (xe - xb == 16) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
+            // (a 16-byte aligned arena: the ragged tail of the tile's last chunk lies in the padding the tile claimed itself)
+            if (xe - xb == 16 || olead == 0) *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = acc;
             else {
                 for (uint32_t p = xb; p < xe; ++p) {
                     const uint32_t q = (uint32_t)((int32_t)p - x0s);

@@ -96,6 +96,15 @@ __device__ __forceinline__ uint4 load16_any(const uint8_t* __restrict__ p, uint3
     const uint32_t sh = (r & 3) * 8;
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
+// The 16 bytes at offset r (0..15) of the 32-byte quantity A | B << 128 (two consecutive aligned loads; B is not looked at
+// when r is 0).
+__device__ __forceinline__ uint4 align16(const uint4& A, const uint4& B, uint32_t r) {
+    uint32_t w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z;
+    if (r & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = B.w; }
+    if (r & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    const uint32_t sh = (r & 3) * 8;
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
 // The 16-byte window at an arbitrary address p, restricted to its bytes [lo, hi) (0 <= lo < hi <= 16): byte j of the
 // result is p[j] inside the range and zero outside.  Only the aligned 16-byte blocks that hold a requested byte are
 // read, so p may be a VIRTUAL address: "where the piece would start if it began at byte 0 of the destination chunk".
