@@ -43,6 +43,10 @@ namespace {
 using namespace ie_dev;
 using namespace ie_tile;
 
+// cache policy of the table probes (random 64-byte slots of a table far larger than L1: no reuse there)
+#ifndef IE_PROBE_HINT
+#define IE_PROBE_HINT ".L1::no_allocate"
+#endif
 constexpr int TT = 128;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
 constexpr int NT = 128;  // threads per CTA: one per template
 #ifndef IE_F_CTAS
@@ -63,7 +67,10 @@ constexpr int PA_UNROLL = IE_F_PA_UNROLL;  // output chunks per thread and step 
 constexpr int F_DEPTH = 8;            // nesting depth of the register pass (deeper: per-thread path)
 constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks of template text per tile
 constexpr int S_CAP = F_SEGS * TT;    // copy segments per tile: cannot overflow
-constexpr int C_CAP = 18 * TT;        // 16-byte output chunks with a segment index (288 bytes of output per template)
+#ifndef IE_F_C_PER
+#define IE_F_C_PER 18
+#endif
+constexpr int C_CAP = IE_F_C_PER * TT;        // 16-byte output chunks with a segment index (288 bytes of output per template)
 constexpr uint32_t CS_EDGE = 0x8000u;  // cs[]: the chunk is not covered by ONE segment (pass B assembles it)
 constexpr uint32_t SEG_VALUE = 0x80000000u;  // staged segment (length word): the source is a value of the table (16-byte units from its base)
 constexpr uint32_t SEG_TEXT = 0x80000000u;   // segment table (source word): an offset into the tile's text; the launch keeps tables >= 32 GiB off this kernel
@@ -333,11 +340,11 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                             do {
                                 // header and inline key come with ONE 256-bit load: one L2 round trip per probe
                                 uint4 q0, q2;
-                                asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                asm volatile("ld.global.nc" IE_PROBE_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                                              : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w)
                                              : "l"(slots + idx));
                                 if (want_tail)
-                                    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                    asm volatile("ld.global.nc" IE_PROBE_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                                                  : "=r"(tail_hdr.x), "=r"(tail_hdr.y), "=r"(tail_hdr.z), "=r"(tail_hdr.w), "=r"(tail_val.x),
                                                    "=r"(tail_val.y), "=r"(tail_val.z), "=r"(tail_val.w)
                                                  : "l"(reinterpret_cast<const uint8_t*>(slots + idx) + 32));
