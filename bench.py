@@ -42,12 +42,12 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tile resolve kernel on this workload, taken
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused tile resolve kernel on this workload, taken
     from the committed ncu capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("ie_resolve_tile_kernel_dram_bytes_per_launch")
+            return json.load(f).get("ie_resolve_fused_kernel_dram_bytes_per_launch")
     return None
 
 
@@ -376,9 +376,9 @@ def main():
                        "l2": "two input/output buffer sets alternated per step; per-step working set %.2f GB > 126 MB L2" % (alg[0] / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks; per-step min/median ms = %.3f/%.3f" % (min(per_step_ms), sorted(per_step_ms)[len(per_step_ms) // 2])},
             "clocks": clocks,
-            "gpu_launches": 3 * args.steps,  # per rank and step: ie_resolve_tile_kernel + the two tiers of ie_resolve_general_kernel (profiles/r01_final_launches.csv)
+            "gpu_launches": 3 * args.steps,  # per rank and step: ie_resolve_fused_kernel + the two tiers of ie_resolve_general_kernel (profiles/r02_final_launches.csv)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "ie_resolve_tile_kernel (+ the two general-tier kernels, empty on this workload, and two small memsets in the same step)",
+                         "kernel": "ie_resolve_fused_kernel (+ the two general-tier kernels, empty on this workload, and two small memsets in the same step)",
                          "algorithmic_bytes_per_launch": alg_mean, "peak_source": peak_src + ", of measured"},
         }
         if e2e:

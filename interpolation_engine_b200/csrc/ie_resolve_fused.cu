@@ -90,6 +90,7 @@ struct SmemF {
     uint32_t t_start[TT + 1];      // template start, tile-relative
     uint4 lowmask[17];             // lowmask[k] = the low k bytes of a 16-byte quantity set (load16_range)
     uint32_t nz[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds an event
+    uint32_t ez[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds a brace escaped by the byte before it
     uint8_t irr[TT];               // templates left to the per-thread path
     uint32_t n_irr;
 };
@@ -188,7 +189,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
 
     // ---- P1: flat brace scan (ie_resolve_tile.cu P1) --------------------------------------------------------------
     // Besides the mask of every chunk, ONE bit per chunk says whether it holds any event (a warp scans 32 consecutive
-    // chunks per step: the ballot of "mask != 0" is that word); PF jumps from event chunk to event chunk through it.
+    // chunks per step: the ballot of "mask != 0" is that word); PF jumps from event chunk to event chunk through it.  A
+    // second bitmap marks the chunks that hold an escaped brace (the first-byte repair of PF looks at text only there).
     for (uint32_t cw = tid & ~31u; cw < n_chunks; cw += NT * F_P1_BATCH) {
         const uint32_t cb = cw + lane;
         uint4 v[F_P1_BATCH];
@@ -212,13 +214,13 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
 #pragma unroll
         for (int u = 0; u < F_P1_BATCH; ++u) {
             const uint32_t c = cb + u * NT;
-            uint32_t mk = 0;
+            uint32_t mk = 0, esc = 0;
             if (c < n_chunks) {
-                mk = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp);
+                mk = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp, &esc);
                 sm.u.cm[c] = mk;
             }
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, mk != 0);
-            if (lane == 0) sm.nz[(cw + u * NT) >> 5] = word;
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, mk != 0), eword = __ballot_sync(0xFFFFFFFFu, esc != 0);
+            if (lane == 0) { sm.nz[(cw + u * NT) >> 5] = word; sm.ez[(cw + u * NT) >> 5] = eword; }
         }
     }
     __syncthreads();
@@ -241,7 +243,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 live = true;
                 // The flat scan took "the previous byte is a backslash" across template boundaries: a template that starts
                 // with a brace right after a template ending in '\\' lost that event -> the general path redoes it.
-                if (start > 0 && __ldg(tp + start - 1) == '\\') {
+                // (only a template whose first chunk holds an escaped brace at all looks at the bytes)
+                if (start > 0 && ((sm.ez[c0 >> 5] >> (c0 & 31)) & 1u) && __ldg(tp + start - 1) == '\\') {
                     const uint8_t b0 = __ldg(tp + start);
                     if (b0 == '{' || b0 == '}') { mode = M_PUNT; live = false; }
                 }

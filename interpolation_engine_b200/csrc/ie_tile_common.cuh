@@ -57,8 +57,9 @@ static __device__ __noinline__ uint32_t scan_chunk_rare(uint32_t w0, uint32_t w1
 // One 16-byte chunk of template text -> 32 bits: bit j = unescaped '{' at byte j, bit 16 + j = unescaped '}', both =
 // punt marker.  `prev` is the byte before the chunk ("previous byte is a backslash" is evaluated on the flat stream;
 // P2 repairs the first byte of each template).
+// `escaped` (optional): set to the chunk's braces that the byte before them escapes (16 bits).
 __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, int32_t p0, uint32_t tile_bytes,
-                                               const uint8_t* __restrict__ tp) {
+                                               const uint8_t* __restrict__ tp, uint32_t* escaped = nullptr) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t O = 0, C = 0, B = 0;
 #pragma unroll
@@ -76,6 +77,7 @@ __device__ __forceinline__ uint32_t scan_chunk(const uint4& v, uint32_t prev, in
     const uint32_t esc = (B << 1) | (prev == '\\' ? 1u : 0u);
     uint32_t m = (O & ~esc) | ((C & ~esc) << 16);
     const uint32_t ec = C & esc;
+    if (escaped) *escaped = (O | C) & esc;
     if (ec | ((w[0] | w[1] | w[2] | w[3]) & 0x80808080u)) m = scan_chunk_rare(w[0], w[1], w[2], w[3], ec, p0, tile_bytes, tp, m);
     return m;
 }
