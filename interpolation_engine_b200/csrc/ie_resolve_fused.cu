@@ -93,10 +93,12 @@ struct SmemF {
     uint32_t ez[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds a brace escaped by the byte before it
     uint8_t irr[TT];               // templates left to the per-thread path
     uint32_t n_irr;
+    uint32_t retry;                // a template outgrew its share of the staging area: the largest range (in templates) that
+                                   // gives it enough, 0xFFFFFFFF = none did
 };
 static_assert(IE_F_CTAS * (sizeof(SmemF) + 1024) <= 196 * 1024, "SmemF outgrew the 196 KB carve-out");
 
-enum : uint32_t { M_SEGS = 0, M_PUNT = 1, M_ERROR = 2, M_IRREGULAR = 3 };
+enum : uint32_t { M_SEGS = 0, M_PUNT = 1, M_ERROR = 2, M_IRREGULAR = 3, M_COUNT = 4 };  // (M_COUNT: inside the register pass only)
 
 // One template on the exact per-thread traversal (ie_device.cuh): sizes, claims its own arena range, writes.
 __device__ __noinline__ void per_thread_one(IeTableView tv, const uint8_t* __restrict__ tmpl, const uint64_t* __restrict__ offs, uint64_t i, uint64_t r,
@@ -150,7 +152,8 @@ __device__ __forceinline__ bool key_append_text(const uint4* __restrict__ lowmas
 }
 
 // Resolves the templates [i0, i0 + nt) of one snapshot as one tile.  Returns false (having written nothing) when the
-// range's text outgrows the chunk-mask table and holds more than one template: the caller retries it in halves.
+// range's text outgrows the chunk-mask table, or one of its templates its share of the staging area, and the range holds
+// more than one template: the caller retries it in halves.
 __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView& tv, uint32_t state, const uint8_t* __restrict__ tmpl,
                                                     const uint64_t* __restrict__ offs, uint64_t n, uint8_t* __restrict__ out, uint64_t out_cap,
                                                     uint64_t* __restrict__ out_offs, uint32_t* __restrict__ out_lens, int32_t* __restrict__ status_out,
@@ -169,7 +172,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     const uint8_t* __restrict__ tp = tmpl + off0;
     const uint64_t tile_bytes64 = off_end - off0;
     sm.t_start[tid] = (uint32_t)(my_off - off0);
-    if (tid == 0) { sm.t_start[TT] = (uint32_t)(off_end - off0); sm.n_irr = 0; }
+    if (tid == 0) { sm.t_start[TT] = (uint32_t)(off_end - off0); sm.n_irr = 0; sm.retry = 0xFFFFFFFFu; }
     if (tid < 17) {
         auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
         sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
@@ -260,9 +263,12 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 }
             }
         }
+        // The staging area is shared out evenly: S_CAP / nt pieces per template (8 for a full tile).  A template that needs
+        // more asks for the range to be retried in halves - 16, 32, ... pieces each - like a range whose text is too long.
+        const uint32_t seg_cap = (uint32_t)S_CAP / nt;
         auto stage_piece = [&](uint32_t src, uint32_t len_kind) -> bool {
-            if (nseg == (uint32_t)F_SEGS) return false;
-            sm.stage[nseg * TT + tid] = make_uint2(src, len_kind);
+            if (nseg == seg_cap) return false;
+            sm.stage[nseg * nt + tid] = make_uint2(src, len_kind);
             ++nseg;
             return true;
         };
@@ -310,10 +316,18 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 const uint32_t kind = (m >> j) & 0x10001u;  // 1 open, 0x10000 close, both: a byte the tile kernels do not interpret
                 if (kind == 0x10001u) { mode = M_PUNT; live = false; break; }
                 const uint32_t pos = c * 16 - lead + j;
+                if (mode == M_COUNT) {
+                    // The template has outgrown its share of the staging area: the rest of the pass only counts the pieces
+                    // it would stage (in `olen`; structure alone bounds them: no lookups), so that the retry can pick its
+                    // range size.
+                    if (kind == 1u) { if (depth == 0 && pos > top_lit) ++olen; ++depth; }
+                    else if (depth) { if (--depth == 0) { ++olen; top_lit = pos + 1; } }
+                    break;
+                }
                 if (kind == 1u) {
                     seen_open = true;
                     if (depth == 0) {
-                        if (pos > top_lit && !stage_piece(top_lit, pos - top_lit)) { mode = M_IRREGULAR; live = false; break; }
+                        if (pos > top_lit && !stage_piece(top_lit, pos - top_lit)) { mode = M_COUNT; olen = nseg + 1; depth = 1; break; }
                         olen += pos - top_lit;
                     } else {
                         if (!(poison & 1u) && !key_append_text(sm.lowmask, tp, lit0, pos, K0, kl0)) { mode = M_IRREGULAR; live = false; break; }
@@ -379,7 +393,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                     const uint32_t vlen = IE_SLOT_VLEN(vl_tf);
                     if (depth == 0) {
                         if (!bad) {
-                            if (vlen && !stage_piece(val_off16, vlen | SEG_VALUE)) { mode = M_IRREGULAR; live = false; break; }
+                            if (vlen && !stage_piece(val_off16, vlen | SEG_VALUE)) { mode = M_COUNT; olen = nseg + 1; top_lit = pos + 1; break; }
                             olen += vlen;
                             if (simple) { status = IE_RES_TYPED | (IE_SLOT_TAG(vl_tf) << 8); aux = tail_hdr.x; }  // the whole template is one group
                         }
@@ -400,6 +414,12 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 }
             } while (0);
         }
+        if (mode == M_COUNT) {
+            const uint32_t need = olen + (end > top_lit ? 1u : 0u);
+            // a range of S_CAP / need templates gives every one of them `need` pieces; more than the whole area: per-thread path
+            if (need <= (uint32_t)S_CAP && nt > 1) atomicMin(&sm.retry, max(1u, (uint32_t)S_CAP / need));
+            mode = M_IRREGULAR;
+        }
         if (active && mode == M_SEGS) {
             if (!seen_open) {  // the loop at interp.rs:54 is never entered (stray '}' stay): verbatim
                 olen = end - start;
@@ -407,14 +427,19 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             } else if (stray || depth != 0) mode = M_PUNT;  // uneven / improper nesting: general path (exact error text, panic)
             else if (err_status) mode = M_ERROR;
             else {
-                if (end > top_lit && !stage_piece(top_lit, end - top_lit)) mode = M_IRREGULAR;
+                if (end > top_lit && !stage_piece(top_lit, end - top_lit)) {
+                    mode = M_IRREGULAR;
+                    if (nseg + 1 <= (uint32_t)S_CAP && nt > 1) atomicMin(&sm.retry, max(1u, (uint32_t)S_CAP / (nseg + 1)));
+                }
                 olen += end - top_lit;
             }
         }
         if (mode != M_SEGS) { olen = 0; nseg = 0; }
-        if (mode == M_PUNT) { status = IE_RES_PUNT; aux = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r; }
-        else if (mode == M_IRREGULAR) sm.irr[atomicAdd(&sm.n_irr, 1u)] = (uint8_t)tid;
     }
+    __syncthreads();
+    if (sm.retry < nt) return false;  // (nothing has left the CTA yet; the caller reads the size hint)
+    if (mode == M_PUNT) { status = IE_RES_PUNT; aux = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r; }
+    else if (mode == M_IRREGULAR) sm.irr[atomicAdd(&sm.n_irr, 1u)] = (uint8_t)tid;
 
     // ---- P4: offsets and the tile's segment table -----------------------------------------------------------------
     // Every tile's output starts 16-byte aligned (totals are rounded up), so the chunk structure of the copy sweep does
@@ -435,7 +460,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     if (!huge && nseg) {
         uint32_t off = loc;
         for (uint32_t k = 0; k < nseg; ++k) {
-            const uint2 pc = sm.stage[k * TT + tid];
+            const uint2 pc = sm.stage[k * nt + tid];
             const uint32_t len = pc.y & ~SEG_VALUE, idx = sbase + k;
             sm.u.seg.out[idx] = off;
             sm.u.seg.src[idx] = (pc.y & SEG_VALUE) ? pc.x : (pc.x | SEG_TEXT);
@@ -625,15 +650,24 @@ __global__ void __launch_bounds__(NT, IE_F_CTAS) ie_resolve_fused_kernel(const I
     if (resolve_range_fused(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias, tiles_per_state, tile_i0,
                             tile_nt))
         return;
-    uint32_t lo = 0, len = (tile_nt + 1) / 2;
+    uint32_t lo = 0, len = tile_nt;
     while (lo < tile_nt) {
+        // a range that came back: half as many templates, or what its densest template asked for; after a range that went
+        // through the size doubles again (the dense template is behind us)
+        __syncthreads();
+        const uint32_t hint = sm.retry;
         __syncthreads();  // the next range re-initialises the shared tile state
-        const uint32_t cur = min(len, tile_nt - lo);
-        if (resolve_range_fused(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias, tiles_per_state,
-                                tile_i0 + lo, cur))
+        len = min((len + 1) / 2, hint);
+        for (;;) {
+            const uint32_t cur = min(len, tile_nt - lo);
+            if (!resolve_range_fused(sm, tv, state, tmpl, offs, n, out, out_cap, out_offs, out_lens, status_out, aux_out, ws, info, out_bias,
+                                     tiles_per_state, tile_i0 + lo, cur))
+                break;
             lo += cur;
-        else
-            len = (cur + 1) / 2;
+            if (lo >= tile_nt) break;
+            len = min(len * 2, tile_nt);
+            __syncthreads();
+        }
     }
 }
 
