@@ -511,19 +511,27 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         // ---- P5: flat 16-byte output sweep (ie_resolve_tile.cu P5) ------------------------------------------------
         auto seg_src = [&](uint32_t idx) -> uintptr_t {
             const uint32_t raw = sm.u.seg.src[idx];
+#ifdef IE_F_DECODE2
+            const bool txt = (int32_t)raw < 0;  // one multiply-add on a selected base and scale
+            return (txt ? (uintptr_t)tp : (uintptr_t)tv.base) + (uint64_t)(raw & ~SEG_TEXT) * (txt ? 1u : 16u);
+#else
             return (raw & SEG_TEXT) ? (uintptr_t)tp + (raw & ~SEG_TEXT) : (uintptr_t)tv.base + (uintptr_t)raw * 16u;
+#endif
         };
         uint8_t* gout = out + tile_begin;
         const uintptr_t o0 = (uintptr_t)gout & ~(uintptr_t)15;
         // Pass A: every chunk that lies inside ONE segment: two aligned loads, register selects, one 16-byte store.
         if (index_chunks) {
-            // (PA_UNROLL chunks per thread and step: their segment lookups first, then all their loads, then the stores)
-            for (uint32_t cb = tid; cb < o_chunks; cb += NT * PA_UNROLL) {
+            // PA_UNROLL chunks per thread and step: their segment lookups first, then all their loads, then the stores.  The
+            // lanes of a warp hold consecutive chunks; where the next lane reads on in the same source (its address is mine
+            // + 16), ITS first block is my second one: it comes by shuffle instead of a second load (the L1 data pipe, not
+            // the issue slots, bounds this kernel; about two in three second loads go away).
+            for (uint32_t cw = tid & ~31u; cw < o_chunks; cw += NT * PA_UNROLL) {
                 uintptr_t sa[PA_UNROLL];
                 bool ok[PA_UNROLL];
 #pragma unroll
                 for (int u = 0; u < PA_UNROLL; ++u) {
-                    const uint32_t c = cb + u * NT;
+                    const uint32_t c = cw + lane + u * NT;
                     const uint32_t sidx = c < o_chunks ? sm.cs[c] : CS_EDGE;
                     ok[u] = !(sidx & CS_EDGE);  // (edge: ragged edge of the tile, or a segment ends inside this chunk: pass B)
                     sa[u] = 0;
@@ -532,16 +540,25 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 uint4 A[PA_UNROLL], B[PA_UNROLL];
 #pragma unroll
                 for (int u = 0; u < PA_UNROLL; ++u) {
-                    A[u] = make_uint4(0, 0, 0, 0); B[u] = A[u];
-                    if (ok[u]) {
-                        const uint4* ap = reinterpret_cast<const uint4*>(sa[u] & ~(uintptr_t)15);
-                        A[u] = __ldg(ap);
-                        if (sa[u] & 15) B[u] = __ldg(ap + 1);
-                    }
+                    A[u] = make_uint4(0, 0, 0, 0);
+                    if (ok[u]) A[u] = __ldg(reinterpret_cast<const uint4*>(sa[u] & ~(uintptr_t)15));
                 }
 #pragma unroll
                 for (int u = 0; u < PA_UNROLL; ++u) {
-                    if (ok[u]) *reinterpret_cast<uint4*>(o0 + (size_t)(cb + u * NT) * 16) = align16(A[u], B[u], (uint32_t)(sa[u] & 15));
+#ifdef IE_F_PA_SHFL
+                    const uint32_t lo_next = __shfl_down_sync(0xFFFFFFFFu, (uint32_t)sa[u], 1), hi_next = __shfl_down_sync(0xFFFFFFFFu, (uint32_t)(sa[u] >> 32), 1);
+                    B[u].x = __shfl_down_sync(0xFFFFFFFFu, A[u].x, 1); B[u].y = __shfl_down_sync(0xFFFFFFFFu, A[u].y, 1);
+                    B[u].z = __shfl_down_sync(0xFFFFFFFFu, A[u].z, 1); B[u].w = __shfl_down_sync(0xFFFFFFFFu, A[u].w, 1);
+                    const bool from_next = lane < 31 && (((uint64_t)hi_next << 32) | lo_next) == (uint64_t)sa[u] + 16;
+                    if (ok[u] && (sa[u] & 15) && !from_next) B[u] = __ldg(reinterpret_cast<const uint4*>(sa[u] & ~(uintptr_t)15) + 1);
+#else
+                    B[u] = make_uint4(0, 0, 0, 0);
+                    if (ok[u] && (sa[u] & 15)) B[u] = __ldg(reinterpret_cast<const uint4*>(sa[u] & ~(uintptr_t)15) + 1);
+#endif
+                }
+#pragma unroll
+                for (int u = 0; u < PA_UNROLL; ++u) {
+                    if (ok[u]) *reinterpret_cast<uint4*>(o0 + (size_t)(cw + lane + u * NT) * 16) = align16(A[u], B[u], (uint32_t)(sa[u] & 15));
                 }
             }
         } else {
