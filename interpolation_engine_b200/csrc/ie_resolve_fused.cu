@@ -65,7 +65,10 @@ constexpr int F_SEGS = IE_F_SEGS;     // copy pieces one template can stage (mor
 #endif
 constexpr int PA_UNROLL = IE_F_PA_UNROLL;  // output chunks per thread and step of the copy sweep's pass A
 constexpr int F_DEPTH = 8;            // nesting depth of the register pass (deeper: per-thread path)
-constexpr int M_CAP = IE_M_PER * TT;  // 16-byte chunks of template text per tile
+#ifndef IE_F_M_PER
+#define IE_F_M_PER IE_M_PER
+#endif
+constexpr int M_CAP = IE_F_M_PER * TT;  // 16-byte chunks of template text per tile (a longer tile is retried in halves)
 constexpr int S_CAP = F_SEGS * TT;    // copy segments per tile: cannot overflow
 #ifndef IE_F_C_PER
 #define IE_F_C_PER 18
@@ -85,12 +88,16 @@ struct SmemF {
             uint32_t src[S_CAP];      //           its source: a value (16-byte units from the table base) or SEG_TEXT | offset in the tile's text
         } seg;
     } u;
-    uint16_t cs[C_CAP + 2];        // segment holding the first byte of each 16-byte aligned output chunk | CS_EDGE
+    union {
+        uint16_t cs[C_CAP + 2];   // P4 -> P5: segment holding the first byte of each 16-byte aligned output chunk | CS_EDGE
+        struct {                  // P0 / P1 -> PF (dead once the scan's barrier has passed):
+            uint32_t t_start[TT + 1];                            // template start, tile-relative
+            uint32_t nz[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // bit c = chunk c holds an event
+            uint32_t ez[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // bit c = chunk c holds a brace escaped by the byte before it
+        } pf;
+    } v;
     uint2 stage[F_SEGS * TT];      // PF -> P4: piece k of template t at [k * TT + t]: (source, length | SEG_VALUE)
-    uint32_t t_start[TT + 1];      // template start, tile-relative
     uint4 lowmask[17];             // lowmask[k] = the low k bytes of a 16-byte quantity set (load16_range)
-    uint32_t nz[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds an event
-    uint32_t ez[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // P1 -> PF: bit c = chunk c holds a brace escaped by the byte before it
     uint8_t irr[TT];               // templates left to the per-thread path
     uint32_t n_irr;
     uint32_t retry;                // a template outgrew its share of the staging area: the largest range (in templates) that
@@ -171,8 +178,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     const uint64_t my_off = active ? __ldg(offs + i) : off_end;
     const uint8_t* __restrict__ tp = tmpl + off0;
     const uint64_t tile_bytes64 = off_end - off0;
-    sm.t_start[tid] = (uint32_t)(my_off - off0);
-    if (tid == 0) { sm.t_start[TT] = (uint32_t)(off_end - off0); sm.n_irr = 0; sm.retry = 0xFFFFFFFFu; }
+    sm.v.pf.t_start[tid] = (uint32_t)(my_off - off0);
+    if (tid == 0) { sm.v.pf.t_start[TT] = (uint32_t)(off_end - off0); sm.n_irr = 0; sm.retry = 0xFFFFFFFFu; }
     if (tid < 17) {
         auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
         sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
@@ -223,7 +230,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 sm.u.cm[c] = mk;
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, mk != 0), eword = __ballot_sync(0xFFFFFFFFu, esc != 0);
-            if (lane == 0) { sm.nz[(cw + u * NT) >> 5] = word; sm.ez[(cw + u * NT) >> 5] = eword; }
+            if (lane == 0) { sm.v.pf.nz[(cw + u * NT) >> 5] = word; sm.v.pf.ez[(cw + u * NT) >> 5] = eword; }
         }
     }
     __syncthreads();
@@ -236,7 +243,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         uint32_t start = 0, end = 0, c0 = 0, c1 = 0, keep_first = 0, keep_last = 0, m0 = 0;
         bool live = false;  // this lane still has events to go through
         if (active) {
-            start = sm.t_start[tid]; end = sm.t_start[tid + 1];
+            start = sm.v.pf.t_start[tid]; end = sm.v.pf.t_start[tid + 1];
             const uint32_t ca = lead + start, cz = lead + end;  // the template's extent in chunk coordinates
             c0 = ca >> 4; c1 = (cz + 15) >> 4;                  // its chunks: [c0, c1)
             // valid bytes of the first / last chunk, replicated into both halves of a mask
@@ -247,7 +254,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 // The flat scan took "the previous byte is a backslash" across template boundaries: a template that starts
                 // with a brace right after a template ending in '\\' lost that event -> the general path redoes it.
                 // (only a template whose first chunk holds an escaped brace at all looks at the bytes)
-                if (start > 0 && ((sm.ez[c0 >> 5] >> (c0 & 31)) & 1u) && __ldg(tp + start - 1) == '\\') {
+                if (start > 0 && ((sm.v.pf.ez[c0 >> 5] >> (c0 & 31)) & 1u) && __ldg(tp + start - 1) == '\\') {
                     const uint8_t b0 = __ldg(tp + start);
                     if (b0 == '{' || b0 == '}') { mode = M_PUNT; live = false; }
                 }
@@ -274,7 +281,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         };
         // event chunks [cwin, cwin + 32) of this template, from the per-chunk bitmap of P1
         auto window = [&](uint32_t cwin) -> uint32_t {
-            uint32_t bits = __funnelshift_r(sm.nz[cwin >> 5], sm.nz[(cwin >> 5) + 1], cwin & 31);
+            uint32_t bits = __funnelshift_r(sm.v.pf.nz[cwin >> 5], sm.v.pf.nz[(cwin >> 5) + 1], cwin & 31);
             if (cwin + 32 > c1) bits &= (1u << (c1 - cwin)) - 1u;
             return bits;
         };
@@ -471,18 +478,18 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 // (pieces of C4-like batches span up to seven chunks: eight predicated stores instead of a loop whose trip
                 // count differs from lane to lane; longer pieces finish in the loop)
                 const uint32_t cf = (lo + 15) >> 4, ce = hi >> 4;  // chunks [cf, ce) lie inside the piece
-                uint16_t* row = &sm.cs[cf];
+                uint16_t* row = &sm.v.cs[cf];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) if (cf + q < ce) row[q] = (uint16_t)idx;
-                for (uint32_t c = cf + 8; c < ce; ++c) sm.cs[c] = (uint16_t)idx;
+                for (uint32_t c = cf + 8; c < ce; ++c) sm.v.cs[c] = (uint16_t)idx;
                 const uint32_t cl = max(cf, ce);
-                if ((cl << 4) < hi) sm.cs[cl] = (uint16_t)(idx | CS_EDGE);
+                if ((cl << 4) < hi) sm.v.cs[cl] = (uint16_t)(idx | CS_EDGE);
             }
             off += len;
         }
     }
     // chunk 0 starts before the tile's first byte unless the tile's output is 16-byte aligned (then the first piece owns it)
-    if (tid == 0) { if (olead) sm.cs[0] = (uint16_t)CS_EDGE; sm.u.seg.out[total_seg] = tile_out; }
+    if (tid == 0) { if (olead) sm.v.cs[0] = (uint16_t)CS_EDGE; sm.u.seg.out[total_seg] = tile_out; }
     // The tile's output range is claimed with one atomic add on the batch's byte counter: tiles land in the arena in
     // completion order (out_offs[] carries every template's position), so no tile ever waits for a predecessor.
     const uint64_t tile_begin = ie_scan::allocate(sm.scan, &info->out_bytes, huge ? 0ull : tile_pad64);  // (its barrier publishes the segment table)
@@ -532,7 +539,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
 #pragma unroll
                 for (int u = 0; u < PA_UNROLL; ++u) {
                     const uint32_t c = cw + lane + u * NT;
-                    const uint32_t sidx = c < o_chunks ? sm.cs[c] : CS_EDGE;
+                    const uint32_t sidx = c < o_chunks ? sm.v.cs[c] : CS_EDGE;
                     ok[u] = !(sidx & CS_EDGE);  // (edge: ragged edge of the tile, or a segment ends inside this chunk: pass B)
                     sa[u] = 0;
                     if (ok[u]) sa[u] = seg_src(sidx) + (c * 16 - olead - sm.u.seg.out[sidx]);
