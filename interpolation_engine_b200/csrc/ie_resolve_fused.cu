@@ -8,17 +8,19 @@
 // masks to copy segments in a single left-to-right pass over its brace events:
 //
 //   P1  flat scan      all lanes stream the tile's bytes as 16-byte coalesced chunks; SIMD-in-register byte compares
-//                      give one 32-bit brace mask per chunk (ie_tile_common.cuh)
-//   PF  resolve        one thread per template, one loop over its events.  The open groups live in REGISTERS: three
-//                      levels of (key so far: 16 bytes, its length, where the next literal piece starts, where the group
-//                      opened).  '{' appends the pending literal piece to the enclosing key (or stages a literal copy
-//                      segment at the top level) and pushes a level; '}' completes the key, hashes it, probes the table
-//                      (one 256-bit load = one L2 round trip), applies the type gate (interp.rs:71-80) and pops: the
-//                      value goes into the parent's key (inline values arrive with the probe) or becomes a copy segment.
-//                      No event arrays, no queue, no atomics; a `{q-{idx-{slot-A}}}` chain is three consecutive
+//                      give one 32-bit brace mask per chunk (ie_tile_common.cuh); two bitmaps by warp ballot: chunks with
+//                      any event, chunks with an escaped brace
+//   PF  resolve        one thread per template, one loop over its events, the lanes of a warp in lockstep.  The innermost
+//                      open group lives in REGISTERS (key so far: 16 bytes, its length, where the next literal piece
+//                      starts, where the group opened), the groups around it on an 8-level per-thread stack in local
+//                      memory.  '{' appends the pending literal piece to the enclosing key (or stages a literal copy
+//                      piece at the top level) and pushes; '}' completes the key, hashes it, probes the table (one
+//                      256-bit load = one L2 round trip), applies the type gate (interp.rs:71-80) and pops: the value
+//                      goes into the parent's key (inline values arrive with the probe) or becomes a copy piece.
+//                      No event arrays, no queue, no shared atomics; a `{q-{idx-{slot-A}}}` chain is three consecutive
 //                      iterations of the same thread, and every lane of a warp runs the same body.
 //   P4  offsets        one CTA scan (bytes + segment counts), one atomic add claims the tile's arena range, the staged
-//                      segments move into the tile's dense segment table (which takes the chunk masks' place)
+//                      pieces move into the tile's dense segment table (which takes the chunk masks' place)
 //   P5  flat copy      all lanes sweep the tile's output range in 16-byte aligned chunks (as in ie_resolve_tile.cu)
 //
 // Exactness: the same argument as ie_resolve_tile.cu — with every spliced value free of unescaped braces and sentinel
@@ -26,10 +28,14 @@
 // failing group with the largest '{' position whose children all succeeded: in close order that is the LAST failing
 // group (a group that closes later and is no ancestor opened later; ancestors of a failed group are never looked up).
 // The failing key is still in registers when the loop ends and is written out from there.
-// What the register pass does not hold — nesting deeper than three levels, a key longer than 16 bytes, more than
-// F_SEGS copy pieces — goes to the exact per-thread traversal of ie_device.cuh at the end of the tile, compacted onto
-// the first lanes; what the tile kernels never interpret (flagged values, uneven braces, sentinel collisions) goes to
-// the general kernel as before.
+// What the register pass does not hold is handed on, exactly:
+//   * a template that needs more copy pieces than its share of the staging area (S_CAP / templates of the range: 8 in a
+//     full tile) counts its pieces and the range comes back to be retried at the size that fits (like a range whose text
+//     outgrows the chunk-mask table);
+//   * nesting deeper than F_DEPTH levels, a key longer than 16 bytes, a template of more than S_CAP pieces: the exact
+//     per-thread traversal of ie_device.cuh at the end of the tile, compacted onto the first lanes;
+//   * what the tile kernels never interpret (flagged values, uneven braces, sentinel collisions): the general kernel.
+// Launches on many snapshots and launches with rescan rounds stay on ie_resolve_tile.cu (ie_resolve.cu picks).
 #include <cuda_runtime.h>
 
 #include "ie_common.cuh"
@@ -59,7 +65,7 @@ constexpr int NT = 128;  // threads per CTA: one per template
 #define IE_F_P1_BATCH 4
 #endif
 constexpr int F_P1_BATCH = IE_F_P1_BATCH;  // chunk loads in flight per thread in P1
-constexpr int F_SEGS = IE_F_SEGS;     // copy pieces one template can stage (more: per-thread path)
+constexpr int F_SEGS = IE_F_SEGS;     // copy pieces per template the staging area holds for a full tile
 #ifndef IE_F_PA_UNROLL
 #define IE_F_PA_UNROLL 2
 #endif
