@@ -49,6 +49,24 @@ namespace {
 using namespace ie_dev;
 using namespace ie_tile;
 
+// -DIE_DEBUG_BOUNDS: every index into a shared-memory table (and into the per-thread group stack) is checked against the
+// table's capacity before it is used; a violation is counted (and the first one recorded) instead of corrupting memory.
+// compute-sanitizer is not available on the GPU pool, this build takes its place: tests/fuzz_campaign.py runs against it
+// unchanged and ie_debug_bound_violations_fused() must stay 0.
+#ifdef IE_DEBUG_BOUNDS
+__device__ unsigned long long g_fused_bound_violations[4];  // count, line, index, capacity of the first one
+__device__ __noinline__ void fused_bound_report(uint32_t i, uint32_t cap, int line) {
+    if (atomicAdd(&g_fused_bound_violations[0], 1ull) == 0) { g_fused_bound_violations[1] = (unsigned long long)line; g_fused_bound_violations[2] = i; g_fused_bound_violations[3] = cap; }
+}
+__device__ __forceinline__ uint32_t fused_bound_check(uint32_t i, uint32_t cap, int line) {
+    if (i >= cap) { fused_bound_report(i, cap, line); return 0u; }
+    return i;
+}
+#define FB(i, cap) fused_bound_check((uint32_t)(i), (uint32_t)(cap), __LINE__)
+#else
+#define FB(i, cap) (i)
+#endif
+
 // cache policy of the table probes (random 64-byte slots of a table far larger than L1: no reuse there)
 #ifndef IE_PROBE_HINT
 #define IE_PROBE_HINT ".L1::no_allocate"
@@ -83,6 +101,7 @@ constexpr int C_CAP = IE_F_C_PER * TT;        // 16-byte output chunks with a se
 constexpr uint32_t CS_EDGE = 0x8000u;  // cs[]: the chunk is not covered by ONE segment (pass B assembles it)
 constexpr uint32_t SEG_VALUE = 0x80000000u;  // staged segment (length word): the source is a value of the table (16-byte units from its base)
 constexpr uint32_t SEG_TEXT = 0x80000000u;   // segment table (source word): an offset into the tile's text; the launch keeps tables >= 32 GiB off this kernel
+constexpr int NZ_WORDS = (M_CAP + IE_F_P1_BATCH * NT) / 32 + 2;  // one bit per chunk a P1 step can touch, + the word a window reads ahead
 static_assert(S_CAP < 0x8000, "segment indices share 16 bits with CS_EDGE");
 
 struct SmemF {
@@ -98,8 +117,8 @@ struct SmemF {
         uint16_t cs[C_CAP + 2];   // P4 -> P5: segment holding the first byte of each 16-byte aligned output chunk | CS_EDGE
         struct {                  // P0 / P1 -> PF (dead once the scan's barrier has passed):
             uint32_t t_start[TT + 1];                            // template start, tile-relative
-            uint32_t nz[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // bit c = chunk c holds an event
-            uint32_t ez[(M_CAP + IE_F_P1_BATCH * NT) / 32 + 2];  // bit c = chunk c holds a brace escaped by the byte before it
+            uint32_t nz[NZ_WORDS];  // bit c = chunk c holds an event
+            uint32_t ez[NZ_WORDS];  // bit c = chunk c holds a brace escaped by the byte before it
         } pf;
     } v;
     uint2 stage[F_SEGS * TT];      // PF -> P4: piece k of template t at [k * TT + t]: (source, length | SEG_VALUE)
@@ -184,8 +203,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     const uint64_t my_off = active ? __ldg(offs + i) : off_end;
     const uint8_t* __restrict__ tp = tmpl + off0;
     const uint64_t tile_bytes64 = off_end - off0;
-    sm.v.pf.t_start[tid] = (uint32_t)(my_off - off0);
-    if (tid == 0) { sm.v.pf.t_start[TT] = (uint32_t)(off_end - off0); sm.n_irr = 0; sm.retry = 0xFFFFFFFFu; }
+    sm.v.pf.t_start[FB(tid, TT + 1)] = (uint32_t)(my_off - off0);
+    if (tid == 0) { sm.v.pf.t_start[FB(TT, TT + 1)] = (uint32_t)(off_end - off0); sm.n_irr = 0; sm.retry = 0xFFFFFFFFu; }
     if (tid < 17) {
         auto low = [](int k) -> uint32_t { return k >= 4 ? 0xFFFFFFFFu : k <= 0 ? 0u : (1u << (8 * k)) - 1u; };
         sm.lowmask[tid] = make_uint4(low((int)tid), low((int)tid - 4), low((int)tid - 8), low((int)tid - 12));
@@ -233,10 +252,10 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             uint32_t mk = 0, esc = 0;
             if (c < n_chunks) {
                 mk = scan_chunk(v[u], pv[u], (int32_t)(c * 16) - (int32_t)lead, tile_bytes, tp, &esc);
-                sm.u.cm[c] = mk;
+                sm.u.cm[FB(c, M_CAP)] = mk;
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, mk != 0), eword = __ballot_sync(0xFFFFFFFFu, esc != 0);
-            if (lane == 0) { sm.v.pf.nz[(cw + u * NT) >> 5] = word; sm.v.pf.ez[(cw + u * NT) >> 5] = eword; }
+            if (lane == 0) { sm.v.pf.nz[FB((cw + u * NT) >> 5, NZ_WORDS)] = word; sm.v.pf.ez[FB((cw + u * NT) >> 5, NZ_WORDS)] = eword; }
         }
     }
     __syncthreads();
@@ -249,7 +268,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         uint32_t start = 0, end = 0, c0 = 0, c1 = 0, keep_first = 0, keep_last = 0, m0 = 0;
         bool live = false;  // this lane still has events to go through
         if (active) {
-            start = sm.v.pf.t_start[tid]; end = sm.v.pf.t_start[tid + 1];
+            start = sm.v.pf.t_start[FB(tid, TT + 1)]; end = sm.v.pf.t_start[FB(tid + 1, TT + 1)];
             const uint32_t ca = lead + start, cz = lead + end;  // the template's extent in chunk coordinates
             c0 = ca >> 4; c1 = (cz + 15) >> 4;                  // its chunks: [c0, c1)
             // valid bytes of the first / last chunk, replicated into both halves of a mask
@@ -260,14 +279,14 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 // The flat scan took "the previous byte is a backslash" across template boundaries: a template that starts
                 // with a brace right after a template ending in '\\' lost that event -> the general path redoes it.
                 // (only a template whose first chunk holds an escaped brace at all looks at the bytes)
-                if (start > 0 && ((sm.v.pf.ez[c0 >> 5] >> (c0 & 31)) & 1u) && __ldg(tp + start - 1) == '\\') {
+                if (start > 0 && ((sm.v.pf.ez[FB(c0 >> 5, NZ_WORDS)] >> (c0 & 31)) & 1u) && __ldg(tp + start - 1) == '\\') {
                     const uint8_t b0 = __ldg(tp + start);
                     if (b0 == '{' || b0 == '}') { mode = M_PUNT; live = false; }
                 }
                 // simple-path layers (interp.rs:45-52): the leading '{' run matched symmetrically by the trailing '}' run.
                 // Group k of the leading run is a simple layer iff k < min(leading, trailing) and it closes at end - 1 - k
                 // (the k bytes behind that close are closes too, so the k groups around it close symmetrically as well).
-                auto ev_at = [&](uint32_t p) -> uint32_t { const uint32_t q = lead + p; return (sm.u.cm[q >> 4] >> (q & 15)) & 0x10001u; };
+                auto ev_at = [&](uint32_t p) -> uint32_t { const uint32_t q = lead + p; return (sm.u.cm[FB(q >> 4, M_CAP)] >> (q & 15)) & 0x10001u; };
                 if (live && ev_at(start) == 1u && ev_at(end - 1) == 0x10000u) {
                     uint32_t ld = 1, tr = 1;
                     while (start + ld < end && ev_at(start + ld) == 1u) ++ld;
@@ -281,13 +300,13 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         const uint32_t seg_cap = (uint32_t)S_CAP / nt;
         auto stage_piece = [&](uint32_t src, uint32_t len_kind) -> bool {
             if (nseg == seg_cap) return false;
-            sm.stage[nseg * nt + tid] = make_uint2(src, len_kind);
+            sm.stage[FB(nseg * nt + tid, F_SEGS * TT)] = make_uint2(src, len_kind);
             ++nseg;
             return true;
         };
         // event chunks [cwin, cwin + 32) of this template, from the per-chunk bitmap of P1
         auto window = [&](uint32_t cwin) -> uint32_t {
-            uint32_t bits = __funnelshift_r(sm.v.pf.nz[cwin >> 5], sm.v.pf.nz[(cwin >> 5) + 1], cwin & 31);
+            uint32_t bits = __funnelshift_r(sm.v.pf.nz[FB(cwin >> 5, NZ_WORDS)], sm.v.pf.nz[FB((cwin >> 5) + 1, NZ_WORDS)], cwin & 31);
             if (cwin + 32 > c1) bits &= (1u << (c1 - cwin)) - 1u;
             return bits;
         };
@@ -315,7 +334,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                     }
                     c = cwin + (uint32_t)__ffs(nzbits) - 1u;
                     nzbits &= nzbits - 1u;
-                    m = sm.u.cm[c];
+                    m = sm.u.cm[FB(c, M_CAP)];
                     if (c == c0) m &= keep_first;  // (the neighbours' events in a shared chunk)
                     if (c + 1 == c1) m &= keep_last;
                     ev = (m | (m >> 16)) & 0xFFFFu;
@@ -345,8 +364,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                     } else {
                         if (!(poison & 1u) && !key_append_text(sm.lowmask, tp, lit0, pos, K0, kl0)) { mode = M_IRREGULAR; live = false; break; }
                         if (depth == (uint32_t)F_DEPTH) { mode = M_IRREGULAR; live = false; break; }
-                        stack_key[depth - 1] = K0;
-                        stack_meta[depth - 1] = kl0 | (op0 << 8);
+                        stack_key[FB(depth - 1, F_DEPTH - 1)] = K0;
+                        stack_meta[FB(depth - 1, F_DEPTH - 1)] = kl0 | (op0 << 8);
                     }
                     K0 = make_uint4(0, 0, 0, 0); kl0 = 0; op0 = pos; lit0 = pos + 1;
                     poison <<= 1;
@@ -412,8 +431,8 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                         }
                         top_lit = pos + 1;
                     } else {
-                        K0 = stack_key[depth - 1];
-                        const uint32_t meta = stack_meta[depth - 1];
+                        K0 = stack_key[FB(depth - 1, F_DEPTH - 1)];
+                        const uint32_t meta = stack_meta[FB(depth - 1, F_DEPTH - 1)];
                         kl0 = meta & 0xFFu; op0 = meta >> 8;
                         if (bad) poison |= 1u;
                         else if (!(poison & 1u)) {
@@ -452,7 +471,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     __syncthreads();
     if (sm.retry < nt) return false;  // (nothing has left the CTA yet; the caller reads the size hint)
     if (mode == M_PUNT) { status = IE_RES_PUNT; aux = 0; ws.general_list[atomicAdd(ws.general_count, 1u)] = (uint32_t)r; }
-    else if (mode == M_IRREGULAR) sm.irr[atomicAdd(&sm.n_irr, 1u)] = (uint8_t)tid;
+    else if (mode == M_IRREGULAR) sm.irr[FB(atomicAdd(&sm.n_irr, 1u), TT)] = (uint8_t)tid;
 
     // ---- P4: offsets and the tile's segment table -----------------------------------------------------------------
     // Every tile's output starts 16-byte aligned (totals are rounded up), so the chunk structure of the copy sweep does
@@ -473,10 +492,10 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     if (!huge && nseg) {
         uint32_t off = loc;
         for (uint32_t k = 0; k < nseg; ++k) {
-            const uint2 pc = sm.stage[k * nt + tid];
+            const uint2 pc = sm.stage[FB(k * nt + tid, F_SEGS * TT)];
             const uint32_t len = pc.y & ~SEG_VALUE, idx = sbase + k;
-            sm.u.seg.out[idx] = off;
-            sm.u.seg.src[idx] = (pc.y & SEG_VALUE) ? pc.x : (pc.x | SEG_TEXT);
+            sm.u.seg.out[FB(idx, S_CAP + 2)] = off;
+            sm.u.seg.src[FB(idx, S_CAP)] = (pc.y & SEG_VALUE) ? pc.x : (pc.x | SEG_TEXT);
             if (index_chunks) {
                 // every 16-byte aligned output chunk whose first byte lies in this piece points back at it; only the last
                 // of them can reach beyond the piece's end (CS_EDGE: pass B assembles that chunk)
@@ -484,18 +503,18 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 // (pieces of C4-like batches span up to seven chunks: eight predicated stores instead of a loop whose trip
                 // count differs from lane to lane; longer pieces finish in the loop)
                 const uint32_t cf = (lo + 15) >> 4, ce = hi >> 4;  // chunks [cf, ce) lie inside the piece
-                uint16_t* row = &sm.v.cs[cf];
+                uint16_t* row = &sm.v.cs[0] + cf;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) if (cf + q < ce) row[q] = (uint16_t)idx;
-                for (uint32_t c = cf + 8; c < ce; ++c) sm.v.cs[c] = (uint16_t)idx;
+                for (int q = 0; q < 8; ++q) if (cf + q < ce) row[FB(cf + q, C_CAP + 2) - cf] = (uint16_t)idx;
+                for (uint32_t c = cf + 8; c < ce; ++c) sm.v.cs[FB(c, C_CAP + 2)] = (uint16_t)idx;
                 const uint32_t cl = max(cf, ce);
-                if ((cl << 4) < hi) sm.v.cs[cl] = (uint16_t)(idx | CS_EDGE);
+                if ((cl << 4) < hi) sm.v.cs[FB(cl, C_CAP + 2)] = (uint16_t)(idx | CS_EDGE);
             }
             off += len;
         }
     }
     // chunk 0 starts before the tile's first byte unless the tile's output is 16-byte aligned (then the first piece owns it)
-    if (tid == 0) { if (olead) sm.v.cs[0] = (uint16_t)CS_EDGE; sm.u.seg.out[total_seg] = tile_out; }
+    if (tid == 0) { if (olead) sm.v.cs[FB(0, C_CAP + 2)] = (uint16_t)CS_EDGE; sm.u.seg.out[FB(total_seg, S_CAP + 2)] = tile_out; }
     // The tile's output range is claimed with one atomic add on the batch's byte counter: tiles land in the arena in
     // completion order (out_offs[] carries every template's position), so no tile ever waits for a predecessor.
     const uint64_t tile_begin = ie_scan::allocate(sm.scan, &info->out_bytes, huge ? 0ull : tile_pad64);  // (its barrier publishes the segment table)
@@ -523,7 +542,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     else if (tile_out) {
         // ---- P5: flat 16-byte output sweep (ie_resolve_tile.cu P5) ------------------------------------------------
         auto seg_src = [&](uint32_t idx) -> uintptr_t {
-            const uint32_t raw = sm.u.seg.src[idx];
+            const uint32_t raw = sm.u.seg.src[FB(idx, S_CAP)];
 #ifdef IE_F_DECODE2
             const bool txt = (int32_t)raw < 0;  // one multiply-add on a selected base and scale
             return (txt ? (uintptr_t)tp : (uintptr_t)tv.base) + (uint64_t)(raw & ~SEG_TEXT) * (txt ? 1u : 16u);
@@ -545,10 +564,10 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
 #pragma unroll
                 for (int u = 0; u < PA_UNROLL; ++u) {
                     const uint32_t c = cw + lane + u * NT;
-                    const uint32_t sidx = c < o_chunks ? sm.v.cs[c] : CS_EDGE;
+                    const uint32_t sidx = c < o_chunks ? sm.v.cs[FB(c, C_CAP + 2)] : CS_EDGE;
                     ok[u] = !(sidx & CS_EDGE);  // (edge: ragged edge of the tile, or a segment ends inside this chunk: pass B)
                     sa[u] = 0;
-                    if (ok[u]) sa[u] = seg_src(sidx) + (c * 16 - olead - sm.u.seg.out[sidx]);
+                    if (ok[u]) sa[u] = seg_src(sidx) + (c * 16 - olead - sm.u.seg.out[FB(sidx, S_CAP + 2)]);
                 }
                 uint4 A[PA_UNROLL], B[PA_UNROLL];
 #pragma unroll
@@ -582,11 +601,11 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 uint32_t lo = 0, hi = total_seg;  // last segment starting at or before xb
                 while (hi - lo > 1) {
                     const uint32_t mid = (lo + hi) >> 1;
-                    if (sm.u.seg.out[mid] <= xb) lo = mid; else hi = mid;
+                    if (sm.u.seg.out[FB(mid, S_CAP + 2)] <= xb) lo = mid; else hi = mid;
                 }
                 const uint32_t sidx = lo;
-                if (sm.u.seg.out[sidx + 1] < xb + 16) continue;  // a segment starts inside this chunk: pass B
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + (xb - sm.u.seg.out[sidx]);
+                if (sm.u.seg.out[FB(sidx + 1, S_CAP + 2)] < xb + 16) continue;  // a segment starts inside this chunk: pass B
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + (xb - sm.u.seg.out[FB(sidx, S_CAP + 2)]);
                 *reinterpret_cast<uint4*>(o0 + (size_t)c * 16) = load16_any(src, 16);
             }
         }
@@ -597,25 +616,25 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             uint32_t c;
             if (j == 0) {
                 c = 0;
-                if (olead == 0 && sm.u.seg.out[1] >= 16 && tile_out >= 16) continue;  // aligned interior chunk: pass A had it
+                if (olead == 0 && sm.u.seg.out[FB(1, S_CAP + 2)] >= 16 && tile_out >= 16) continue;  // aligned interior chunk: pass A had it
             } else if (j == total_seg) {
                 c = o_chunks - 1;
                 const int32_t x0l = (int32_t)(c * 16) - (int32_t)olead;
                 if ((uint32_t)(x0l + 16) <= tile_out) continue;                       // last chunk is full: pass A or a boundary item
-                if (c == 0 || (int32_t)sm.u.seg.out[j - 1] > x0l) continue;           // item 0 or a boundary item owns it
+                if (c == 0 || (int32_t)sm.u.seg.out[FB(j - 1, S_CAP + 2)] > x0l) continue;           // item 0 or a boundary item owns it
             } else {
-                const uint32_t xo = sm.u.seg.out[j];
+                const uint32_t xo = sm.u.seg.out[FB(j, S_CAP + 2)];
                 c = (olead + xo) >> 4;
                 const int32_t x0j = (int32_t)(c * 16) - (int32_t)olead;
                 if (c == 0 || (int32_t)xo == x0j) continue;                            // chunk 0 is item 0's; an aligned start is no boundary
-                if ((int32_t)sm.u.seg.out[j - 1] > x0j) continue;                      // an earlier boundary in the same chunk owns it
+                if ((int32_t)sm.u.seg.out[FB(j - 1, S_CAP + 2)] > x0j) continue;                      // an earlier boundary in the same chunk owns it
             }
             const int32_t x0s = (int32_t)(c * 16) - (int32_t)olead;
             const uint32_t xb = x0s < 0 ? 0u : (uint32_t)x0s;
             const uint32_t xe = min(tile_out, (uint32_t)(x0s + 16));
             uint32_t sidx = j ? j - 1 : 0;
-            if (j == total_seg) { while (sm.u.seg.out[sidx] > xb) --sidx; }
-            uint32_t so = sm.u.seg.out[sidx], se = sm.u.seg.out[sidx + 1];
+            if (j == total_seg) { while (sm.u.seg.out[FB(sidx, S_CAP + 2)] > xb) --sidx; }
+            uint32_t so = sm.u.seg.out[FB(sidx, S_CAP + 2)], se = sm.u.seg.out[FB(sidx + 1, S_CAP + 2)];
             // The pieces' bytes land at their place in the chunk through virtual source addresses (load16_range).  The
             // first two pieces (a boundary chunk nearly always has exactly two) are set up together so that their loads
             // are in flight together; a chunk that spans more segments takes the loop.
@@ -624,7 +643,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
             {
                 const uint32_t xn1 = min(xe, se);
                 const bool two = xn1 < xe;
-                const uint32_t se2 = two ? sm.u.seg.out[sidx + 2] : se;
+                const uint32_t se2 = two ? sm.u.seg.out[FB(sidx + 2, S_CAP + 2)] : se;
                 const uint32_t xn2 = min(xe, se2);
                 const uint8_t* src1 = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + ((int32_t)x0s - (int32_t)so);
                 const uint8_t* src2 = reinterpret_cast<const uint8_t*>(seg_src(two ? sidx + 1 : sidx)) + ((int32_t)x0s - (int32_t)se);
@@ -636,7 +655,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                 if (two) { ++sidx; so = se; se = se2; }
             }
             while (x < xe) {
-                ++sidx; so = se; se = sm.u.seg.out[sidx + 1];
+                ++sidx; so = se; se = sm.u.seg.out[FB(sidx + 1, S_CAP + 2)];
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(seg_src(sidx)) + ((int32_t)x0s - (int32_t)so);
                 const uint32_t xn = min(xe, se);
                 const uint4 v = load16_range(sm.lowmask, src, (uint32_t)((int32_t)x - x0s), (uint32_t)((int32_t)xn - x0s));
@@ -656,7 +675,7 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
     }
     // ---- what the register pass left: the exact per-thread traversal, compacted onto the first lanes ---------------
     if (huge ? (active && (mode == M_SEGS || mode == M_IRREGULAR)) : tid < n_irr) {
-        const uint32_t t = huge ? tid : sm.irr[tid];
+        const uint32_t t = huge ? tid : sm.irr[FB(tid, TT)];
         per_thread_one(tv, tmpl, offs, i0 + t, (uint64_t)state * n + i0 + t, out, out_cap, out_offs, out_lens, status_out, aux_out, ws.general_list,
                        ws.general_count, ws.overflow, info, out_bias);
     }
@@ -711,3 +730,11 @@ cudaError_t ie_launch_resolve_fused(const IeTableView* d_views, uint32_t n_state
                                                                           d_out_lens, d_status, d_aux, ws, d_info, out_bias, tt);
     return cudaGetLastError();
 }
+
+#ifdef IE_DEBUG_BOUNDS
+// out4: violations counted so far, then source line / index / capacity of the first one
+extern "C" int ie_debug_bound_violations_fused(unsigned long long* out4) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out4, g_fused_bound_violations, sizeof(unsigned long long) * 4) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -359,7 +359,7 @@ def main():
         n_done += deep_and_mutate(eng, oracle, seed, bad)
         seed += 1
     print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - first_seed, len(bad)))
-    for name in ("ie_debug_bound_violations", "ie_debug_bound_violations_small"):
+    for name in ("ie_debug_bound_violations", "ie_debug_bound_violations_small", "ie_debug_bound_violations_fused"):
         if hasattr(eng.lib, name):  # IE_DEBUG_BOUNDS build: every tile-table index was checked against its capacity
             import ctypes
             v = (ctypes.c_ulonglong * 4)()
