@@ -71,10 +71,13 @@ __device__ __forceinline__ uint32_t fused_bound_check(uint32_t i, uint32_t cap, 
 #ifndef IE_PROBE_HINT
 #define IE_PROBE_HINT ".L1::no_allocate"
 #endif
-constexpr int TT = 128;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
-constexpr int NT = 128;  // threads per CTA: one per template
+#ifndef IE_F_TT
+#define IE_F_TT 128
+#endif
+constexpr int TT = IE_F_TT;  // templates per tile at most (the launch picks tt <= TT from the mean template length)
+constexpr int NT = IE_F_TT;  // threads per CTA: one per template
 #ifndef IE_F_CTAS
-#define IE_F_CTAS 8
+#define IE_F_CTAS (1024 / IE_F_TT)
 #endif
 #ifndef IE_F_SEGS
 #define IE_F_SEGS 8
@@ -725,6 +728,8 @@ __global__ void __launch_bounds__(NT, IE_F_CTAS) ie_resolve_fused_kernel(const I
 cudaError_t ie_launch_resolve_fused(const IeTableView* d_views, uint32_t n_states, const uint8_t* d_tmpl, const uint64_t* d_offs, uint64_t n, uint8_t* d_out,
                                     uint64_t out_cap, uint64_t* d_out_offs, uint32_t* d_out_lens, int32_t* d_status, uint32_t* d_aux,
                                     const IeWorkspace& ws, ie_batch_info* d_info, uint64_t out_bias, uint32_t tt, cudaStream_t stream) {
+    if (TT > IE_RESOLVE_TILE && tt == IE_RESOLVE_TILE) tt = TT;  // (experiment builds with larger / smaller tiles)
+    if (tt > (uint32_t)TT) tt = TT;
     const uint64_t tiles = (n + tt - 1) / tt;
     ie_resolve_fused_kernel<<<(unsigned)(tiles * n_states), NT, 0, stream>>>(d_views, (uint32_t)tiles, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs,
                                                                           d_out_lens, d_status, d_aux, ws, d_info, out_bias, tt);
