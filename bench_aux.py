@@ -169,7 +169,7 @@ def bench_c3(eng, ie, workloads, torch, dev, orc):
                                        "device_build_kernels_ms": table.build_ms,
                                        "note": "ie_table_pack_many = upload of the raw packed arrays + build kernels on the device (hash, claim, classify, copy)"}},
             "roofline": {"bound": "hbm", "achieved": alg / (r.kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (r.kernel_ms * 1e-3) / 1e9 / peak,
-                         "traffic": None, "kernel": "ie_resolve_tile_kernel", "algorithmic_bytes_per_launch": alg,
+                         "traffic": None, "kernel": "ie_resolve_fused_kernel", "algorithmic_bytes_per_launch": alg,
                          "note": "template text counted once per state although it is L2-resident after the first", "peak_source": src + ", of measured"},
             "e2e": {"value": n / e2e_s, "unit": "strings/s", "ms_per_step": e2e_s * 1e3, "with_table_build": n / (e2e_s + table.pack_call_s),
                     "h2d_bytes_per_step": int(arena.bytes.nbytes + arena.offs.nbytes), "d2h_bytes_per_step": int(r.lens.sum()) + 20 * n,

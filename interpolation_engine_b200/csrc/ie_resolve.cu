@@ -463,12 +463,9 @@ cudaError_t ie_launch_resolve(const IeTableView* d_views, uint32_t n_states, con
     if (small_tiles) err = ie_launch_resolve_tiles_small(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                                          d_info, out_bias, tt < IE_SMALL_TILE ? tt : IE_SMALL_TILE, rd, stream);
 #ifndef IE_NO_FUSED
-    // The fused single-pass kernel takes the launches it is built for: one snapshot (full tiles), no rescan rounds, a table
-    // whose value references fit 31 bits of 16-byte units.  Keys longer than 16 bytes, nesting deeper than eight levels and
-    // templates of more than eight copy pieces leave it for a serial per-thread path, which the cloned-states shape (many
-    // snapshots x a few hundred short templates: C3, where a long key sits in every tile) would pay in every tile: those
-    // launches stay on the phase-wise kernel (measured: 0.70 ms against 1.74 ms for C3's 4.0 M pairs).
-    else if (!rescan_rounds && n_states == 1 && table_bytes < (1ull << 35))
+    // The fused single-pass kernel takes every launch without rescan rounds (the rounds' splice bookkeeping lives in the
+    // phase-wise kernel) on a table whose value references fit 31 bits of 16-byte units.
+    else if (!rescan_rounds && table_bytes < (1ull << 35))
         err = ie_launch_resolve_fused(d_views, n_states, d_tmpl, d_offs, n, d_out, out_cap, d_out_offs, d_out_lens, d_status, d_aux, ws,
                                                            d_info, out_bias, tt, stream);
 #endif

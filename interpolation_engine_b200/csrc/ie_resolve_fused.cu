@@ -32,10 +32,13 @@
 //   * a template that needs more copy pieces than its share of the staging area (S_CAP / templates of the range: 8 in a
 //     full tile) counts its pieces and the range comes back to be retried at the size that fits (like a range whose text
 //     outgrows the chunk-mask table);
-//   * nesting deeper than F_DEPTH levels, a key longer than 16 bytes, a template of more than S_CAP pieces: the exact
-//     per-thread traversal of ie_device.cuh at the end of the tile, compacted onto the first lanes;
+//   * a literal key of more than 16 bytes (no group inside it) is hashed and compared from the tile's text by the byte-wise
+//     lookup of ie_device.cuh, in place (its lanes' neighbours wait for it: a long key costs its warp about 1.5 us);
+//   * nesting deeper than F_DEPTH levels, a key of more than 16 bytes ASSEMBLED from pieces, a template of more than S_CAP
+//     pieces: the exact per-thread traversal of ie_device.cuh at the end of the tile, compacted onto the first lanes;
 //   * what the tile kernels never interpret (flagged values, uneven braces, sentinel collisions): the general kernel.
-// Launches on many snapshots and launches with rescan rounds stay on ie_resolve_tile.cu (ie_resolve.cu picks).
+// Launches with rescan rounds (and the 32-template tiles of many snapshots x a handful of templates) stay on
+// ie_resolve_tile.cu (ie_resolve.cu picks).
 #include <cuda_runtime.h>
 
 #include "ie_common.cuh"
@@ -171,6 +174,17 @@ __device__ __noinline__ void per_thread_tile(IeTableView tv, const uint8_t* __re
     if (threadIdx.x < nt)
         per_thread_one(tv, tmpl, offs, i0 + threadIdx.x, r0 + threadIdx.x, out, out_cap, out_offs, out_lens, status_out, aux_out, general_list, general_count,
                        overflow, info, out_bias);
+}
+
+// A literal key longer than 16 bytes (no group inside it): hashed and compared from memory by the byte-wise lookup of
+// ie_device.cuh, out of line - the register pass pays for it only where such a key occurs.  Returns the slot index, or
+// LONG_MISS / LONG_MISS_ARG (interp.rs:109-116, :136).
+constexpr uint32_t LONG_MISS = 0xFFFFFFFFu, LONG_MISS_ARG = 0xFFFFFFFEu;
+__device__ __forceinline__ uint32_t lookup_long_key(const uint8_t* base, uint32_t mask, const uint8_t* __restrict__ key, uint32_t len) {
+    const IeTableView tv{base, mask, 0u};
+    const IeSlot* s = ie_lookup(tv, key, len);
+    if (s) return (uint32_t)(s - reinterpret_cast<const IeSlot*>(base));
+    return is_arg_key(key, len) ? LONG_MISS_ARG : LONG_MISS;
 }
 
 // The literal piece [from, to) of the tile's text appended to a key held in registers.  False: the key outgrows 16 bytes.
@@ -381,9 +395,21 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                     const uint32_t layer = op0 - start;
                     const bool simple = layer < m0 && pos == end - 1 - layer;
                     if (!(poison & 1u)) {
-                        if (!key_append_text(sm.lowmask, tp, lit0, pos, K0, kl0)) { mode = M_IRREGULAR; live = false; break; }
                         uint32_t err = 0;
-                        if (kl0 == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
+                        const bool long_key = kl0 == 0 && pos - lit0 > 16;  // a literal key that does not fit the register quad
+                        if (long_key) {
+                            const uint32_t si = lookup_long_key(tv.base, tv.mask, tp + lit0, pos - lit0);
+                            if (si >= LONG_MISS_ARG) err = si == LONG_MISS_ARG ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
+                            else {
+                                const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(slots + si));
+                                vl_tf = q0.z; val_off16 = q0.w;
+                                if (depth > 1 || simple) {
+                                    tail_hdr = __ldg(reinterpret_cast<const uint4*>(slots + si) + 2);
+                                    tail_val = __ldg(reinterpret_cast<const uint4*>(slots + si) + 3);
+                                }
+                            }
+                        } else if (!key_append_text(sm.lowmask, tp, lit0, pos, K0, kl0)) { mode = M_IRREGULAR; live = false; break; }
+                        else if (kl0 == 0) err = IE_RES_EMPTY_KEY;  // interp.rs:105
                         else {
                             const uint32_t h = hash_short(K0, kl0);
                             uint32_t idx = h & tv.mask;
@@ -414,12 +440,14 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
                                 }
                                 err = arg ? IE_RES_ARG_MISSING : IE_RES_NOT_FOUND;
                                 vl_tf = 0;
-                            } else if (!simple) {
-                                if (!tag_splices(IE_SLOT_TAG(vl_tf))) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
-                                else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) { mode = M_PUNT; live = false; break; }  // interp.rs:81-83 would rescan it
                             }
                         }
-                        if (err) { fail = true; EK = K0; ekl = kl0; err_status = err; }
+                        if (!err && !simple) {
+                            if (!tag_splices(IE_SLOT_TAG(vl_tf))) err = IE_RES_UNSUPPORTED;  // interp.rs:71-80
+                            else if (IE_SLOT_FLAGS(vl_tf) & IE_VF_ANY) { mode = M_PUNT; live = false; break; }  // interp.rs:81-83 would rescan it
+                        }
+                        // the failing key: the register quad, or (a long literal key) where it stands in the tile's text
+                        if (err) { fail = true; err_status = err; if (long_key) { EK.x = lit0; ekl = pos - lit0; } else { EK = K0; ekl = kl0; } }
                     }
                     // pop
                     const bool bad = fail || (poison & 1u);
@@ -527,12 +555,15 @@ __device__ __forceinline__ bool resolve_range_fused(SmemF& sm, const IeTableView
         out_offs[r] = tile_begin + loc + out_bias; out_lens[r] = olen; status_out[r] = (int32_t)status; aux_out[r] = aux;
     }
     if (active && mode == M_ERROR) {
-        // the failing key goes out from the registers it was assembled in, into a range of its own
+        // the failing key goes out from the registers it was assembled in (a long literal key: from the tile's text), into a
+        // range of its own
         uint64_t off = 0;
-        if (ekl) off = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), 16ull);
+        const uint32_t claim = (ekl + 15u) & ~15u;
+        if (ekl) off = atomicAdd(reinterpret_cast<unsigned long long*>(&info->out_bytes), (unsigned long long)claim);
         out_offs[r] = off + out_bias; out_lens[r] = ekl; status_out[r] = (int32_t)err_status; aux_out[r] = 0;
         if (ekl) {
-            if (off + 16 > out_cap) *ws.overflow = 1u;
+            if (off + claim > out_cap) *ws.overflow = 1u;
+            else if (ekl > 16) { for (uint32_t q = 0; q < ekl; ++q) out[off + q] = __ldg(tp + EK.x + q); }
             else if (((uintptr_t)(out + off) & 15) == 0) *reinterpret_cast<uint4*>(out + off) = EK;
             else for (uint32_t q = 0; q < ekl; ++q) {
                 const uint32_t wq = q < 4 ? EK.x : q < 8 ? EK.y : q < 12 ? EK.z : EK.w;

@@ -323,8 +323,16 @@ def main():
     seed = first_seed = int(argv[1]) if len(argv) > 1 else 1
     eng, oracle = ie.Engine(0), oracle_lib.load()
     t_end, n_done, bad = time.time() + seconds, 0, []
+    leg_s = {}  # seconds per leg (printed at the end: a leg that suddenly dominates is a performance cliff)
+
+    def timed(name, fn, *a, **kw):
+        t0 = time.time()
+        r = fn(*a, **kw)
+        leg_s[name] = leg_s.get(name, 0.0) + time.time() - t0
+        return r
     mirror_only = "--mirror-only" in sys.argv   # only the JSON-level leg (cheap per check: for volume there)
     while time.time() < t_end and len(bad) < 20:
+        t_batch = time.time()
         ins, templates = batch(seed) if seed % 3 else big_table_batch(seed)
         if mirror_only:
             n_done += host_mirror(eng, oracle, seed, ins, templates, bad, rounds=200)
@@ -353,12 +361,16 @@ def main():
                     aux, bad)
             for b in (d_t, d_o) + bufs:
                 b.free()
-        n_done += len(templates) * 5 + glob_and_escape(eng, oracle, seed, templates, bad)
-        n_done += many_states(eng, oracle, seed, ins, templates, bad)
-        n_done += host_mirror(eng, oracle, seed, ins, templates, bad)
-        n_done += deep_and_mutate(eng, oracle, seed, bad)
+        leg_s["resolve"] = leg_s.get("resolve", 0.0) + time.time() - t_batch
+        n_done += len(templates) * 5 + timed("glob_and_escape", glob_and_escape, eng, oracle, seed, templates, bad)
+        n_done += timed("many_states", many_states, eng, oracle, seed, ins, templates, bad)
+        n_done += timed("host_mirror", host_mirror, eng, oracle, seed, ins, templates, bad)
+        n_done += timed("deep_and_mutate", deep_and_mutate, eng, oracle, seed, bad)
+        if "--progress" in sys.argv:
+            print("seed %d done at %.1f s: %s" % (seed, time.time() - (t_end - seconds), ", ".join("%s %.1f" % kv for kv in sorted(leg_s.items()))), flush=True)
         seed += 1
     print("fuzz campaign: %d results compared over %d batches, %d mismatches" % (n_done, seed - first_seed, len(bad)))
+    print("seconds per leg: " + ", ".join("%s %.1f" % kv for kv in sorted(leg_s.items())))
     for name in ("ie_debug_bound_violations", "ie_debug_bound_violations_small", "ie_debug_bound_violations_fused"):
         if hasattr(eng.lib, name):  # IE_DEBUG_BOUNDS build: every tile-table index was checked against its capacity
             import ctypes

@@ -454,10 +454,13 @@ def test_fused_kernel_edges(eng, oracle):
         chain[name + str(d + 1)] = str(d + 2)   # {h{i}} -> h1 -> 2, {g{h{i}}} -> g2 -> 3, ...
     ins = {"a": "A", "e": "", "n": 5, "flag": True, "nil": None, "obj": {"k": 1}, "arr": [1, "x"], "k": "a", "kk": "k",
            "x" * 16: "sixteen", "y" * 17: "seventeen", "z" * 33: "thirtythree", "pre-A-suffix-0016": "c16", "pre-A-suffix-00017": "c17",
-           "brace": "has {a} inside", "bs": "ends with " + BS, "quirk": "." + BS + "}", "v113": "v" * 113, **chain}
+           "brace": "has {a} inside", "a_long_key_with_braces_": "v {a} v", "a_long_boolean_key_012": True, "a_long_number_key_0123": 42, "pre-seventeen": "P17",
+           "bs": "ends with " + BS, "quirk": "." + BS + "}", "v113": "v" * 113, **chain}
     nest = lambda depth: "".join("{" + c for c in "XYZabcdefgh"[11 - depth:]) + "{i}" + "}" * depth
     cases = [nest(d) for d in range(0, 12)] + ["x " + nest(d) + " y" for d in range(0, 12)] + [
         "{" + "x" * 16 + "}", "{" + "y" * 17 + "}", "{" + "z" * 33 + "}", "{" + "x" * 15 + "}", "{" + "q" * 17 + "}", "{" + "q" * 40 + "} tail",
+        "{ARG12345678901234567}", "x{ARG1234567890123456x}", "{pre-{" + "y" * 17 + "}}", "{missing-{" + "y" * 17 + "}}", "x {a_long_boolean_key_012} y", "{a_long_boolean_key_012}",
+        "{a_long_number_key_0123}", "n={a_long_number_key_0123}", "{a_long_key_with_braces_}", "x {a_long_key_with_braces_}", "{{" + "y" * 17 + "}}", "{" + "w" * 200 + "}",
         "{pre-{a}-suffix-0016}", "{pre-{a}-suffix-00017}", "{pre-{a}-suffix-000018}", "lit {pre-{a}-suffix-0016} lit {" + "y" * 17 + "} lit",
         "{a} x " * 4, "{a} x " * 5, "{a}" * 9, "{a} x " * 40, "w {a} " * 200, "{e}{e}{e}{e}{e}{e}{e}{e}{e}{e}", "{e}",
         "{missing}", "{a} {missing}", "{missing1} {a} {missing2}", "{m1{missing}} {a}", "{a{missing}} {missing-too}", "{k{missing}}x{alsomissing}",
